@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the mclSTExp retrieval hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg3|cfg1] [--impl reference]
+
+A "step" is one pass of the fold-loop body of the reference (evel_her2st.py:174-187:
+find_matches + top-k weighted expression average) over one synthetic batch:
+N bank spots x Q query spots, 256-d embeddings, top-50, 1000 HVGs.  The default
+workload is BASELINE.json configs[3] ("cfg4": 1M-spot bank x 64k queries), the
+configuration the north-star target is quoted on; it fits one B200.
+
+One JSON line is printed by rank 0:
+  value   = query spots / s with every input resident in HBM (CUDA events, max over ranks)
+  e2e     = the same through the public host-array API (retrieval.retrieve): pinned-host
+            inputs copied H2D and results read back D2H inside the timed region
+  roofline= dominant kernel, algorithmic FLOPs or bytes / its CUDA-event time (live)
+  cpu_baseline = the oracle's restatement of the reference path (torch CPU + NumPy, the
+            reference's own libraries) on a bounded query sample, host cores of this box
+  extra   = contrastive-loss steps/s (second half of the BASELINE metric) when available
+
+`--impl reference` times that CPU path alone (all host threads) and prints the same line
+with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from mclstexp_b200 import synth  # noqa: E402
+
+METRIC = "retrieval query spots/sec (cosine top-k + weighted expression average)"
+UNIT = "query spots/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"],
+                    source="MEASURED_PEAKS.json (measured)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="B200_PROFILING.md fallback")
+
+
+# --------------------------------------------------------------------------- inputs
+def make_inputs_device(cfg, seed, device, flavour="clustered"):
+    """Seeded synthetic inputs generated on the device (big configs); same recipe as
+    mclstexp_b200.synth."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    N, Q, D, G = cfg["N"], cfg["Q"], cfg["D"], cfg["G"]
+
+    def emb(rows, centres):
+        if flavour == "iid":
+            return torch.randn(rows, D, generator=g, device=device)
+        which = torch.randint(0, centres.shape[0], (rows,), generator=g, device=device)
+        x = centres[which] + torch.randn(rows, D, generator=g, device=device)
+        x = x - x.mean(1, keepdim=True)
+        return x / (x.std(1, keepdim=True, unbiased=False) + 1e-6)
+
+    centres = 4.0 * torch.randn(64, D, generator=g, device=device)
+    bank = emb(N, centres)
+    qry = emb(Q, centres)
+    expr = torch.empty(N, G, device=device)
+    step = 1 << 16
+    for r0 in range(0, N, step):
+        r1 = min(N, r0 + step)
+        # Gamma(0.5, 2) == chi-square(1) * 1.0 -> (randn^2)
+        lam = torch.randn(r1 - r0, G, generator=g, device=device).square_()
+        cnt = torch.poisson(lam, generator=g)
+        lib = cnt.sum(1, keepdim=True).clamp_(min=1.0)
+        expr[r0:r1] = torch.log10(1.0 + cnt / lib * 1e4)
+    return bank, qry, expr
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index=0, period=0.1):
+        self.samples, self.reasons, self.period, self.index = [], set(), period, index
+        self._stop = threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake_slowdown": 0x80, "sw_thermal_slowdown": 0x20,
+                 "applications_clocks_setting": 0x2, "sync_boost": 0x10}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.t.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_time(cfg, mode, budget_s=20.0, seed=7, threads=None):
+    """Times the oracle's literal restatement of evel_her2st.py:74-84 + :175-187 on a bounded
+    query sample of the SAME workload (full bank), all host threads.  cfg4 cannot run whole on
+    a CPU (the Q x N float32 similarity matrix alone is 262 GB): queries go in
+    chunks of <= 512 and the rate is per query."""
+    from oracle import oracle
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    N, D, G, k = cfg["N"], cfg["D"], cfg["G"], cfg["k"]
+    rng = np.random.default_rng(seed)
+    bank = rng.standard_normal((N, D), dtype=np.float32)
+    expr = rng.random((N, G), dtype=np.float32)
+    done, t_total, chunk = 0, 0.0, 64
+    cap = min(cfg["Q"], 2048)
+    while True:
+        qry = rng.standard_normal((chunk, D), dtype=np.float32)
+        t0 = time.perf_counter()
+        oracle.retrieve_ref(bank, expr, qry, k, mode)
+        dt = time.perf_counter() - t0
+        done += chunk
+        t_total += dt
+        if t_total >= budget_s or done >= cap:
+            break
+        per_q = t_total / done
+        chunk = int(max(1, min(512, cap - done, (budget_s - t_total) / per_q)))
+    return dict(value=done / t_total, unit=UNIT, cores=threads, kind="port",
+                sample=f"{done} of {cfg['Q']} queries (chunks <= 512) against the full "
+                       f"{N}-spot bank, k={k}, G={G}, {t_total:.1f} s of CPU time; per-query rate",
+                torch=torch.__version__, numpy=np.__version__), t_total, done
+
+
+# --------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("MCLST_BENCH_WORKLOAD", "cfg4"))
+    ap.add_argument("--mode", default="inv_sq_l2")
+    ap.add_argument("--flavour", default="clustered")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exact-only", action="store_true")
+    args = ap.parse_args()
+    assert args.warmup >= 3 or args.impl == "reference", "timing rules: W >= 3"
+    cfg = dict(synth.CONFIGS[args.workload])
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    config = {"workload": f"{args.workload}: N={cfg['N']} bank spots x Q={cfg['Q']} queries, D={cfg['D']}, "
+                          f"top_k={cfg['k']}, G={cfg['G']} genes, weights={args.mode}, {args.flavour} embeddings",
+              "l2": "inputs larger than L2 (126 MB)" }
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        for _ in range(max(1, args.steps)):
+            cb, t, done = cpu_reference_time(cfg, args.mode, budget_s=args.cpu_budget)
+            vals.append(cb["value"])
+        v = float(np.mean(vals))
+        cb["value"] = v
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT,
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * cfg["Q"] / v, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}}))
+        return
+
+    from mclstexp_b200 import _lib, retrieval
+    assert torch.cuda.is_available(), "bench.py needs a B200 (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        from mclstexp_b200 import distributed as mdist
+    peaks = load_peaks()
+    N, Q, D, G, k = cfg["N"], cfg["Q"], cfg["D"], cfg["G"], cfg["k"]
+
+    bank, qry, expr = make_inputs_device(cfg, 1234 + 4, dev, args.flavour)
+    if world > 1:
+        shard = mdist.BankShard.from_full(bank, expr, rank, world)
+        del bank, expr
+        torch.cuda.empty_cache()
+
+        def step():
+            return mdist.retrieve_sharded(shard, qry, k, args.mode)
+    else:
+        def step():
+            return retrieval.retrieve_device(bank, expr, qry, k, args.mode, want_emb=False,
+                                             out_dtype=torch.float32, exact_only=args.exact_only)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    _lib.profile_enable(True)
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            out = step()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = (_lib.launch_count() - l0) // args.steps
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
+    counters = retrieval.last_counters()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = Q / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (live CUDA-event times from the timed region)
+    per = {}
+    for name, t in prof:
+        per.setdefault(name, []).append(t)
+    kern = {n: float(np.mean(v)) for n, v in per.items()}
+    share = {n: float(np.sum(v)) / args.steps for n, v in per.items()}
+    top = max(share, key=share.get) if share else None
+    n_local = N // world
+    alg = {   # algorithmic work per launch: FLOPs for the similarity kernels, bytes otherwise
+        "sim_topk": ("tensor", 2.0 * Q * n_local * D),
+        "exact_topk": ("tensor", 2.0 * Q * n_local * D),
+        "weighted_average": ("hbm", Q * k * G * 4.0 + Q * k * D * 4.0 + Q * G * 4.0),
+        "row_norms": ("hbm", (n_local + Q) * D * 4.0),
+        "pack_rows": ("hbm", (n_local + Q) * D * 6.0),
+    }
+    roofline = None
+    if top in alg:
+        bound, work = alg[top]
+        t = kern[top] * 1e-3
+        if bound == "tensor":
+            ach, peak, unit = work / t / 1e12, peaks["tf_sust"], "TFLOP/s"
+        else:
+            ach, peak, unit = work / t / 1e9, peaks["hbm"], "GB/s"
+        roofline = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
+                    "frac": ach / peak, "traffic": None, "peak_source": peaks["source"],
+                    "kernel_ms": kern[top], "share_of_step": share[top] / ms,
+                    "kernels_ms_per_step": share}
+    # whole-step roofline: max(FLOPs / tensor peak, bytes / HBM peak)
+    step_flops = 2.0 * Q * n_local * D
+    step_bytes = Q * k * G * 4.0 + Q * G * 4.0 + (n_local + Q) * D * 4.0 + Q * k * D * 4.0
+    t_roof = max(step_flops / (peaks["tf_sust"] * 1e12), step_bytes / (peaks["hbm"] * 1e9))
+    step_roof = {"t_roof_ms": t_roof * 1e3, "frac": t_roof * 1e3 / ms}
+
+    # ---- end to end through the public host-array API
+    e2e = None
+    if not args.no_e2e and world == 1:
+        hb = torch.empty(bank.shape, dtype=torch.float32).pin_memory()
+        hq = torch.empty(qry.shape, dtype=torch.float32).pin_memory()
+        he = torch.empty(expr.shape, dtype=torch.float32).pin_memory()
+        hb.copy_(bank), hq.copy_(qry), he.copy_(expr)
+        del bank, expr
+        torch.cuda.empty_cache()
+        ho_idx = torch.empty((Q, k), dtype=torch.int64).pin_memory()
+        ho_expr = torch.empty((Q, G), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            b = hb.to(dev, non_blocking=True)
+            q = hq.to(dev, non_blocking=True)
+            e = he.to(dev, non_blocking=True)
+            idx, val, _, ex = retrieval.retrieve_device(b, e, q, k, args.mode, want_emb=False,
+                                                        out_dtype=torch.float32,
+                                                        exact_only=args.exact_only)
+            ho_idx.copy_(idx, non_blocking=True)
+            ho_expr.copy_(ex, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        n_e2e = max(1, min(args.steps, 3))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        dt = (time.perf_counter() - t0) / n_e2e
+        e2e = {"value": Q / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": int(hb.numel() * 4 + hq.numel() * 4 + he.numel() * 4),
+               "d2h_bytes_per_step": int(ho_idx.numel() * 8 + ho_expr.numel() * 4)}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _, _ = cpu_reference_time(cfg, args.mode, budget_s=args.cpu_budget)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f16 tensor-core candidates, "
+                "f64-accumulated f32 re-rank, f32 average", "data": "synthetic", "config": config,
+                "clocks": clk.summary(), "gpu_launches": int(launches), "e2e": e2e,
+                "roofline": roofline, "step_roofline": step_roof, "cpu_baseline": cpu_baseline,
+                "path_counters": counters}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,128 @@
+/*
+ * mclst_b200.h -- C-ABI of libmclst_b200.so: the B200 (sm_100a) kernels behind the
+ * mclSTExp contrastive-alignment + retrieval hot path.
+ *
+ * The reference (ZhicengShi/mclSTExp) is pure Python/PyTorch and has NO FFI layer of its
+ * own; each entry point below names the reference lines whose
+ * arithmetic it replaces, and INTEGRATION.md shows the ctypes stub a maintainer adds to
+ * model.py / evel_*.py.  Conventions:
+ *
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     parameter name ends in _host;
+ *   - the caller owns every buffer (inputs, outputs, workspace); a *_workspace_bytes()
+ *     query precedes each op that needs scratch; the library keeps no tensor state;
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and never synchronises;
+ *   - return value: 0 = ok, negative = MCLST_ERR_*, positive = cudaError_t;
+ *     mclst_last_error() returns a thread-local message for the last failure;
+ *   - matrices are row-major float32 with an explicit leading dimension (elements).
+ */
+#ifndef MCLST_B200_H
+#define MCLST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mclst_stream_t; /* cudaStream_t */
+
+enum {
+  MCLST_OK = 0,
+  MCLST_ERR_INVALID = -1,     /* bad argument (null pointer, k > N, misaligned, ...) */
+  MCLST_ERR_WORKSPACE = -2,   /* workspace too small */
+  MCLST_ERR_UNSUPPORTED = -3, /* shape outside what the kernels are built for */
+  MCLST_ERR_DEVICE = -4       /* not an sm_100 device */
+};
+
+/* weight modes of the top-k expression average */
+enum {
+  MCLST_W_INV_SQ_L1 = 0, /* evel_her2st.py:178-184  (ord=1)                          */
+  MCLST_W_INV_SQ_L2 = 1, /* evel_visium.py:197-200, evel_cscc.py:209-211             */
+  MCLST_W_SIMILARITY = 2,/* evel_cscc.py:201 (commented variant): value / sum(value) */
+  MCLST_W_UNIFORM = 3,   /* BLEEP_inference.ipynb cell 5 "average" / "simple" (k=1)  */
+  MCLST_W_BLEEP_EXP = 4  /* BLEEP_inference.ipynb cell 5 "weighted_average"          */
+};
+
+/* flags of mclst_find_matches / mclst_retrieve */
+enum {
+  MCLST_FM_DEFAULT = 0,
+  MCLST_FM_EXACT_ONLY = 1 /* skip the tensor-core candidate pass, brute-force every query */
+};
+
+/* contrastive-loss target modes */
+enum {
+  MCLST_T_EYE = 0,      /* model.py:242-247                                        */
+  MCLST_T_SOFT_DIV = 1, /* baselines/Bleep/models.py:34-43   (.../2/T)             */
+  MCLST_T_SOFT_MUL = 2  /* baselines/Bleep/models.py:70-79   (.../2*T)             */
+};
+
+int mclst_version(void);
+const char* mclst_last_error(void);
+/* sm count / compute capability of the current device; MCLST_ERR_DEVICE if not sm_100 */
+int mclst_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernels this library has launched since load (claim for bench.py gpu_launches) */
+int64_t mclst_launch_count(void);
+/* counters of the last mclst_find_matches call on this thread are written to the workspace
+ * head (device): [0] queries resolved by the tensor-core path, [1] queries that fell back
+ * to the exact brute-force path.  Copy them out with mclst_read_counters (synchronises). */
+int mclst_read_counters(const void* workspace, int64_t counters_host[4], mclst_stream_t stream);
+
+/* Per-kernel CUDA-event trace for bench.py's roofline block.  enable(1) starts recording
+ * one event per internal kernel launch on the launching stream; collect() synchronises and
+ * returns (name, milliseconds) per kernel since the last collect.  names: 48-byte records. */
+int mclst_profile_enable(int on);
+int mclst_profile_collect(char* names_out, float* ms_out, int cap, int* n);
+
+/* ---------------------------------------------------------------- retrieval ---------- */
+
+/* find_matches  (evel_her2st.py:74-84, evel_visium.py:94-104, evel_cscc.py:74-84).
+ * L2-normalise bank rows and query rows (F.normalize, eps 1e-12), rank every bank row by
+ * cosine similarity per query and return the top_k, sorted by (similarity descending,
+ * index ascending).  out_indices [n_query, top_k] int64 (torch.topk's dtype), each index
+ * + index_offset (bank shards).  out_values (nullable) [n_query, top_k] float32 are the
+ * similarities the cSCC flavour returns. */
+int mclst_find_matches_workspace_bytes(int64_t n_bank, int64_t n_query, int dim, int top_k,
+                                       int flags, size_t* bytes);
+int mclst_find_matches(const float* bank, int64_t n_bank, int64_t ld_bank,
+                       const float* query, int64_t n_query, int64_t ld_query,
+                       int dim, int top_k, int64_t index_offset,
+                       int64_t* out_indices, float* out_values,
+                       void* workspace, size_t workspace_bytes, int flags,
+                       mclst_stream_t stream);
+
+/* The per-query loop evel_her2st.py:175-187 / evel_visium.py:194-205 /
+ * evel_cscc.py:198-215 / BLEEP_inference.ipynb cell 5: weights from the UN-normalised
+ * spot_key rows selected by `indices` and the query, then the weighted average of those
+ * spot_key rows (out_emb, nullable) and of the matching expression_key rows (out_expr).
+ * expression_key is [n_bank, genes] float32 (expr_is_f64 = 0) or float64 (= 1); outputs
+ * are float64 (out_is_f64 = 1, the reference's np.zeros dtype) or float32.
+ * indices [n_query, top_k] int64 are LOCAL row numbers (indices - index_offset).
+ * values (only MCLST_W_SIMILARITY) [n_query, top_k] float32. */
+int mclst_weighted_average(const float* spot_key, int64_t n_bank, int64_t ld_key,
+                           const void* expression_key, int64_t ld_expr, int genes, int expr_is_f64,
+                           const float* image_query, int64_t n_query, int64_t ld_query, int dim,
+                           const int64_t* indices, const float* values, int top_k,
+                           int64_t index_offset, int weight_mode,
+                           void* out_emb, void* out_expr, int out_is_f64,
+                           mclst_stream_t stream);
+
+/* Partial (sharded-bank) form of the same loop: writes UN-normalised weights
+ * w [n_query, top_k] float32 for the winners this shard owns (index in
+ * [index_offset, index_offset + n_bank), others 0) and accumulates nothing.  Used by the
+ * multi-GPU merge; see mclstexp_b200/retrieval.py. */
+int mclst_neighbor_distances(const float* spot_key, int64_t n_bank, int64_t ld_key,
+                             const float* image_query, int64_t n_query, int64_t ld_query, int dim,
+                             const int64_t* indices, int top_k, int64_t index_offset, int p,
+                             float* out_dist, mclst_stream_t stream);
+int mclst_weighted_gather(const void* expression_key, int64_t n_bank, int64_t ld_expr, int genes,
+                          int expr_is_f64, const int64_t* indices, const float* weights,
+                          int64_t n_query, int top_k, int64_t index_offset,
+                          float* out_partial /* [n_query, genes] float32, overwritten */,
+                          mclst_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCLST_B200_H */

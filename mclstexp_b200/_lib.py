@@ -1,0 +1,109 @@
+"""ctypes binding of libmclst_b200.so (see include/mclst_b200.h).
+
+There is deliberately NO CPU fallback: if the shared object is missing or a call
+fails, the product path raises.  ``load()`` is cheap and needs no GPU (the CPU
+test-suite uses it to check that every symbol the header declares is exported).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import List
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmclst_b200.so")
+HEADER = os.path.join(os.path.dirname(HERE), "include", "mclst_b200.h")
+
+# weight modes / flags (mirrors of the header enums)
+W_INV_SQ_L1, W_INV_SQ_L2, W_SIMILARITY, W_UNIFORM, W_BLEEP_EXP = range(5)
+WEIGHT_MODES = {"inv_sq_l1": 0, "inv_sq_l2": 1, "similarity": 2, "uniform": 3, "bleep_exp": 4}
+FM_DEFAULT, FM_EXACT_ONLY = 0, 1
+T_EYE, T_SOFT_DIV, T_SOFT_MUL = 0, 1, 2
+
+_lib = None
+
+
+class MclstError(RuntimeError):
+    pass
+
+
+def header_symbols() -> List[str]:
+    """Every function the public header declares."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mclst_[a-z0-9_]+)\s*\(", src)))
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MclstError(
+            f"{LIB_PATH} is missing: build it with `python -m mclstexp_b200.build` "
+            "(there is no CPU fallback for the mclSTExp hot path)")
+    lib = C.CDLL(LIB_PATH)
+    p, i64, i32, sz = C.c_void_p, C.c_int64, C.c_int, C.c_size_t
+    lib.mclst_version.restype = i32
+    lib.mclst_last_error.restype = C.c_char_p
+    lib.mclst_launch_count.restype = i64
+    lib.mclst_device_info.argtypes = [C.POINTER(i32)] * 3
+    lib.mclst_profile_enable.argtypes = [i32]
+    lib.mclst_profile_collect.argtypes = [C.c_char_p, C.POINTER(C.c_float), i32, C.POINTER(i32)]
+    lib.mclst_read_counters.argtypes = [p, C.POINTER(i64), p]
+    lib.mclst_find_matches_workspace_bytes.argtypes = [i64, i64, i32, i32, i32, C.POINTER(sz)]
+    lib.mclst_find_matches.argtypes = [p, i64, i64, p, i64, i64, i32, i32, i64, p, p, p, sz, i32, p]
+    lib.mclst_weighted_average.argtypes = [p, i64, i64, p, i64, i32, i32, p, i64, i64, i32, p, p,
+                                           i32, i64, i32, p, p, i32, p]
+    lib.mclst_neighbor_distances.argtypes = [p, i64, i64, p, i64, i64, i32, p, i32, i64, i32, p, p]
+    lib.mclst_weighted_gather.argtypes = [p, i64, i64, i32, i32, p, p, i64, i32, i64, p, p]
+    for name in header_symbols():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export it
+        if fn.restype is C.c_int and name not in ("mclst_version",):
+            fn.restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().mclst_last_error().decode(errors="replace")
+        raise MclstError(f"{what or 'libmclst_b200'} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().mclst_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    check(load().mclst_profile_enable(int(on)), "profile_enable")
+
+
+def profile_collect(cap: int = 65536):
+    """[(kernel name, milliseconds)] for every traced launch since the last collect."""
+    names = C.create_string_buffer(48 * cap)
+    ms = (C.c_float * cap)()
+    n = C.c_int()
+    check(load().mclst_profile_collect(names, ms, cap, C.byref(n)), "profile_collect")
+    raw = names.raw
+    return [(raw[48 * i:48 * i + 48].split(b"\0")[0].decode(), float(ms[i])) for i in range(n.value)]
+
+
+def require_cuda(*tensors) -> None:
+    import torch
+    if not torch.cuda.is_available():
+        raise MclstError("no CUDA device: the mclSTExp hot path runs only on a B200 "
+                         "(sm_100a); there is no CPU fallback")
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise MclstError("expected CUDA tensors (no CPU fallback)")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())

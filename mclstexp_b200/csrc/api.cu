@@ -1,0 +1,174 @@
+// extern "C" surface of libmclst_b200.so: error plumbing + retrieval orchestration.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include "common.cuh"
+#include "retrieval.cuh"
+
+namespace mclst {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- per-kernel event trace ------------------------------------------------------------
+struct ProfMark { cudaEvent_t ev; const char* name; };
+static bool g_prof_on = false;
+static std::vector<ProfMark> g_marks;
+static std::vector<cudaEvent_t> g_pool;
+static std::mutex g_prof_mu;
+
+void prof_mark(cudaStream_t st, const char* name) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEvent_t ev;
+  if (!g_pool.empty()) { ev = g_pool.back(); g_pool.pop_back(); }
+  else if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, st);
+  g_marks.push_back({ev, name});
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+// Layout of the find_matches workspace.  The first 256 bytes are counters.
+struct FmWorkspace {
+  int64_t* counters;
+  float* bank_nrm;
+  float* q_nrm;
+  float* scratch;
+  size_t bytes;
+};
+
+static FmWorkspace carve_fm(void* ws, size_t cap, int64_t n_bank, int64_t n_query, int dim,
+                            int top_k, int flags) {
+  (void)dim; (void)top_k; (void)flags;
+  Arena a(ws, cap);
+  FmWorkspace w{};
+  w.counters = a.take<int64_t>(32);
+  w.bank_nrm = a.take<float>((size_t)n_bank);
+  w.q_nrm = a.take<float>((size_t)n_query);
+  w.scratch = a.take<float>(exact_topk_scratch_floats(n_bank, n_query));
+  w.bytes = align_up(a.off, 256);
+  return w;
+}
+
+}  // namespace mclst
+
+using namespace mclst;
+
+extern "C" int mclst_version(void) { return 100; }
+extern "C" const char* mclst_last_error(void) { return g_err; }
+extern "C" int64_t mclst_launch_count(void) { return g_launches.load(); }
+
+extern "C" int mclst_device_info(int* sms, int* major, int* minor) {
+  int dev = 0;
+  MCLST_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  MCLST_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sms) *sms = p.multiProcessorCount;
+  if (major) *major = p.major;
+  if (minor) *minor = p.minor;
+  MCLST_REQUIRE(p.major == 10, MCLST_ERR_DEVICE, "device is sm_%d%d, this library is sm_100a only",
+                p.major, p.minor);
+  return 0;
+}
+
+extern "C" int mclst_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  for (auto& m : g_marks) g_pool.push_back(m.ev);
+  g_marks.clear();
+  return 0;
+}
+
+// Synchronises the device, then writes up to `cap` records: names_out[i] (<= 47 chars + NUL,
+// 48-byte stride) and ms_out[i] = time from mark i to mark i+1 (the last mark of a call is
+// named "end" and closes the previous kernel).  Returns the number of records via *n.
+extern "C" int mclst_profile_collect(char* names_out, float* ms_out, int cap, int* n) {
+  MCLST_REQUIRE(names_out && ms_out && n, MCLST_ERR_INVALID, "profile_collect: null pointer");
+  MCLST_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int cnt = 0;
+  for (size_t i = 0; i + 1 < g_marks.size() && cnt < cap; ++i) {
+    if (!strcmp(g_marks[i].name, "end")) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_marks[i].ev, g_marks[i + 1].ev) != cudaSuccess) continue;
+    strncpy(names_out + 48 * cnt, g_marks[i].name, 47);
+    names_out[48 * cnt + 47] = 0;
+    ms_out[cnt++] = ms;
+  }
+  for (auto& m : g_marks) g_pool.push_back(m.ev);
+  g_marks.clear();
+  *n = cnt;
+  return 0;
+}
+
+extern "C" int mclst_read_counters(const void* workspace, int64_t out[4], mclst_stream_t stream) {
+  MCLST_REQUIRE(workspace && out, MCLST_ERR_INVALID, "read_counters: null pointer");
+  MCLST_CUDA(cudaMemcpyAsync(out, workspace, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+  MCLST_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int mclst_find_matches_workspace_bytes(int64_t n_bank, int64_t n_query, int dim,
+                                                  int top_k, int flags, size_t* bytes) {
+  MCLST_REQUIRE(bytes, MCLST_ERR_INVALID, "workspace_bytes: null pointer");
+  MCLST_REQUIRE(n_bank >= 0 && n_query >= 0 && dim >= 1 && top_k >= 1, MCLST_ERR_INVALID,
+                "workspace_bytes: bad shape");
+  *bytes = carve_fm(nullptr, 0, n_bank, n_query, dim, top_k, flags).bytes;
+  return 0;
+}
+
+extern "C" int mclst_find_matches(const float* bank, int64_t n_bank, int64_t ld_bank,
+                                  const float* query, int64_t n_query, int64_t ld_query, int dim,
+                                  int top_k, int64_t index_offset, int64_t* out_indices,
+                                  float* out_values, void* workspace, size_t workspace_bytes,
+                                  int flags, mclst_stream_t stream) {
+  MCLST_REQUIRE(bank && query && out_indices && workspace, MCLST_ERR_INVALID,
+                "find_matches: null pointer");
+  MCLST_REQUIRE(dim >= 1 && ld_bank >= dim && ld_query >= dim, MCLST_ERR_INVALID,
+                "find_matches: bad dim/ld");
+  // torch.topk raises when k exceeds the dimension (evel_her2st.py:82)
+  MCLST_REQUIRE(top_k >= 1 && top_k <= n_bank, MCLST_ERR_INVALID,
+                "find_matches: top_k %d out of range for %lld bank rows", top_k, (long long)n_bank);
+  MCLST_REQUIRE(n_bank < (1ll << 31), MCLST_ERR_UNSUPPORTED, "find_matches: bank shard too large");
+  if (n_query == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  FmWorkspace w = carve_fm(workspace, workspace_bytes, n_bank, n_query, dim, top_k, flags);
+  MCLST_REQUIRE(w.bytes <= workspace_bytes, MCLST_ERR_WORKSPACE,
+                "find_matches: workspace %zu < %zu", workspace_bytes, w.bytes);
+  MCLST_CUDA(cudaMemsetAsync(w.counters, 0, 256, st));
+  int rc;
+  prof_mark(st, "row_norms");
+  if ((rc = launch_row_norms(bank, n_bank, ld_bank, dim, w.bank_nrm, st))) return rc;
+  if ((rc = launch_row_norms(query, n_query, ld_query, dim, w.q_nrm, st))) return rc;
+  // exact path for every query
+  prof_mark(st, "exact_topk");
+  rc = launch_exact_topk(bank, n_bank, ld_bank, w.bank_nrm, query, ld_query, w.q_nrm, dim,
+                         nullptr, nullptr, (int)n_query, n_query, top_k, index_offset, w.scratch,
+                         out_indices, out_values, st);
+  prof_mark(st, "end");
+  return rc;
+}

@@ -1,0 +1,201 @@
+"""Evaluation retrieval of mclSTExp on B200: the reference's Python surface
+(``find_matches`` + the per-query weighted-average loop) over libmclst_b200.so.
+
+Reference being mirrored (paths relative to /root/reference):
+  * ``find_matches``           evel_her2st.py:74-84, evel_visium.py:94-104,
+                               evel_cscc.py:74-84 (returns values too)
+  * the weighted-average loop  evel_her2st.py:175-187 (L1), evel_visium.py:194-205 and
+                               evel_cscc.py:198-215 (L2), BLEEP_inference.ipynb cell 5
+
+PyTorch is used only for device memory and streams; every number is produced by
+the CUDA kernels in ``csrc/``.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import WEIGHT_MODES, check, load, ptr, require_cuda, stream_ptr
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+__all__ = ["find_matches", "find_matches_cscc", "find_matches_device", "weighted_topk_average",
+           "weighted_topk_average_device", "retrieve", "retrieve_device", "last_counters"]
+
+_last_ws: Optional[torch.Tensor] = None
+
+
+def _dev_f32(x: ArrayLike, device=None) -> torch.Tensor:
+    """What ``torch.tensor(x)`` does at evel_her2st.py:76-77, but onto the GPU."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    if t.dtype != torch.float32:
+        t = t.float()
+    if not t.is_cuda:
+        if not torch.cuda.is_available():
+            raise _lib.MclstError("no CUDA device: find_matches has no CPU fallback")
+        t = t.to(device or "cuda", non_blocking=True)
+    if t.dim() == 1:
+        t = t[None]
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def find_matches_device(spot_embeddings: torch.Tensor, query_embeddings: torch.Tensor,
+                        top_k: int = 1, index_offset: int = 0, exact_only: bool = False,
+                        need_values: bool = True) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
+    """Device-resident form: float32 CUDA [N,D], [Q,D] -> (values f32 [Q,k] | None,
+    indices int64 [Q,k]), rows sorted by (similarity desc, index asc)."""
+    global _last_ws
+    require_cuda(spot_embeddings, query_embeddings)
+    lib = load()
+    bank, qry = spot_embeddings, query_embeddings
+    assert bank.dtype == torch.float32 and qry.dtype == torch.float32
+    assert bank.dim() == 2 and qry.dim() == 2 and bank.shape[1] == qry.shape[1]
+    assert bank.stride(1) == 1 and qry.stride(1) == 1
+    N, D = bank.shape
+    Q = qry.shape[0]
+    flags = _lib.FM_EXACT_ONLY if exact_only else _lib.FM_DEFAULT
+    nbytes = C.c_size_t()
+    check(lib.mclst_find_matches_workspace_bytes(N, Q, D, top_k, flags, C.byref(nbytes)),
+          "find_matches_workspace_bytes")
+    ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=bank.device)
+    idx = torch.empty((Q, top_k), dtype=torch.int64, device=bank.device)
+    val = torch.empty((Q, top_k), dtype=torch.float32, device=bank.device) if need_values else None
+    with torch.cuda.device(bank.device):
+        check(lib.mclst_find_matches(ptr(bank), N, bank.stride(0), ptr(qry), Q, qry.stride(0), D,
+                                     top_k, index_offset, ptr(idx), ptr(val), ptr(ws),
+                                     ws.numel(), flags, stream_ptr()), "find_matches")
+    _last_ws = ws
+    return val, idx
+
+
+def last_counters() -> dict:
+    """{'tensor_core': n, 'exact_fallback': n} of the most recent find_matches (synchronises)."""
+    if _last_ws is None:
+        return {}
+    out = (C.c_int64 * 4)()
+    with torch.cuda.device(_last_ws.device):
+        check(load().mclst_read_counters(ptr(_last_ws), out, stream_ptr()), "read_counters")
+    return {"tensor_core": int(out[0]), "exact_fallback": int(out[1])}
+
+
+def find_matches(spot_embeddings: ArrayLike, query_embeddings: ArrayLike, top_k: int = 1,
+                 return_values: bool = False, exact_only: bool = False):
+    """Drop-in for evel_her2st.py:74-84: array-likes in, ``np.ndarray`` int64 [Q,k] out
+    (``(k,)`` when there is a single query: the reference's ``squeeze(0)``, :82).  With
+    ``return_values`` the cSCC flavour (evel_cscc.py:74-84): ``(values, indices)``.
+    Tie rule (undefined in the reference): lowest index first."""
+    bank = _dev_f32(spot_embeddings)
+    qry = _dev_f32(query_embeddings, bank.device)
+    val, idx = find_matches_device(bank, qry, top_k, exact_only=exact_only, need_values=return_values)
+    idx_np = idx.cpu().numpy()
+    if idx_np.shape[0] == 1:
+        idx_np = idx_np[0]
+    if return_values:
+        val_np = val.cpu().numpy()
+        if val_np.shape[0] == 1:
+            val_np = val_np[0]
+        return val_np, idx_np
+    return idx_np
+
+
+def find_matches_cscc(spot_embeddings, query_embeddings, top_k=1):
+    """evel_cscc.py:74-84."""
+    return find_matches(spot_embeddings, query_embeddings, top_k, return_values=True)
+
+
+def weighted_topk_average_device(spot_key: torch.Tensor, expression_key: torch.Tensor,
+                                 image_query: torch.Tensor, indices: torch.Tensor,
+                                 mode: str = "inv_sq_l2", values: Optional[torch.Tensor] = None,
+                                 want_emb: bool = True, out_dtype=torch.float64
+                                 ) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
+    require_cuda(spot_key, expression_key, image_query, indices)
+    lib = load()
+    assert spot_key.dtype == torch.float32 and image_query.dtype == torch.float32
+    assert expression_key.dtype in (torch.float32, torch.float64)
+    assert indices.dtype == torch.int64 and indices.dim() == 2 and indices.is_contiguous()
+    assert out_dtype in (torch.float32, torch.float64)
+    Q, k = indices.shape
+    N, D = spot_key.shape
+    G = expression_key.shape[1]
+    assert expression_key.shape[0] == N and image_query.shape == (Q, D)
+    assert spot_key.stride(1) == 1 and expression_key.stride(1) == 1 and image_query.stride(1) == 1
+    if values is not None:
+        values = values.contiguous().float()
+    dev = spot_key.device
+    emb = torch.empty((Q, D), dtype=out_dtype, device=dev) if want_emb else None
+    expr = torch.empty((Q, G), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.mclst_weighted_average(
+            ptr(spot_key), N, spot_key.stride(0), ptr(expression_key), expression_key.stride(0), G,
+            int(expression_key.dtype == torch.float64), ptr(image_query), Q, image_query.stride(0),
+            D, ptr(indices), ptr(values), k, 0, WEIGHT_MODES[mode], ptr(emb), ptr(expr),
+            int(out_dtype == torch.float64), stream_ptr()), "weighted_average")
+    return emb, expr
+
+
+def weighted_topk_average(spot_key: ArrayLike, expression_key: ArrayLike, image_query: ArrayLike,
+                          indices: ArrayLike, p: int = 2, mode: Optional[str] = None,
+                          values: Optional[ArrayLike] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """Replaces the inline loop evel_her2st.py:175-187 (``p=1``) / evel_visium.py:194-205,
+    evel_cscc.py:198-215 (``p=2``); ``mode`` selects the other variants
+    ('similarity', 'uniform', 'bleep_exp').  Returns float64 arrays like the reference's
+    ``np.zeros`` results: (matched_spot_embeddings_pred [Q,D], matched_spot_expression_pred [Q,G])."""
+    if mode is None:
+        mode = {1: "inv_sq_l1", 2: "inv_sq_l2"}[p]
+    sk = _dev_f32(spot_key)
+    iq = _dev_f32(image_query, sk.device)
+    ek = expression_key if isinstance(expression_key, torch.Tensor) else \
+        torch.from_numpy(np.ascontiguousarray(expression_key))
+    if ek.dtype not in (torch.float32, torch.float64):
+        ek = ek.float()
+    ek = ek.to(sk.device)
+    idx = indices if isinstance(indices, torch.Tensor) else torch.from_numpy(np.asarray(indices))
+    idx = idx.to(sk.device, torch.int64)
+    if idx.dim() == 1:
+        idx = idx[None]
+    idx = idx.contiguous()
+    val = None
+    if values is not None:
+        val = _dev_f32(values, sk.device)
+    emb, expr = weighted_topk_average_device(sk, ek, iq, idx, mode, val)
+    return emb.cpu().numpy(), expr.cpu().numpy()
+
+
+def retrieve_device(spot_key: torch.Tensor, expression_key: torch.Tensor, image_query: torch.Tensor,
+                    top_k: int = 50, mode: str = "inv_sq_l2", want_emb: bool = False,
+                    out_dtype=torch.float32, exact_only: bool = False):
+    """find_matches + weighted average with everything resident on the device.
+    Returns (indices int64 [Q,k], values f32 [Q,k], emb_pred | None, expr_pred [Q,G])."""
+    val, idx = find_matches_device(spot_key, image_query, top_k, exact_only=exact_only)
+    emb, expr = weighted_topk_average_device(spot_key, expression_key, image_query, idx, mode,
+                                             val if mode == "similarity" else None, want_emb,
+                                             out_dtype)
+    return idx, val, emb, expr
+
+
+def retrieve(spot_key: ArrayLike, expression_key: ArrayLike, image_query: ArrayLike, top_k: int = 50,
+             p: int = 2, mode: Optional[str] = None):
+    """The whole fold-loop body evel_her2st.py:174-187 in one call, host arrays in and out:
+    (indices [Q,k] int64, matched_spot_embeddings_pred [Q,D] f64,
+    matched_spot_expression_pred [Q,G] f64)."""
+    if mode is None:
+        mode = {1: "inv_sq_l1", 2: "inv_sq_l2"}[p]
+    sk = _dev_f32(spot_key)
+    iq = _dev_f32(image_query, sk.device)
+    ek = expression_key if isinstance(expression_key, torch.Tensor) else \
+        torch.from_numpy(np.ascontiguousarray(expression_key))
+    if ek.dtype not in (torch.float32, torch.float64):
+        ek = ek.float()
+    ek = ek.to(sk.device, non_blocking=True)
+    idx, val, emb, expr = retrieve_device(sk, ek, iq, top_k, mode, want_emb=True,
+                                          out_dtype=torch.float64)
+    return idx.cpu().numpy(), emb.cpu().numpy(), expr.cpu().numpy()

@@ -1,0 +1,173 @@
+"""Parity of the CUDA retrieval path (through the C-ABI) with the oracle and with the
+golden fixtures made from the reference's own code.  Needs a B200."""
+import numpy as np
+import pytest
+import torch
+
+from mclstexp_b200 import retrieval, synth
+from oracle import oracle
+from test_oracle_golden import _retrieval_inputs, LOOPS
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-3      # north star: predicted expression within 1e-3 relative error under FP32
+
+
+def _check_spec(bank, qry, k, exact_only):
+    val, idx = retrieval.find_matches(bank, qry, k, return_values=True, exact_only=exact_only)
+    sval, sidx = oracle.find_matches_spec(bank, qry, k)
+    if idx.ndim == 1:
+        idx, val = idx[None], val[None]
+    assert idx.dtype == np.int64 and val.dtype == np.float32
+    np.testing.assert_array_equal(idx, sidx)           # bit-exact indices, ties -> lowest index
+    np.testing.assert_array_equal(val, sval)           # bit-exact float32 similarities
+
+
+@pytest.mark.parametrize("exact_only", [True, False])
+@pytest.mark.parametrize("name", ["iid", "clustered", "pm1"])
+@pytest.mark.parametrize("k", [1, 50, 200])
+def test_find_matches_bit_exact_vs_spec(golden_retrieval, name, k, exact_only):
+    z, meta = golden_retrieval
+    bank, qry, _ = _retrieval_inputs(meta, name)
+    _check_spec(bank, qry, k, exact_only)
+
+
+@pytest.mark.parametrize("exact_only", [True, False])
+@pytest.mark.parametrize("name", ["iid", "clustered"])
+@pytest.mark.parametrize("k", [1, 50, 200])
+def test_find_matches_vs_reference_golden(golden_retrieval, name, k, exact_only):
+    """Against what the reference's own find_matches returned (evel_her2st.py:74-84)."""
+    z, meta = golden_retrieval
+    bank, qry, _ = _retrieval_inputs(meta, name)
+    idx = retrieval.find_matches(bank, qry, k, exact_only=exact_only)
+    ref = z[f"{name}/find_matches/k{k}/indices"]
+    ok = oracle.decidable_rows(bank, qry, k)
+    np.testing.assert_array_equal(idx[ok], ref[ok])
+    val, _ = retrieval.find_matches(bank, qry, k, return_values=True, exact_only=exact_only)
+    np.testing.assert_allclose(val, z[f"{name}/find_matches/k{k}/values"], rtol=0, atol=5e-7)
+
+
+def test_pm1_known_answer_against_reference_values(golden_retrieval):
+    z, meta = golden_retrieval
+    bank, qry, _ = _retrieval_inputs(meta, "pm1")
+    val, idx = retrieval.find_matches(bank, qry, 50, return_values=True)
+    np.testing.assert_array_equal(val, z["pm1/find_matches/k50/values"])   # exact arithmetic
+
+
+def test_q1_squeeze_quirk(golden_retrieval):
+    z, meta = golden_retrieval
+    bank, qry, _ = _retrieval_inputs(meta, "iid")
+    idx = retrieval.find_matches(bank, qry[:1], 5)
+    assert idx.shape == (5,)
+    np.testing.assert_array_equal(idx, z["iid/find_matches/q1/indices"])
+
+
+@pytest.mark.parametrize("exact_only", [True, False])
+@pytest.mark.parametrize("N,Q,D,k", [(50, 3, 256, 50), (257, 130, 256, 7), (1000, 5, 100, 33),
+                                     (513, 129, 64, 64), (3000, 300, 256, 600), (40, 1, 8, 40)])
+def test_find_matches_ragged_shapes(N, Q, D, k, exact_only):
+    bank = synth.embeddings(N, D, 900 + N)
+    qry = synth.embeddings(Q, D, 901 + N)
+    _check_spec(bank, qry, k, exact_only)
+
+
+@pytest.mark.parametrize("exact_only", [True, False])
+def test_find_matches_degenerate_rows(exact_only):
+    bank = synth.embeddings(300, 256, 5)
+    bank[7] = 0.0                       # zero-norm row: F.normalize eps keeps it at 0
+    bank[11] = bank[3]                  # exact duplicate -> exact tie, lowest index first
+    qry = synth.embeddings(9, 256, 6)
+    qry[2] = 0.0                        # zero query: every similarity is 0 -> indices 0..k-1
+    _check_spec(bank, qry, 20, exact_only)
+    idx = retrieval.find_matches(bank, qry, 20, exact_only=exact_only)
+    np.testing.assert_array_equal(idx[2], np.arange(20))
+
+
+def test_find_matches_errors():
+    bank = synth.embeddings(10, 16, 1)
+    with pytest.raises(RuntimeError):
+        retrieval.find_matches(bank, bank[:2], 11)       # k > N, torch.topk raises too
+
+
+def test_empty_queries():
+    bank = torch.tensor(synth.embeddings(10, 16, 1)).cuda()
+    val, idx = retrieval.find_matches_device(bank, bank[:0], 3)
+    assert idx.shape == (0, 3)
+
+
+@pytest.mark.parametrize("name", ["iid", "clustered"])
+@pytest.mark.parametrize("tag,mode", LOOPS)
+def test_weighted_average_vs_reference_golden(golden_retrieval, name, tag, mode):
+    z, meta = golden_retrieval
+    bank, qry, expr = _retrieval_inputs(meta, name)
+    idx = z[f"{name}/{tag}/indices"].astype(np.int64)
+    emb, ex = retrieval.weighted_topk_average(bank, expr, qry, idx, mode=mode)
+    assert emb.dtype == np.float64 and ex.dtype == np.float64
+    np.testing.assert_allclose(emb, z[f"{name}/{tag}/emb_pred"], rtol=RTOL, atol=1e-5)
+    np.testing.assert_allclose(ex, z[f"{name}/{tag}/expr_pred"], rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["inv_sq_l1", "inv_sq_l2", "similarity", "uniform", "bleep_exp"])
+@pytest.mark.parametrize("G,dtype", [(785, np.float32), (1000, np.float32), (171, np.float64), (4, np.float32)])
+def test_weighted_average_modes_and_layouts(mode, G, dtype):
+    N, Q, D, k = 600, 21, 256, 50
+    bank = synth.embeddings(N, D, 41, "clustered")
+    qry = synth.embeddings(Q, D, 42, "clustered")
+    expr = synth.expression(N, G, 43, dtype=dtype)
+    val, idx = oracle.find_matches_spec(bank, qry, k)
+    emb, ex = retrieval.weighted_topk_average(bank, expr, qry, idx, mode=mode, values=val)
+    emb64, ex64 = oracle.weighted_average_spec(bank, expr, qry, idx, mode, val)
+    np.testing.assert_allclose(emb, emb64, rtol=RTOL, atol=1e-5)
+    np.testing.assert_allclose(ex, ex64, rtol=RTOL, atol=1e-6)
+
+
+def test_weighted_average_zero_distance_defined():
+    bank = synth.embeddings(64, 32, 1)
+    qry = bank[[3, 7]].copy()
+    expr = synth.expression(64, 12, 2)
+    idx = np.array([[3, 5, 9], [1, 7, 2]], np.int64)
+    for mode in ("inv_sq_l1", "inv_sq_l2"):
+        _, ex = retrieval.weighted_topk_average(bank, expr, qry, idx, mode=mode)
+        np.testing.assert_allclose(ex[0], expr[3], rtol=1e-6)
+        np.testing.assert_allclose(ex[1], expr[7], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name,tag", [("iid", "loop_her2st"), ("clustered", "loop_visium"),
+                                      ("iid", "loop_cscc")])
+def test_retrieve_fold_body_vs_reference_golden(golden_retrieval, name, tag):
+    """The whole fold-loop body (find_matches + loop) against the reference's verbatim run."""
+    z, meta = golden_retrieval
+    bank, qry, expr = _retrieval_inputs(meta, name)
+    info = meta[name][tag]
+    idx, emb, ex = retrieval.retrieve(bank, expr, qry, top_k=info["k"], mode=info["mode"])
+    ok = oracle.decidable_rows(bank, qry, info["k"])
+    ref_idx = z[f"{name}/{tag}/indices"]
+    np.testing.assert_array_equal(idx[ok], ref_idx[ok])
+    np.testing.assert_allclose(ex, z[f"{name}/{tag}/expr_pred"], rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(emb, z[f"{name}/{tag}/emb_pred"], rtol=RTOL, atol=1e-5)
+
+
+def test_cfg3_shape_properties():
+    """BASELINE cfg3 size (N=30000, Q=4000): size-independent properties + sampled rows."""
+    c = synth.CONFIGS["cfg3"]
+    bank = synth.embeddings(c["N"], c["D"], 1237, "clustered")
+    qry = synth.embeddings(c["Q"], c["D"], 1238, "clustered")
+    expr = synth.expression(c["N"], c["G"], 1239)
+    tb, tq, te = (torch.tensor(a).cuda() for a in (bank, qry, expr))
+    idx, val, _, ex = retrieval.retrieve_device(tb, te, tq, c["k"], "inv_sq_l2")
+    idx_c, val_c, ex_c = idx.cpu().numpy(), val.cpu().numpy(), ex.cpu().numpy()
+    assert (np.diff(val_c, axis=1) <= 0).all()                       # sorted descending
+    assert all(len(set(r)) == c["k"] for r in idx_c[::97])            # no duplicates
+    assert idx_c.min() >= 0 and idx_c.max() < c["N"]
+    rows = np.arange(0, c["Q"], 131)
+    sval, sidx = oracle.find_matches_spec(bank, qry[rows], c["k"])
+    np.testing.assert_array_equal(idx_c[rows], sidx)
+    np.testing.assert_array_equal(val_c[rows], sval)
+    _, ex64 = oracle.weighted_average_spec(bank, expr, qry[rows], sidx, "inv_sq_l2")
+    np.testing.assert_allclose(ex_c[rows], ex64, rtol=RTOL, atol=1e-6)
+    # convexity: a weighted average of rows lies inside their per-gene range
+    g = expr[idx_c[rows]]
+    assert (ex_c[rows] <= g.max(1) + 1e-5).all() and (ex_c[rows] >= g.min(1) - 1e-5).all()
+    # the exact path and the default path agree everywhere
+    val_e, idx_e = retrieval.find_matches_device(tb, tq, c["k"], exact_only=True)
+    assert torch.equal(idx_e, idx) and torch.equal(val_e, val)
