@@ -64,9 +64,9 @@ const char* mclst_last_error(void);
 int mclst_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* number of kernels this library has launched since load (claim for bench.py gpu_launches) */
 int64_t mclst_launch_count(void);
-/* counters of the last mclst_find_matches call on this thread are written to the workspace
- * head (device): [0] queries resolved by the tensor-core path, [1] queries that fell back
- * to the exact brute-force path.  Copy them out with mclst_read_counters (synchronises). */
+/* mclst_find_matches keeps counters at the head of its workspace (device).  This copies them
+ * out (synchronises `stream`): [0] queries resolved by the tensor-core candidate path,
+ * [1] queries recomputed by the exact brute-force path. */
 int mclst_read_counters(const void* workspace, int64_t counters_host[4], mclst_stream_t stream);
 
 /* Per-kernel CUDA-event trace for bench.py's roofline block.  enable(1) starts recording
@@ -91,6 +91,14 @@ int mclst_find_matches(const float* bank, int64_t n_bank, int64_t ld_bank,
                        int64_t* out_indices, float* out_values,
                        void* workspace, size_t workspace_bytes, int flags,
                        mclst_stream_t stream);
+
+/* Testing aid: the raw similarities of the tensor-core candidate pass (fp16-rounded
+ * normalised operands, fp32 accumulation) written to out [n_query, ld_out]; workspace as for
+ * mclst_find_matches with top_k = 1.  Not part of the reference surface. */
+int mclst_debug_similarity(const float* bank, int64_t n_bank, int64_t ld_bank,
+                           const float* query, int64_t n_query, int64_t ld_query, int dim,
+                           float* out, int64_t ld_out, void* workspace, size_t workspace_bytes,
+                           mclst_stream_t stream);
 
 /* The per-query loop evel_her2st.py:175-187 / evel_visium.py:194-205 /
  * evel_cscc.py:198-215 / BLEEP_inference.ipynb cell 5: weights from the UN-normalised

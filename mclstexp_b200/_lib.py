@@ -54,6 +54,7 @@ def load() -> C.CDLL:
     lib.mclst_read_counters.argtypes = [p, C.POINTER(i64), p]
     lib.mclst_find_matches_workspace_bytes.argtypes = [i64, i64, i32, i32, i32, C.POINTER(sz)]
     lib.mclst_find_matches.argtypes = [p, i64, i64, p, i64, i64, i32, i32, i64, p, p, p, sz, i32, p]
+    lib.mclst_debug_similarity.argtypes = [p, i64, i64, p, i64, i64, i32, p, i64, p, sz, p]
     lib.mclst_weighted_average.argtypes = [p, i64, i64, p, i64, i32, i32, p, i64, i64, i32, p, p,
                                            i32, i64, i32, p, p, i32, p]
     lib.mclst_neighbor_distances.argtypes = [p, i64, i64, p, i64, i64, i32, p, i32, i64, i32, p, p]

@@ -51,23 +51,39 @@ int sm_count() {
   return cached;
 }
 
-// Layout of the find_matches workspace.  The first 256 bytes are counters.
+// Layout of the find_matches workspace.  The first 256 bytes are int32 counters:
+// [0] queries recomputed by the exact brute-force path, [1] queries resolved by the
+// tensor-core path.
 struct FmWorkspace {
-  int64_t* counters;
+  int* counters;
+  bool use_tc;
+  TcWorkspace tc;
   float* bank_nrm;
   float* q_nrm;
   float* scratch;
   size_t bytes;
 };
 
+static bool tc_eligible(int64_t n_bank, int64_t n_query, int dim, int top_k, int flags) {
+  (void)n_query;
+  return !(flags & MCLST_FM_EXACT_ONLY) && dim <= 256 && tc_cap_for_k(top_k) != 0 &&
+         n_bank >= top_k;
+}
+
 static FmWorkspace carve_fm(void* ws, size_t cap, int64_t n_bank, int64_t n_query, int dim,
                             int top_k, int flags) {
-  (void)dim; (void)top_k; (void)flags;
   Arena a(ws, cap);
   FmWorkspace w{};
-  w.counters = a.take<int64_t>(32);
-  w.bank_nrm = a.take<float>((size_t)n_bank);
-  w.q_nrm = a.take<float>((size_t)n_query);
+  w.counters = a.take<int>(64);
+  w.use_tc = tc_eligible(n_bank, n_query, dim, top_k, flags);
+  if (w.use_tc) {
+    tc_workspace(a, n_bank, n_query, dim, top_k, w.tc);
+    w.bank_nrm = w.tc.b_nrm;
+    w.q_nrm = w.tc.q_nrm;
+  } else {
+    w.bank_nrm = a.take<float>((size_t)n_bank);
+    w.q_nrm = a.take<float>((size_t)n_query);
+  }
   w.scratch = a.take<float>(exact_topk_scratch_floats(n_bank, n_query));
   w.bytes = align_up(a.off, 256);
   return w;
@@ -126,9 +142,13 @@ extern "C" int mclst_profile_collect(char* names_out, float* ms_out, int cap, in
 
 extern "C" int mclst_read_counters(const void* workspace, int64_t out[4], mclst_stream_t stream) {
   MCLST_REQUIRE(workspace && out, MCLST_ERR_INVALID, "read_counters: null pointer");
-  MCLST_CUDA(cudaMemcpyAsync(out, workspace, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost,
-                             (cudaStream_t)stream));
+  int c[4] = {0, 0, 0, 0};
+  MCLST_CUDA(cudaMemcpyAsync(c, workspace, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   MCLST_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  out[0] = c[1];   // tensor-core path
+  out[1] = c[0];   // exact fallback
+  out[2] = c[2];
+  out[3] = c[3];
   return 0;
 }
 
@@ -146,6 +166,7 @@ extern "C" int mclst_find_matches(const float* bank, int64_t n_bank, int64_t ld_
                                   int top_k, int64_t index_offset, int64_t* out_indices,
                                   float* out_values, void* workspace, size_t workspace_bytes,
                                   int flags, mclst_stream_t stream) {
+  if (n_query == 0 && n_bank >= 0) return 0;
   MCLST_REQUIRE(bank && query && out_indices && workspace, MCLST_ERR_INVALID,
                 "find_matches: null pointer");
   MCLST_REQUIRE(dim >= 1 && ld_bank >= dim && ld_query >= dim, MCLST_ERR_INVALID,
@@ -161,14 +182,54 @@ extern "C" int mclst_find_matches(const float* bank, int64_t n_bank, int64_t ld_
                 "find_matches: workspace %zu < %zu", workspace_bytes, w.bytes);
   MCLST_CUDA(cudaMemsetAsync(w.counters, 0, 256, st));
   int rc;
-  prof_mark(st, "row_norms");
-  if ((rc = launch_row_norms(bank, n_bank, ld_bank, dim, w.bank_nrm, st))) return rc;
-  if ((rc = launch_row_norms(query, n_query, ld_query, dim, w.q_nrm, st))) return rc;
-  // exact path for every query
-  prof_mark(st, "exact_topk");
+  if (!w.use_tc) {
+    prof_mark(st, "row_norms");
+    if ((rc = launch_row_norms(bank, n_bank, ld_bank, dim, w.bank_nrm, st))) return rc;
+    if ((rc = launch_row_norms(query, n_query, ld_query, dim, w.q_nrm, st))) return rc;
+    prof_mark(st, "exact_topk");
+    rc = launch_exact_topk(bank, n_bank, ld_bank, w.bank_nrm, query, ld_query, w.q_nrm, dim,
+                           nullptr, nullptr, (int)n_query, n_query, top_k, index_offset, w.scratch,
+                           out_indices, out_values, st);
+    prof_mark(st, "end");
+    return rc;
+  }
+  const TcWorkspace& t = w.tc;
+  MCLST_CUDA(cudaMemsetAsync(t.stats, 0, 16 * sizeof(uint32_t), st));
+  prof_mark(st, "pack_rows");
+  if ((rc = launch_pack_rows(bank, n_bank, t.n_pad, ld_bank, dim, t.nkb, t.bpack, t.b_nrm,
+                             t.b_resid, t.stats, st))) return rc;
+  if ((rc = launch_pack_rows(query, n_query, t.q_pad, ld_query, dim, t.nkb, t.qpack, t.q_nrm,
+                             t.q_resid, t.stats + 8, st))) return rc;
+  prof_mark(st, "sim_topk");
+  if ((rc = launch_sim_topk(t, n_bank, n_query, top_k, nullptr, 0, st))) return rc;
+  prof_mark(st, "rerank");
+  if ((rc = launch_rerank(t, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k,
+                          index_offset, out_indices, out_values, w.counters, st))) return rc;
+  prof_mark(st, "exact_fallback");
   rc = launch_exact_topk(bank, n_bank, ld_bank, w.bank_nrm, query, ld_query, w.q_nrm, dim,
-                         nullptr, nullptr, (int)n_query, n_query, top_k, index_offset, w.scratch,
+                         t.fb_list, w.counters, 0, n_query, top_k, index_offset, w.scratch,
                          out_indices, out_values, st);
   prof_mark(st, "end");
   return rc;
+}
+
+// Testing aid: the raw tensor-core similarities the candidate pass sees (fp16-rounded
+// normalised operands, fp32 accumulation), written to out [n_query, ld_out].
+extern "C" int mclst_debug_similarity(const float* bank, int64_t n_bank, int64_t ld_bank,
+                                      const float* query, int64_t n_query, int64_t ld_query,
+                                      int dim, float* out, int64_t ld_out, void* workspace,
+                                      size_t workspace_bytes, mclst_stream_t stream) {
+  MCLST_REQUIRE(bank && query && out && workspace, MCLST_ERR_INVALID, "debug_similarity: null");
+  MCLST_REQUIRE(dim >= 1 && dim <= 256, MCLST_ERR_UNSUPPORTED, "debug_similarity: dim");
+  cudaStream_t st = (cudaStream_t)stream;
+  FmWorkspace w = carve_fm(workspace, workspace_bytes, n_bank, n_query, dim, 1, 0);
+  MCLST_REQUIRE(w.use_tc && w.bytes <= workspace_bytes, MCLST_ERR_WORKSPACE, "debug_similarity: ws");
+  const TcWorkspace& t = w.tc;
+  int rc;
+  MCLST_CUDA(cudaMemsetAsync(t.stats, 0, 16 * sizeof(uint32_t), st));
+  if ((rc = launch_pack_rows(bank, n_bank, t.n_pad, ld_bank, dim, t.nkb, t.bpack, t.b_nrm,
+                             t.b_resid, t.stats, st))) return rc;
+  if ((rc = launch_pack_rows(query, n_query, t.q_pad, ld_query, dim, t.nkb, t.qpack, t.q_nrm,
+                             t.q_resid, t.stats + 8, st))) return rc;
+  return launch_sim_topk(t, n_bank, n_query, 1, out, ld_out, st);
 }

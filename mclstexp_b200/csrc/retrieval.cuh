@@ -16,4 +16,26 @@ int launch_exact_topk(const float* bank, int64_t N, int64_t ldb, const float* ba
                       int k, int64_t index_offset, float* scratch, int64_t* out_idx,
                       float* out_val, cudaStream_t st);
 
+// ---- tensor-core candidate path (sim_topk.cu)
+struct TcWorkspace {
+  int nkb, S, cap;
+  int64_t q_pad, n_pad;
+  uint32_t* stats;          // [0..7] bank: max residual bits, non-finite flag; [8..15] queries
+  uint8_t *qpack, *bpack;
+  float *q_nrm, *q_resid, *b_nrm, *b_resid;
+  uint2* cand;
+  int* cand_cnt;
+  int* fb_list;
+};
+int tc_cap_for_k(int k);
+void tc_workspace(Arena& a, int64_t n_bank, int64_t n_query, int dim, int top_k, TcWorkspace& w);
+int launch_pack_rows(const float* x, int64_t rows, int64_t rows_pad, int64_t ld, int dim, int nkb,
+                     uint8_t* packed, float* nrm, float* resid, uint32_t* stats, cudaStream_t st);
+int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int top_k, float* dump,
+                    int64_t dump_ld, cudaStream_t st);
+int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64_t ldb,
+                  const float* query, int64_t n_query, int64_t ldq, int dim, int top_k,
+                  int64_t index_offset, int64_t* out_idx, float* out_val, int* counters,
+                  cudaStream_t st);
+
 }  // namespace mclst

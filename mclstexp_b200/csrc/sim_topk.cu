@@ -1,0 +1,547 @@
+// Cosine-similarity top-k on the 5th-generation tensor cores (find_matches,
+// reference evel_her2st.py:74-84) -- candidate generation + exact re-rank.
+//
+//   pack_rows      fp32 rows -> L2-normalised fp16 "TilePack" operand (+ norm, fp16 rounding
+//                  residual per row).  HBM-bound, one warp per row.
+//   sim_topk       persistent-per-CTA GEMM: 128 queries (TMEM lanes) x 256 bank rows (TMEM
+//                  columns) per tile, K = 256.  Warp 0 streams bank slices with cp.async.bulk
+//                  (TMA engine) into a 4-stage shared-memory ring, warp 1 issues
+//                  tcgen05.mma.kind::f16 into a double-buffered 2 x 256-column TMEM
+//                  accumulator, warps 2-5 drain it with tcgen05.ld: every thread owns one
+//                  query row, compares 32 similarities per load against its running
+//                  threshold and appends the rare survivors to a per-(query, split) candidate
+//                  buffer in global memory (L2 resident).  The Q x N similarity matrix is
+//                  never materialised.
+//   rerank         per query: merge the splits' candidates, keep those within 2*eps of the
+//                  k-th best approximate score, recompute them exactly (fp64 accumulation of
+//                  the fp32-normalised rows), sort by (value desc, index asc), emit top-k.
+//
+// Exactness argument (DESIGN.md "retrieval/exactness"): with |approx - exact| <= eps for
+// every (query, row) pair -- eps = (r_q + max_s r_s) * (1 + 2^-9) + E_ACC, r = fp16 rounding
+// residual norms measured at pack time (Cauchy-Schwarz), E_ACC the tensor-core accumulation
+// bound -- any row whose approximate score is below (k-th best approximate) - 2*eps is
+// strictly worse than k rows, so it cannot be in the exact top-k.  The running threshold
+// only ever uses a LOWER bound of the running k-th best, so nothing needed is dropped.
+// Rows for which the band overflows the candidate buffer (massive ties, pathological
+// clustering) are flagged and recomputed by the exact brute-force kernel.
+#include <algorithm>
+#include "common.cuh"
+#include "retrieval.cuh"
+#include "umma.cuh"
+
+namespace mclst {
+
+using namespace ptx;
+
+// Bound on the tcgen05 fp32 accumulation error for |scores| <= 1, K <= 256.  Measured on
+// B200 (tests/test_simtopk_gpu.py): max 1.5e-7 -- the bound keeps a 13x margin.
+constexpr float E_ACC = 2.0e-6f;
+
+// ============================================================================ pack_rows
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t rows_pad, int64_t ld, int dim,
+                 int nkb, uint8_t* __restrict__ packed, float* __restrict__ nrm,
+                 float* __restrict__ resid, uint32_t* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows_pad) return;
+  const int nchunks = nkb * 8;               // 16-byte chunks (8 halves) per row; <= 32
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  if (r < rows && lane < nchunks) {
+    const float* p = x + r * ld + lane * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (lane * 8 + i < dim) v[i] = __ldg(p + i);
+  }
+  double ss = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ss = fma((double)v[i], (double)v[i], ss);
+  ss = warp_sum(ss);
+  const float n = fmaxf((float)sqrt(ss), 1e-12f);
+  float res = 0.f;
+  uint32_t h2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = __fdiv_rn(v[2 * i], n), b = __fdiv_rn(v[2 * i + 1], n);
+    const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+    const float da = a - __half2float(ha), db = b - __half2float(hb);
+    res = fmaf(da, da, res);
+    res = fmaf(db, db, res);
+    h2[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+  }
+  res = warp_sum(res);
+  if (lane < nchunks)
+    *reinterpret_cast<uint4*>(packed + tilepack_chunk_offset(r, lane, nkb)) =
+        make_uint4(h2[0], h2[1], h2[2], h2[3]);
+  if (lane == 0) {
+    const float rr = (r < rows) ? sqrtf(res) * 1.00001f + 1e-12f : 0.f;
+    nrm[r] = n;
+    resid[r] = rr;
+    if (r < rows) {
+      atomicMax(&stats[0], __float_as_uint(rr));
+      if (!(ss <= 1.0e300)) atomicOr(&stats[1], 1u);       // inf / NaN input
+    }
+  }
+}
+
+// ============================================================================ sim_topk
+constexpr int ST_THREADS = 192;
+constexpr int ST_STAGES = 4;
+constexpr int ST_BN = 256;                      // bank rows per tile (TMEM columns)
+constexpr int ST_STAGE_BYTES = 2 * TP_SLICE_BYTES;   // 256 rows x 64 halves
+constexpr int ST_A_BYTES = 4 * TP_SLICE_BYTES;       // up to 4 K slices (dim <= 256)
+constexpr int ST_SMEM = ST_A_BYTES + ST_STAGES * ST_STAGE_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+
+struct SimParams {
+  const uint8_t* qpack;
+  const uint8_t* bpack;
+  int nkb;
+  int64_t Q, N;
+  int tiles_total, S, k;
+  const float* q_resid;
+  const uint32_t* bank_stats;
+  uint2* cand;
+  int* cand_cnt;
+  float* dump;          // debug: raw similarities [Q, dump_ld]
+  int64_t dump_ld;
+};
+
+// Warp-cooperative prune of the candidate buffers of every lane with need == true:
+// new threshold = (lower bound of the k-th best kept score) - e2; entries at or below it
+// are dropped.  Leaves the buffer compacted in ascending bank index.
+template <int CAP>
+__device__ __forceinline__ void warp_prune(uint2* my_buf, int& cnt, float& thr, bool& flagged,
+                                           bool need, int k, float e2, int lane) {
+  constexpr int EPL = CAP / 32;
+  unsigned mask = __ballot_sync(0xffffffffu, need);
+  while (mask) {
+    const int L = __ffs(mask) - 1;
+    mask &= mask - 1;
+    uint2* buf = reinterpret_cast<uint2*>(
+        __shfl_sync(0xffffffffu, (unsigned long long)my_buf, L));
+    const int n = __shfl_sync(0xffffffffu, cnt, L);
+    const float le2 = __shfl_sync(0xffffffffu, e2, L);
+    __syncwarp();
+    uint32_t keys[EPL], vals[EPL], idxs[EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      const int i = lane + 32 * j;
+      if (i < n) {
+        const uint2 e = buf[i];
+        vals[j] = e.x;
+        idxs[j] = e.y;
+        keys[j] = f2ord(__uint_as_float(e.x));
+      } else {
+        keys[j] = 0u; vals[j] = 0u; idxs[j] = 0u;
+      }
+    }
+    uint32_t T = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 8; --bit) {
+      const uint32_t cand = T | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) c += (keys[j] >= cand) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= k) T = cand;
+    }
+    // T <= key of the k-th best (low 8 bits cleared): conservative lower bound
+    const float new_thr = ord2f(T) - le2;
+    __syncwarp();
+    int out = 0;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      const int i = lane + 32 * j;
+      const bool keep = (i < n) && (__uint_as_float(vals[j]) > new_thr);
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) buf[out + __popc(bal & ((1u << lane) - 1u))] = make_uint2(vals[j], idxs[j]);
+      out += __popc(bal);
+    }
+    __syncwarp();
+    if (lane == L) {
+      cnt = out;
+      thr = new_thr;
+      if (out > CAP - 64) {            // band denser than the buffer: give the row to the exact path
+        flagged = true;
+        thr = __int_as_float(0x7f800000);
+      }
+    }
+  }
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+sim_topk_kernel(const SimParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + ST_A_BYTES;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + ST_STAGES * ST_STAGE_BYTES);
+  uint64_t* bar_empty = bar_full + ST_STAGES;
+  uint64_t* bar_a = bar_empty + ST_STAGES;
+  uint64_t* bar_tfull = bar_a + 1;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, s = blockIdx.y;
+  const int nkb = p.nkb;
+  const int t0 = (int)(((int64_t)p.tiles_total * s) / p.S);
+  const int t1 = (int)(((int64_t)p.tiles_total * (s + 1)) / p.S);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ST_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    mbar_init(bar_a, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint64_t pol_keep = policy_evict_last();
+      mbar_arrive_expect_tx(bar_a, (uint32_t)(nkb * TP_SLICE_BYTES));
+      for (int kb = 0; kb < nkb; ++kb)
+        bulk_g2s(sA + kb * TP_SLICE_BYTES,
+                 p.qpack + ((size_t)qb * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES, bar_a);
+      uint32_t stage = 0, phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bar_full[stage], ST_STAGE_BYTES);
+          uint8_t* dst = sB + stage * ST_STAGE_BYTES;
+          const uint8_t* src0 = p.bpack + ((size_t)(2 * t) * nkb + kb) * TP_SLICE_BYTES;
+          const uint8_t* src1 = p.bpack + ((size_t)(2 * t + 1) * nkb + kb) * TP_SLICE_BYTES;
+          bulk_g2s_hint(dst, src0, TP_SLICE_BYTES, &bar_full[stage], pol_keep);
+          bulk_g2s_hint(dst + TP_SLICE_BYTES, src1, TP_SLICE_BYTES, &bar_full[stage], pol_keep);
+          if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, ST_BN, false);
+      mbar_wait(bar_a, 0);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(sA);
+      const uint32_t b_base = smem_u32(sB);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&bar_tempty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * ST_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bar_full[stage], phase);
+          tc_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t ad = make_smem_desc_sw128(a_base + kb * TP_SLICE_BYTES + k4 * 32);
+            const uint64_t bd = make_smem_desc_sw128(b_base + stage * ST_STAGE_BYTES + k4 * 32);
+            mma_f16_ss(d_tmem, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+          }
+          mma_commit(&bar_empty[stage]);
+          if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(&bar_tfull[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: threshold filter
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int64_t q = (int64_t)qb * 128 + row;
+    const bool q_valid = q < p.Q;
+    uint2* my_buf = p.cand + ((size_t)q * p.S + s) * CAP;
+    const float rs_max = __uint_as_float(p.bank_stats[0]);
+    const float rq = q_valid ? p.q_resid[q] : 0.f;
+    const float eps = 1.002f * (rq + rs_max) + E_ACC + 2e-7f;
+    const float e2 = 2.02f * eps;
+    float thr = q_valid ? __int_as_float(0xff800000) : __int_as_float(0x7f800000);
+    int cnt = 0;
+    bool flagged = false;
+    const int k = p.k;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    int it = 0;
+    for (int t = t0; t < t1; ++t, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = t_lane + buf * ST_BN;
+      const int64_t tile_base = (int64_t)t * ST_BN;
+      const int n_valid = (int)min((int64_t)ST_BN, p.N - tile_base);   // < 256 only in the last tile
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(taddr, va);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t (&v)[32] = (c & 1) ? vb : va;
+        tmem_ld_wait();
+        if (c < 7) {
+          if (c & 1) tmem_ld_32x32(taddr + (c + 1) * 32, va);
+          else tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+        } else {
+          // all 256 columns are in registers: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_tempty[buf]);
+        }
+        const int col0 = c * 32;
+        if (p.dump != nullptr && q_valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < n_valid) p.dump[q * p.dump_ld + tile_base + col0 + j] = __uint_as_float(v[j]);
+        }
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) any |= (__uint_as_float(v[j]) > thr);
+        if (any) {
+          const uint32_t nb = (uint32_t)(tile_base + col0);
+          if (col0 + 32 <= n_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (__uint_as_float(v[j]) > thr) my_buf[cnt++] = make_uint2(v[j], nb + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (__uint_as_float(v[j]) > thr && col0 + j < n_valid)
+                my_buf[cnt++] = make_uint2(v[j], nb + j);
+          }
+        }
+        const bool need = cnt > CAP - 32;
+        if (__any_sync(0xffffffffu, need))
+          warp_prune<CAP>(my_buf, cnt, thr, flagged, need, k, e2, lane);
+      }
+    }
+    if (q_valid) p.cand_cnt[(size_t)q * p.S + s] = flagged ? -1 : cnt;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ============================================================================ rerank
+constexpr int RR_MAX = 1024;     // most survivors re-ranked exactly per query
+
+struct RerankParams {
+  const uint2* cand;
+  const int* cand_cnt;
+  int S, cap, k;
+  int64_t Q, N;
+  const float* bank; int64_t ldb; const float* bank_nrm;
+  const float* query; int64_t ldq; const float* q_nrm; const float* q_resid;
+  const uint32_t* bank_stats; const uint32_t* q_stats;
+  int dim;
+  int64_t index_offset;
+  int64_t* out_idx; float* out_val;
+  int* fb_list; int* counters;     // counters[0] = fallback count, [1] = resolved here
+};
+
+__global__ void __launch_bounds__(128)
+rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
+  extern __shared__ __align__(16) unsigned char rr_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * warps_per_block + warp;
+  if (warp >= warps_per_block || q >= p.Q) return;
+  unsigned long long* ent = reinterpret_cast<unsigned long long*>(rr_smem) +
+                            (size_t)warp * per_warp_entries;   // (key << 32) | idx, later sort keys
+  // ---- gather the splits' candidates
+  bool bad = (p.bank_stats[1] | p.q_stats[1]) != 0;    // non-finite input: exact path decides
+  int M = 0;
+  for (int s = 0; s < p.S; ++s) {
+    const int c = p.cand_cnt[(size_t)q * p.S + s];
+    if (c < 0) { bad = true; break; }
+    const uint2* src = p.cand + ((size_t)q * p.S + s) * p.cap;
+    for (int i = lane; i < c; i += 32) {
+      const uint2 e = src[i];
+      ent[M + i] = ((unsigned long long)f2ord(__uint_as_float(e.x)) << 32) | e.y;
+    }
+    M += c;
+  }
+  __syncwarp();
+  int n_s = 0;
+  if (!bad) {
+    // ---- k-th best approximate score (exact, 32-bit radix descent)
+    uint32_t T = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t candT = T | (1u << bit);
+      int c = 0;
+      for (int i = lane; i < M; i += 32) c += ((uint32_t)(ent[i] >> 32) >= candT) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= p.k) T = candT;
+    }
+    const float rs_max = __uint_as_float(p.bank_stats[0]);
+    const float eps = 1.002f * (p.q_resid[q] + rs_max) + E_ACC + 2e-7f;
+    const float band = ord2f(T) - 2.02f * eps;
+    // ---- compact the band in place
+    for (int base = 0; base < M; base += 32) {
+      const int i = base + lane;
+      unsigned long long e = 0;
+      bool keep = false;
+      if (i < M) { e = ent[i]; keep = ord2f((uint32_t)(e >> 32)) > band; }
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      __syncwarp();
+      if (keep) ent[n_s + __popc(bal & ((1u << lane) - 1u))] = e;
+      n_s += __popc(bal);
+      __syncwarp();
+    }
+    if (n_s > RR_MAX || n_s > per_warp_entries) bad = true;
+  }
+  if (bad) {
+    if (lane == 0) p.fb_list[atomicAdd(&p.counters[0], 1)] = (int)q;
+    return;
+  }
+  // ---- exact similarity of every survivor
+  double qh[8];
+  const float nq = p.q_nrm[q];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int d = lane + 32 * t;
+    qh[t] = d < p.dim ? (double)__fdiv_rn(__ldg(p.query + q * p.ldq + d), nq) : 0.0;
+  }
+  for (int i = 0; i < n_s; ++i) {
+    const uint32_t r = (uint32_t)ent[i];
+    const float* sp = p.bank + (int64_t)r * p.ldb;
+    const float bn = p.bank_nrm[r];
+    double acc = 0.0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int d = lane + 32 * t;
+      if (d < p.dim) acc = fma((double)__fdiv_rn(__ldg(sp + d), bn), qh[t], acc);
+    }
+    acc = warp_sum(acc);
+    __syncwarp();
+    if (lane == 0)
+      ent[i] = ((unsigned long long)f2ord((float)acc) << 32) | (unsigned long long)(0xffffffffu - r);
+  }
+  __syncwarp();
+  // ---- sort (value desc, index asc)
+  int P = 1;
+  while (P < n_s) P <<= 1;
+  for (int i = n_s + lane; i < P; i += 32) ent[i] = 0ull;
+  __syncwarp();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = lane; t < (P >> 1); t += 32) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = ent[lo], b = ent[hi];
+        if ((a < b) == desc) { ent[lo] = b; ent[hi] = a; }
+      }
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < p.k; i += 32) {
+    const unsigned long long e = ent[i];
+    p.out_idx[q * p.k + i] = (int64_t)(0xffffffffu - (uint32_t)e) + p.index_offset;
+    if (p.out_val) p.out_val[q * p.k + i] = ord2f((uint32_t)(e >> 32));
+  }
+  if (lane == 0) atomicAdd(&p.counters[1], 1);
+}
+
+// ============================================================================ host side
+int sim_topk_splits(int64_t n_query, int64_t n_bank) {
+  const int sms = sm_count();
+  const int64_t qblocks = ceil_div(n_query, 128);
+  const int64_t tiles = ceil_div(n_bank, ST_BN);
+  int best = 1;
+  double best_eff = 0.0;
+  const int smax = (int)std::min<int64_t>(16, tiles);
+  for (int S = 1; S <= smax; ++S) {
+    const int64_t ctas = qblocks * S;
+    const double eff = (double)ctas / (double)(ceil_div(ctas, sms) * sms);
+    if (eff > best_eff * 1.02) { best_eff = eff; best = S; }
+  }
+  return best;
+}
+
+int tc_cap_for_k(int k) { return k <= 192 ? 256 : (k <= 896 ? 1024 : 0); }
+
+void tc_workspace(Arena& a, int64_t n_bank, int64_t n_query, int dim, int top_k, TcWorkspace& w) {
+  const int nkb = (dim + 63) / 64;
+  w.nkb = nkb;
+  w.q_pad = (int64_t)align_up((size_t)n_query, 128);
+  w.n_pad = (int64_t)align_up((size_t)n_bank, ST_BN);
+  w.S = sim_topk_splits(n_query, n_bank);
+  w.cap = tc_cap_for_k(top_k);
+  w.stats = a.take<uint32_t>(16);
+  w.qpack = a.take<uint8_t>(tilepack_bytes(w.q_pad, nkb * 64));
+  w.bpack = a.take<uint8_t>(tilepack_bytes(w.n_pad, nkb * 64));
+  w.q_nrm = a.take<float>((size_t)w.q_pad);
+  w.q_resid = a.take<float>((size_t)w.q_pad);
+  w.b_nrm = a.take<float>((size_t)w.n_pad);
+  w.b_resid = a.take<float>((size_t)w.n_pad);
+  w.cand = a.take<uint2>((size_t)w.q_pad * w.S * w.cap);
+  w.cand_cnt = a.take<int>((size_t)w.q_pad * w.S);
+  w.fb_list = a.take<int>((size_t)n_query);
+}
+
+int launch_pack_rows(const float* x, int64_t rows, int64_t rows_pad, int64_t ld, int dim, int nkb,
+                     uint8_t* packed, float* nrm, float* resid, uint32_t* stats, cudaStream_t st) {
+  const int wpb = 8;
+  pack_rows_kernel<<<(unsigned)ceil_div(rows_pad, wpb), wpb * 32, 0, st>>>(
+      x, rows, rows_pad, ld, dim, nkb, packed, nrm, resid, stats);
+  MCLST_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int top_k, float* dump,
+                    int64_t dump_ld, cudaStream_t st) {
+  SimParams p;
+  p.qpack = w.qpack; p.bpack = w.bpack; p.nkb = w.nkb; p.Q = n_query; p.N = n_bank;
+  p.tiles_total = (int)(w.n_pad / ST_BN); p.S = w.S; p.k = top_k;
+  p.q_resid = w.q_resid; p.bank_stats = w.stats; p.cand = w.cand; p.cand_cnt = w.cand_cnt;
+  p.dump = dump; p.dump_ld = dump_ld;
+  dim3 grid((unsigned)(w.q_pad / 128), (unsigned)w.S);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MCLST_CUDA(cudaFuncSetAttribute(sim_topk_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+    MCLST_CUDA(cudaFuncSetAttribute(sim_topk_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+    attr_set = true;
+  }
+  if (w.cap == 256) sim_topk_kernel<256><<<grid, ST_THREADS, ST_SMEM, st>>>(p);
+  else sim_topk_kernel<1024><<<grid, ST_THREADS, ST_SMEM, st>>>(p);
+  MCLST_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64_t ldb,
+                  const float* query, int64_t n_query, int64_t ldq, int dim, int top_k,
+                  int64_t index_offset, int64_t* out_idx, float* out_val, int* counters,
+                  cudaStream_t st) {
+  RerankParams p;
+  p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.S = w.S; p.cap = w.cap; p.k = top_k;
+  p.Q = n_query; p.N = n_bank; p.bank = bank; p.ldb = ldb; p.bank_nrm = w.b_nrm;
+  p.query = query; p.ldq = ldq; p.q_nrm = w.q_nrm; p.q_resid = w.q_resid;
+  p.bank_stats = w.stats; p.q_stats = w.stats + 8; p.dim = dim; p.index_offset = index_offset;
+  p.out_idx = out_idx; p.out_val = out_val; p.fb_list = w.fb_list; p.counters = counters;
+  // shared memory: per warp max(S*cap, pow2 >= RR_MAX... ) entries of 8 bytes
+  int per_warp = 1;
+  while (per_warp < w.S * w.cap) per_warp <<= 1;      // bitonic sort needs a power of two
+  int wpb = 4;
+  while (wpb > 1 && (size_t)wpb * per_warp * 8 > 160 * 1024) wpb >>= 1;
+  MCLST_REQUIRE((size_t)per_warp * 8 <= 200 * 1024, MCLST_ERR_UNSUPPORTED,
+                "rerank: S*cap = %d too large", per_warp);
+  const size_t smem = (size_t)wpb * per_warp * 8;
+  static size_t attr = 0;
+  if (smem > attr) {
+    MCLST_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)std::max<size_t>(smem, 48 * 1024)));
+    attr = smem;
+  }
+  rerank_kernel<<<(unsigned)ceil_div(n_query, wpb), 128, smem, st>>>(p, wpb, per_warp);
+  MCLST_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mclst

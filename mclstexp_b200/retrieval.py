@@ -199,3 +199,23 @@ def retrieve(spot_key: ArrayLike, expression_key: ArrayLike, image_query: ArrayL
     idx, val, emb, expr = retrieve_device(sk, ek, iq, top_k, mode, want_emb=True,
                                           out_dtype=torch.float64)
     return idx.cpu().numpy(), emb.cpu().numpy(), expr.cpu().numpy()
+
+
+def debug_similarity(spot_embeddings: ArrayLike, query_embeddings: ArrayLike) -> torch.Tensor:
+    """Testing aid: the raw similarities seen by the tensor-core candidate pass
+    (fp16-rounded normalised operands, fp32 accumulate) as a CUDA tensor [Q,N]."""
+    bank = _dev_f32(spot_embeddings)
+    qry = _dev_f32(query_embeddings, bank.device)
+    require_cuda(bank, qry)
+    lib = load()
+    N, D = bank.shape
+    Q = qry.shape[0]
+    nbytes = C.c_size_t()
+    check(lib.mclst_find_matches_workspace_bytes(N, Q, D, 1, 0, C.byref(nbytes)), "workspace")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=bank.device)
+    out = torch.full((Q, N), float("nan"), dtype=torch.float32, device=bank.device)
+    with torch.cuda.device(bank.device):
+        check(lib.mclst_debug_similarity(ptr(bank), N, bank.stride(0), ptr(qry), Q, qry.stride(0),
+                                         D, ptr(out), out.stride(0), ptr(ws), ws.numel(),
+                                         stream_ptr()), "debug_similarity")
+    return out

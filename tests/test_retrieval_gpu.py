@@ -103,8 +103,11 @@ def test_weighted_average_vs_reference_golden(golden_retrieval, name, tag, mode)
     idx = z[f"{name}/{tag}/indices"].astype(np.int64)
     emb, ex = retrieval.weighted_topk_average(bank, expr, qry, idx, mode=mode)
     assert emb.dtype == np.float64 and ex.dtype == np.float64
-    np.testing.assert_allclose(emb, z[f"{name}/{tag}/emb_pred"], rtol=RTOL, atol=1e-5)
-    np.testing.assert_allclose(ex, z[f"{name}/{tag}/expr_pred"], rtol=RTOL, atol=1e-6)
+    # bleep_exp exponentiates float32 squared distances ~5e2: the reference's own float32
+    # round-off is 1e-4-level there, so elements near zero get an absolute tolerance
+    a = 2e-4 if mode == "bleep_exp" else 1e-5
+    np.testing.assert_allclose(emb, z[f"{name}/{tag}/emb_pred"], rtol=RTOL, atol=a)
+    np.testing.assert_allclose(ex, z[f"{name}/{tag}/expr_pred"], rtol=RTOL, atol=a * 0.1)
 
 
 @pytest.mark.parametrize("mode", ["inv_sq_l1", "inv_sq_l2", "similarity", "uniform", "bleep_exp"])
@@ -117,8 +120,9 @@ def test_weighted_average_modes_and_layouts(mode, G, dtype):
     val, idx = oracle.find_matches_spec(bank, qry, k)
     emb, ex = retrieval.weighted_topk_average(bank, expr, qry, idx, mode=mode, values=val)
     emb64, ex64 = oracle.weighted_average_spec(bank, expr, qry, idx, mode, val)
-    np.testing.assert_allclose(emb, emb64, rtol=RTOL, atol=1e-5)
-    np.testing.assert_allclose(ex, ex64, rtol=RTOL, atol=1e-6)
+    a = 2e-4 if mode == "bleep_exp" else 1e-5
+    np.testing.assert_allclose(emb, emb64, rtol=RTOL, atol=a)
+    np.testing.assert_allclose(ex, ex64, rtol=RTOL, atol=a * 0.1)
 
 
 def test_weighted_average_zero_distance_defined():
