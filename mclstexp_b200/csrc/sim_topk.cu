@@ -25,6 +25,7 @@
 // Rows for which the band overflows the candidate buffer (massive ties, pathological
 // clustering) are flagged and recomputed by the exact brute-force kernel.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "retrieval.cuh"
 #include "umma.cuh"
@@ -110,11 +111,16 @@ struct SimParams {
 
 // Warp-cooperative prune of the candidate buffers of every lane with need == true:
 // new threshold = (lower bound of the k-th best kept score) - e2; entries at or below it
-// are dropped.  Leaves the buffer compacted in ascending bank index.
+// are dropped.  Leaves the buffer compacted in ascending bank index.  Deliberately NOT
+// inlined: it runs once per ~10 tiles and inlining it 8x made the epilogue spill out of the
+// instruction cache (ncu: 57% stall_no_inst in the first version).
+struct PruneState { int cnt; float thr; int flagged; };
+
 template <int CAP>
-__device__ __forceinline__ void warp_prune(uint2* my_buf, int& cnt, float& thr, bool& flagged,
-                                           bool need, int k, float e2, int lane) {
+__device__ __noinline__ PruneState warp_prune(uint2* my_buf, int cnt, float thr, int flagged,
+                                              bool need, int k, float e2) {
   constexpr int EPL = CAP / 32;
+  const int lane = threadIdx.x & 31;
   unsigned mask = __ballot_sync(0xffffffffu, need);
   while (mask) {
     const int L = __ffs(mask) - 1;
@@ -164,14 +170,46 @@ __device__ __forceinline__ void warp_prune(uint2* my_buf, int& cnt, float& thr, 
       cnt = out;
       thr = new_thr;
       if (out > CAP - 64) {            // band denser than the buffer: give the row to the exact path
-        flagged = true;
+        flagged = 1;
         thr = __int_as_float(0x7f800000);
       }
     }
   }
+  PruneState r;
+  r.cnt = cnt; r.thr = thr; r.flagged = flagged;
+  return r;
 }
 
+// One 32-column chunk of one query row: append every similarity above the running threshold.
 template <int CAP>
+__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint2* my_buf, int& cnt,
+                                             float& thr, int& flagged, uint32_t nb, int n_left,
+                                             int k, float e2) {
+  float m = __uint_as_float(v[0]);
+#pragma unroll
+  for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+  if (m > thr) {
+    if (n_left >= 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (__uint_as_float(v[j]) > thr) my_buf[cnt++] = make_uint2(v[j], nb + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (__uint_as_float(v[j]) > thr && j < n_left) my_buf[cnt++] = make_uint2(v[j], nb + j);
+    }
+  }
+  const bool need = cnt > CAP - 32;
+  if (__any_sync(0xffffffffu, need)) {
+    const PruneState ps = warp_prune<CAP>(my_buf, cnt, thr, flagged, need, k, e2);
+    cnt = ps.cnt; thr = ps.thr; flagged = ps.flagged;
+  }
+}
+
+// CL = cluster size along the query-block axis: the CL CTAs of a cluster stream the same bank
+// tiles in lockstep; each loads 1/CL of every stage and multicasts it to all of them, so the
+// L2 -> SM traffic per similarity drops by CL.
+template <int CAP, int CL>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 sim_topk_kernel(const SimParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -190,9 +228,11 @@ sim_topk_kernel(const SimParams p) {
   const int nkb = p.nkb;
   const int t0 = (int)(((int64_t)p.tiles_total * s) / p.S);
   const int t1 = (int)(((int64_t)p.tiles_total * (s + 1)) / p.S);
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < ST_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < ST_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], CL); }
     mbar_init(bar_a, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
     fence_mbar_init();
@@ -200,6 +240,7 @@ sim_topk_kernel(const SimParams p) {
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();        // peers' barriers must exist before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -212,6 +253,7 @@ sim_topk_kernel(const SimParams p) {
         bulk_g2s(sA + kb * TP_SLICE_BYTES,
                  p.qpack + ((size_t)qb * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES, bar_a);
       uint32_t stage = 0, phase = 0;
+      constexpr uint32_t kShare = ST_STAGE_BYTES / CL;          // bytes this CTA fetches per stage
       for (int t = t0; t < t1; ++t) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bar_empty[stage], phase ^ 1);
@@ -219,8 +261,16 @@ sim_topk_kernel(const SimParams p) {
           uint8_t* dst = sB + stage * ST_STAGE_BYTES;
           const uint8_t* src0 = p.bpack + ((size_t)(2 * t) * nkb + kb) * TP_SLICE_BYTES;
           const uint8_t* src1 = p.bpack + ((size_t)(2 * t + 1) * nkb + kb) * TP_SLICE_BYTES;
-          bulk_g2s_hint(dst, src0, TP_SLICE_BYTES, &bar_full[stage], pol_keep);
-          bulk_g2s_hint(dst + TP_SLICE_BYTES, src1, TP_SLICE_BYTES, &bar_full[stage], pol_keep);
+          if (CL == 1) {
+            bulk_g2s_hint(dst, src0, TP_SLICE_BYTES, &bar_full[stage], pol_keep);
+            bulk_g2s_hint(dst + TP_SLICE_BYTES, src1, TP_SLICE_BYTES, &bar_full[stage], pol_keep);
+          } else {
+            // stage image = [slice of row-block 2t | slice of row-block 2t+1]; this CTA's share
+            const uint32_t off = crank * kShare;
+            const uint8_t* src = (off < (uint32_t)TP_SLICE_BYTES) ? src0 + off
+                                                                   : src1 + (off - TP_SLICE_BYTES);
+            bulk_g2s_mcast(dst + off, src, kShare, &bar_full[stage], kMask, pol_keep);
+          }
           if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -249,7 +299,8 @@ sim_topk_kernel(const SimParams p) {
             const uint64_t bd = make_smem_desc_sw128(b_base + stage * ST_STAGE_BYTES + k4 * 32);
             mma_f16_ss(d_tmem, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
           }
-          mma_commit(&bar_empty[stage]);
+          if (CL == 1) mma_commit(&bar_empty[stage]);
+          else mma_commit_mcast(&bar_empty[stage], kMask);
           if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
         }
         mma_commit(&bar_tfull[buf]);
@@ -268,10 +319,11 @@ sim_topk_kernel(const SimParams p) {
     const float e2 = 2.02f * eps;
     float thr = q_valid ? __int_as_float(0xff800000) : __int_as_float(0x7f800000);
     int cnt = 0;
-    bool flagged = false;
+    int flagged = 0;
     const int k = p.k;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     int it = 0;
+#pragma unroll 1
     for (int t = t0; t < t1; ++t, ++it) {
       const int buf = it & 1;
       mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
@@ -281,44 +333,32 @@ sim_topk_kernel(const SimParams p) {
       const int n_valid = (int)min((int64_t)ST_BN, p.N - tile_base);   // < 256 only in the last tile
       uint32_t va[32], vb[32];
       tmem_ld_32x32(taddr, va);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t (&v)[32] = (c & 1) ? vb : va;
+#pragma unroll 1
+      for (int c = 0; c < 8; c += 2) {
         tmem_ld_wait();
-        if (c < 7) {
-          if (c & 1) tmem_ld_32x32(taddr + (c + 1) * 32, va);
-          else tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+        tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+        if (p.dump != nullptr && q_valid) {
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < n_valid) p.dump[q * p.dump_ld + tile_base + c * 32 + j] = __uint_as_float(va[j]);
+        }
+        filter_chunk<CAP>(va, my_buf, cnt, thr, flagged, (uint32_t)(tile_base + c * 32),
+                          n_valid - c * 32, k, e2);
+        tmem_ld_wait();
+        if (c < 6) {
+          tmem_ld_32x32(taddr + (c + 2) * 32, va);
         } else {
           // all 256 columns are in registers: hand the accumulator back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_tempty[buf]);
         }
-        const int col0 = c * 32;
         if (p.dump != nullptr && q_valid) {
-#pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < n_valid) p.dump[q * p.dump_ld + tile_base + col0 + j] = __uint_as_float(v[j]);
+            if ((c + 1) * 32 + j < n_valid)
+              p.dump[q * p.dump_ld + tile_base + (c + 1) * 32 + j] = __uint_as_float(vb[j]);
         }
-        bool any = false;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) any |= (__uint_as_float(v[j]) > thr);
-        if (any) {
-          const uint32_t nb = (uint32_t)(tile_base + col0);
-          if (col0 + 32 <= n_valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (__uint_as_float(v[j]) > thr) my_buf[cnt++] = make_uint2(v[j], nb + j);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (__uint_as_float(v[j]) > thr && col0 + j < n_valid)
-                my_buf[cnt++] = make_uint2(v[j], nb + j);
-          }
-        }
-        const bool need = cnt > CAP - 32;
-        if (__any_sync(0xffffffffu, need))
-          warp_prune<CAP>(my_buf, cnt, thr, flagged, need, k, e2, lane);
+        filter_chunk<CAP>(vb, my_buf, cnt, thr, flagged, (uint32_t)(tile_base + (c + 1) * 32),
+                          n_valid - (c + 1) * 32, k, e2);
       }
     }
     if (q_valid) p.cand_cnt[(size_t)q * p.S + s] = flagged ? -1 : cnt;
@@ -326,6 +366,7 @@ sim_topk_kernel(const SimParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();        // nobody leaves while peers may still multicast into it
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -450,9 +491,20 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
 }
 
 // ============================================================================ host side
-int sim_topk_splits(int64_t n_query, int64_t n_bank) {
-  const int sms = sm_count();
+int sim_topk_cluster(int64_t n_query) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("MCLST_SIM_CLUSTER");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 1 || forced == 2 || forced == 4) return forced;
   const int64_t qblocks = ceil_div(n_query, 128);
+  return qblocks >= 8 ? 2 : 1;
+}
+
+int sim_topk_splits(int64_t n_query, int64_t n_bank, int cluster) {
+  const int sms = sm_count();
+  const int64_t qblocks = ceil_div(ceil_div(n_query, 128), cluster) * cluster;
   const int64_t tiles = ceil_div(n_bank, ST_BN);
   int best = 1;
   double best_eff = 0.0;
@@ -470,9 +522,10 @@ int tc_cap_for_k(int k) { return k <= 192 ? 256 : (k <= 896 ? 1024 : 0); }
 void tc_workspace(Arena& a, int64_t n_bank, int64_t n_query, int dim, int top_k, TcWorkspace& w) {
   const int nkb = (dim + 63) / 64;
   w.nkb = nkb;
-  w.q_pad = (int64_t)align_up((size_t)n_query, 128);
+  w.cluster = sim_topk_cluster(n_query);
+  w.q_pad = (int64_t)align_up((size_t)n_query, 128 * w.cluster);
   w.n_pad = (int64_t)align_up((size_t)n_bank, ST_BN);
-  w.S = sim_topk_splits(n_query, n_bank);
+  w.S = sim_topk_splits(n_query, n_bank, w.cluster);
   w.cap = tc_cap_for_k(top_k);
   w.stats = a.take<uint32_t>(16);
   w.qpack = a.take<uint8_t>(tilepack_bytes(w.q_pad, nkb * 64));
@@ -495,6 +548,31 @@ int launch_pack_rows(const float* x, int64_t rows, int64_t rows_pad, int64_t ld,
   return 0;
 }
 
+template <int CAP, int CL>
+static int launch_sim_topk_t(const SimParams& p, dim3 grid, cudaStream_t st) {
+  auto kern = sim_topk_kernel<CAP, CL>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MCLST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(ST_THREADS);
+  cfg.dynamicSmemBytes = ST_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MCLST_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  MCLST_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int top_k, float* dump,
                     int64_t dump_ld, cudaStream_t st) {
   SimParams p;
@@ -503,16 +581,16 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
   p.q_resid = w.q_resid; p.bank_stats = w.stats; p.cand = w.cand; p.cand_cnt = w.cand_cnt;
   p.dump = dump; p.dump_ld = dump_ld;
   dim3 grid((unsigned)(w.q_pad / 128), (unsigned)w.S);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MCLST_CUDA(cudaFuncSetAttribute(sim_topk_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
-    MCLST_CUDA(cudaFuncSetAttribute(sim_topk_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
-    attr_set = true;
+  const int key = w.cap * 10 + w.cluster;
+  switch (key) {
+    case 2561: return launch_sim_topk_t<256, 1>(p, grid, st);
+    case 2562: return launch_sim_topk_t<256, 2>(p, grid, st);
+    case 2564: return launch_sim_topk_t<256, 4>(p, grid, st);
+    case 10241: return launch_sim_topk_t<1024, 1>(p, grid, st);
+    case 10242: return launch_sim_topk_t<1024, 2>(p, grid, st);
+    case 10244: return launch_sim_topk_t<1024, 4>(p, grid, st);
   }
-  if (w.cap == 256) sim_topk_kernel<256><<<grid, ST_THREADS, ST_SMEM, st>>>(p);
-  else sim_topk_kernel<1024><<<grid, ST_THREADS, ST_SMEM, st>>>(p);
-  MCLST_LAUNCH_CHECK();
-  return 0;
+  MCLST_REQUIRE(false, MCLST_ERR_UNSUPPORTED, "sim_topk: cap %d cluster %d", w.cap, w.cluster);
 }
 
 int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64_t ldb,
