@@ -58,8 +58,8 @@ struct FmWorkspace {
   int* counters;
   bool use_tc;
   TcWorkspace tc;
-  float* bank_nrm;
-  float* q_nrm;
+  double* bank_nrm;
+  double* q_nrm;
   float* scratch;
   size_t bytes;
 };
@@ -81,8 +81,8 @@ static FmWorkspace carve_fm(void* ws, size_t cap, int64_t n_bank, int64_t n_quer
     w.bank_nrm = w.tc.b_nrm;
     w.q_nrm = w.tc.q_nrm;
   } else {
-    w.bank_nrm = a.take<float>((size_t)n_bank);
-    w.q_nrm = a.take<float>((size_t)n_query);
+    w.bank_nrm = a.take<double>((size_t)n_bank);
+    w.q_nrm = a.take<double>((size_t)n_query);
   }
   w.scratch = a.take<float>(exact_topk_scratch_floats(n_bank, n_query));
   w.bytes = align_up(a.off, 256);

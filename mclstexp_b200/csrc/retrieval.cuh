@@ -4,25 +4,27 @@
 
 namespace mclst {
 
-int launch_row_norms(const float* x, int64_t rows, int64_t ld, int dim, float* nrm, cudaStream_t st);
+int launch_row_norms(const float* x, int64_t rows, int64_t ld, int dim, double* nrm, cudaStream_t st);
 
 int exact_topk_ctas(int64_t n_bank, int64_t n_query);
 size_t exact_topk_scratch_floats(int64_t n_bank, int64_t n_query);
 // qlist/qcount_ptr (device) select a subset of queries; when both are null queries
 // 0..qcount-1 are processed.  n_query_cap bounds the subset size (grid / scratch sizing).
-int launch_exact_topk(const float* bank, int64_t N, int64_t ldb, const float* bank_nrm,
-                      const float* query, int64_t ldq, const float* q_nrm, int dim,
+int launch_exact_topk(const float* bank, int64_t N, int64_t ldb, const double* bank_nrm,
+                      const float* query, int64_t ldq, const double* q_nrm, int dim,
                       const int* qlist, const int* qcount_ptr, int qcount, int64_t n_query_cap,
                       int k, int64_t index_offset, float* scratch, int64_t* out_idx,
                       float* out_val, cudaStream_t st);
 
 // ---- tensor-core candidate path (sim_topk.cu)
 struct TcWorkspace {
-  int nkb, S, cap, cluster;
+  int nkb, S, SS, cap, cluster, epw;   // SS = S * (epw / 4) candidate streams per query
   int64_t q_pad, n_pad;
   uint32_t* stats;          // [0..7] bank: max residual bits, non-finite flag; [8..15] queries
   uint8_t *qpack, *bpack;
-  float *q_nrm, *q_resid, *b_nrm, *b_resid;
+  double *q_nrm, *b_nrm;
+  float *q_resid, *b_resid;
+  uint32_t* gthr;
   uint2* cand;
   int* cand_cnt;
   int* fb_list;
@@ -30,7 +32,7 @@ struct TcWorkspace {
 int tc_cap_for_k(int k);
 void tc_workspace(Arena& a, int64_t n_bank, int64_t n_query, int dim, int top_k, TcWorkspace& w);
 int launch_pack_rows(const float* x, int64_t rows, int64_t rows_pad, int64_t ld, int dim, int nkb,
-                     uint8_t* packed, float* nrm, float* resid, uint32_t* stats, cudaStream_t st);
+                     uint8_t* packed, double* nrm, float* resid, uint32_t* stats, cudaStream_t st);
 int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int top_k, float* dump,
                     int64_t dump_ld, cudaStream_t st);
 int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64_t ldb,

@@ -3,10 +3,10 @@
 // the device, and the fallback for queries the tensor-core candidate pass cannot
 // certify (sim_topk.cu).
 //
-//   key(q, s) = float32( sum_d  double(q_d / nq) * double(s_d / ns) )
+//   key(q, s) = float32( (sum_d double(q_d) * double(s_d)) / (nq * ns) )
 //
-// with nq, ns = max(float32(sqrt(sum_d double(x_d)^2)), 1e-12)  (F.normalize, eps
-// 1e-12).  Ranking is (key descending, bank index ascending).  NaN ranks largest
+// with nq, ns = max(sqrt(sum_d double(x_d)^2), 1e-12) in float64 (F.normalize's eps 1e-12
+// clamp): the float64 cosine of the raw float32 rows, rounded once to float32.  Ranking is (key descending, bank index ascending).  NaN ranks largest
 // (ATen topk semantics).  See oracle/oracle.py::find_matches_spec.
 #include "common.cuh"
 #include "retrieval.cuh"
@@ -16,7 +16,7 @@ namespace mclst {
 // ---------------------------------------------------------------- row norms
 __global__ void __launch_bounds__(256)
 row_norm_kernel(const float* __restrict__ x, int64_t rows, int64_t ld, int dim,
-                float* __restrict__ nrm) {
+                double* __restrict__ nrm) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -27,10 +27,10 @@ row_norm_kernel(const float* __restrict__ x, int64_t rows, int64_t ld, int dim,
     ss = fma(v, v, ss);
   }
   ss = warp_sum(ss);
-  if (lane == 0) nrm[r] = fmaxf((float)sqrt(ss), 1e-12f);
+  if (lane == 0) nrm[r] = fmax(sqrt(ss), 1e-12);
 }
 
-int launch_row_norms(const float* x, int64_t rows, int64_t ld, int dim, float* nrm,
+int launch_row_norms(const float* x, int64_t rows, int64_t ld, int dim, double* nrm,
                      cudaStream_t st) {
   if (rows == 0) return 0;
   const int wpb = 8;
@@ -147,14 +147,14 @@ __device__ void block_select_topk(const float* __restrict__ scores, int64_t N, i
 template <int QB>
 __global__ void __launch_bounds__(EX_THREADS)
 exact_topk_kernel(const float* __restrict__ bank, int64_t N, int64_t ldb,
-                  const float* __restrict__ bank_nrm,
+                  const double* __restrict__ bank_nrm,
                   const float* __restrict__ query, int64_t ldq,
-                  const float* __restrict__ q_nrm, int dim,
+                  const double* __restrict__ q_nrm, int dim,
                   const int* __restrict__ qlist, const int* __restrict__ qcount_ptr, int qcount,
                   int k, int64_t index_offset, float* __restrict__ scratch, int64_t n_pad,
                   int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* qd = reinterpret_cast<double*>(smem_raw);                       // [QB][dim]
+  double* qd = reinterpret_cast<double*>(smem_raw);                       // [QB][dim] raw query rows
   unsigned long long* sel = reinterpret_cast<unsigned long long*>(qd + (size_t)QB * dim);
   int* hist = reinterpret_cast<int*>(sel + EX_KMAX);
   int* sh = hist + 256;
@@ -163,18 +163,19 @@ exact_topk_kernel(const float* __restrict__ bank, int64_t N, int64_t ldb,
   float* my_scratch = scratch + (size_t)blockIdx.x * QB * n_pad;
   for (int g = blockIdx.x; g * QB < nq; g += gridDim.x) {
     int qs[QB];
+    double qn[QB];
 #pragma unroll
     for (int j = 0; j < QB; ++j) {
       const int slot = g * QB + j;
       qs[j] = slot < nq ? (qlist ? qlist[slot] : slot) : -1;
+      qn[j] = qs[j] >= 0 ? q_nrm[qs[j]] : 1.0;
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < QB; ++j) {
       if (qs[j] >= 0) {
-        const float nq_ = q_nrm[qs[j]];
         for (int d = tid; d < dim; d += EX_THREADS)
-          qd[j * dim + d] = (double)__fdiv_rn(query[(int64_t)qs[j] * ldq + d], nq_);
+          qd[j * dim + d] = (double)query[(int64_t)qs[j] * ldq + d];
       } else {
         for (int d = tid; d < dim; d += EX_THREADS) qd[j * dim + d] = 0.0;
       }
@@ -182,19 +183,19 @@ exact_topk_kernel(const float* __restrict__ bank, int64_t N, int64_t ldb,
     __syncthreads();
     for (int64_t r = warp; r < N; r += EX_THREADS / 32) {
       const float* p = bank + r * ldb;
-      const float bn = bank_nrm[r];
+      const double bn = bank_nrm[r];
       double acc[QB];
 #pragma unroll
       for (int j = 0; j < QB; ++j) acc[j] = 0.0;
       for (int d = lane; d < dim; d += 32) {
-        const double s = (double)__fdiv_rn(__ldg(p + d), bn);
+        const double s = (double)__ldg(p + d);
 #pragma unroll
         for (int j = 0; j < QB; ++j) acc[j] = fma(s, qd[j * dim + d], acc[j]);
       }
 #pragma unroll
       for (int j = 0; j < QB; ++j) {
         const double v = warp_sum(acc[j]);
-        if (lane == 0) my_scratch[(size_t)j * n_pad + r] = (float)v;
+        if (lane == 0) my_scratch[(size_t)j * n_pad + r] = (float)(v / (qn[j] * bn));
       }
     }
     __syncthreads();
@@ -224,8 +225,8 @@ size_t exact_topk_scratch_floats(int64_t n_bank, int64_t n_query) {
   return (size_t)exact_topk_ctas(n_bank, n_query) * EX_QB * align_up((size_t)n_bank, 64);
 }
 
-int launch_exact_topk(const float* bank, int64_t N, int64_t ldb, const float* bank_nrm,
-                      const float* query, int64_t ldq, const float* q_nrm, int dim,
+int launch_exact_topk(const float* bank, int64_t N, int64_t ldb, const double* bank_nrm,
+                      const float* query, int64_t ldq, const double* q_nrm, int dim,
                       const int* qlist, const int* qcount_ptr, int qcount, int64_t n_query_cap,
                       int k, int64_t index_offset, float* scratch, int64_t* out_idx,
                       float* out_val, cudaStream_t st) {

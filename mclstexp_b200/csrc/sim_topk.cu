@@ -39,9 +39,11 @@ using namespace ptx;
 constexpr float E_ACC = 2.0e-6f;
 
 // ============================================================================ pack_rows
+// One warp per row, dim <= 256: lane l owns elements 8l..8l+7 (one 16-byte fp16 chunk).
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t rows_pad, int64_t ld, int dim,
-                 int nkb, uint8_t* __restrict__ packed, float* __restrict__ nrm,
+                 int nkb, uint8_t* __restrict__ packed, double* __restrict__ nrm,
                  float* __restrict__ resid, uint32_t* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -52,15 +54,25 @@ pack_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t rows_pad, in
   for (int i = 0; i < 8; ++i) v[i] = 0.f;
   if (r < rows && lane < nchunks) {
     const float* p = x + r * ld + lane * 8;
+    if (VEC) {                               // dim % 8 == 0, 16-byte aligned rows
+      if (lane * 8 < dim) {
+        const float4 a = ldg_stream(reinterpret_cast<const float4*>(p));
+        const float4 b = ldg_stream(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      }
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (lane * 8 + i < dim) v[i] = __ldg(p + i);
+      for (int i = 0; i < 8; ++i)
+        if (lane * 8 + i < dim) v[i] = __ldg(p + i);
+    }
   }
   double ss = 0.0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) ss = fma((double)v[i], (double)v[i], ss);
   ss = warp_sum(ss);
-  const float n = fmaxf((float)sqrt(ss), 1e-12f);
+  const double n64 = fmax(sqrt(ss), 1e-12);
+  const float n = (float)n64;
   float res = 0.f;
   uint32_t h2[4];
 #pragma unroll
@@ -78,7 +90,7 @@ pack_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t rows_pad, in
         make_uint4(h2[0], h2[1], h2[2], h2[3]);
   if (lane == 0) {
     const float rr = (r < rows) ? sqrtf(res) * 1.00001f + 1e-12f : 0.f;
-    nrm[r] = n;
+    nrm[r] = n64;
     resid[r] = rr;
     if (r < rows) {
       atomicMax(&stats[0], __float_as_uint(rr));
@@ -88,7 +100,6 @@ pack_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t rows_pad, in
 }
 
 // ============================================================================ sim_topk
-constexpr int ST_THREADS = 192;
 constexpr int ST_STAGES = 4;
 constexpr int ST_BN = 256;                      // bank rows per tile (TMEM columns)
 constexpr int ST_STAGE_BYTES = 2 * TP_SLICE_BYTES;   // 256 rows x 64 halves
@@ -103,11 +114,19 @@ struct SimParams {
   int tiles_total, S, k;
   const float* q_resid;
   const uint32_t* bank_stats;
-  uint2* cand;
-  int* cand_cnt;
+  uint2* cand;          // [q_pad][S * CP][CAP]  (approx score bits, bank row)
+  int* cand_cnt;        // [q_pad][S * CP]       (-1: overflow, row goes to the exact path)
+  uint32_t* gthr;       // [q_pad] running per-query threshold shared by all streams (ordered key, 0 = none)
   float* dump;          // debug: raw similarities [Q, dump_ld]
   int64_t dump_ld;
+  int ablate;           // timing experiments only (MCLST_SIM_ABLATE): 1 = load TMEM but do not filter, 2 = do not even load
 };
+
+// eps: |tensor-core score - exact cosine| for a pair with fp16 residual norms rq, rs
+// (Cauchy-Schwarz on the operand rounding) + accumulation bound + fp32 normalisation slack.
+__device__ __forceinline__ float pair_eps(float rq, float rs) {
+  return 1.002f * (rq + rs) + E_ACC + 1e-6f;
+}
 
 // Warp-cooperative prune of the candidate buffers of every lane with need == true:
 // new threshold = (lower bound of the k-th best kept score) - e2; entries at or below it
@@ -117,8 +136,8 @@ struct SimParams {
 struct PruneState { int cnt; float thr; int flagged; };
 
 template <int CAP>
-__device__ __noinline__ PruneState warp_prune(uint2* my_buf, int cnt, float thr, int flagged,
-                                              bool need, int k, float e2) {
+__device__ __noinline__ PruneState warp_prune(uint2* my_buf, uint32_t* my_gthr, int cnt, float thr,
+                                              int flagged, bool need, int k, float e2) {
   constexpr int EPL = CAP / 32;
   const int lane = threadIdx.x & 31;
   unsigned mask = __ballot_sync(0xffffffffu, need);
@@ -153,9 +172,15 @@ __device__ __noinline__ PruneState warp_prune(uint2* my_buf, int cnt, float thr,
       c = __reduce_add_sync(0xffffffffu, c);
       if (c >= k) T = cand;
     }
-    // T <= key of the k-th best (low 8 bits cleared): conservative lower bound
-    const float new_thr = ord2f(T) - le2;
-    __syncwarp();
+    // T <= key of the k-th best (low 8 bits cleared): conservative lower bound.  Publish it
+    // and adopt whatever better bound another stream of the same query already found.
+    float new_thr = ord2f(T) - le2;
+    if (lane == L) {
+      const uint32_t mine = f2ord(new_thr);
+      const uint32_t old = atomicMax(my_gthr, mine);
+      if (old > mine) new_thr = ord2f(old);
+    }
+    new_thr = __shfl_sync(0xffffffffu, new_thr, L);
     int out = 0;
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
@@ -181,37 +206,51 @@ __device__ __noinline__ PruneState warp_prune(uint2* my_buf, int cnt, float thr,
 }
 
 // One 32-column chunk of one query row: append every similarity above the running threshold.
+// Two-level test (chunk max, then 8-wide group max) keeps the common "one survivor in the
+// warp" case at ~25 instructions.
 template <int CAP>
-__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint2* my_buf, int& cnt,
-                                             float& thr, int& flagged, uint32_t nb, int n_left,
-                                             int k, float e2) {
-  float m = __uint_as_float(v[0]);
+__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint2* my_buf,
+                                             uint32_t* my_gthr, int& cnt, float& thr, int& flagged,
+                                             uint32_t nb, int n_left, int k, float e2) {
+  float g[4];
 #pragma unroll
-  for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-  if (m > thr) {
-    if (n_left >= 32) {
+  for (int h = 0; h < 4; ++h) {
+    float m = __uint_as_float(v[8 * h]);
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (__uint_as_float(v[j]) > thr) my_buf[cnt++] = make_uint2(v[j], nb + j);
-    } else {
+    for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(v[8 * h + j]));
+    g[h] = m;
+  }
+  if (fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])) > thr) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (__uint_as_float(v[j]) > thr && j < n_left) my_buf[cnt++] = make_uint2(v[j], nb + j);
+    for (int h = 0; h < 4; ++h) {
+      if (g[h] > thr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (__uint_as_float(v[8 * h + j]) > thr && 8 * h + j < n_left)
+            my_buf[cnt++] = make_uint2(v[8 * h + j], nb + 8 * h + j);
+      }
     }
   }
   const bool need = cnt > CAP - 32;
   if (__any_sync(0xffffffffu, need)) {
-    const PruneState ps = warp_prune<CAP>(my_buf, cnt, thr, flagged, need, k, e2);
+    const PruneState ps = warp_prune<CAP>(my_buf, my_gthr, cnt, thr, flagged, need, k, e2);
     cnt = ps.cnt; thr = ps.thr; flagged = ps.flagged;
   }
 }
 
-// CL = cluster size along the query-block axis: the CL CTAs of a cluster stream the same bank
-// tiles in lockstep; each loads 1/CL of every stage and multicasts it to all of them, so the
-// L2 -> SM traffic per similarity drops by CL.
-template <int CAP, int CL>
-__global__ void __launch_bounds__(ST_THREADS, 1)
+// CL  = cluster size along the query-block axis: the CL CTAs of a cluster stream the same bank
+//       tiles in lockstep; each loads 1/CL of every stage and multicasts it to all of them.
+// EPW = epilogue warps (4, 8 or 16).  TMEM lanes can only be read by the warp whose id % 4
+//       matches the lane quadrant, so EPW/4 warps share a quadrant and split the 256 columns
+//       of a tile between them; each (query, column part) is its own candidate stream.  One
+//       epilogue warp per scheduler cannot hide its own dependent-issue latency (ncu on the
+//       4-warp version: epilogue-bound at 25% issue utilisation), hence 8 by default.
+template <int CAP, int CL, int EPW>
+__global__ void __launch_bounds__(64 + 32 * EPW, 1)
 sim_topk_kernel(const SimParams p) {
+  constexpr int CP = EPW / 4;              // column parts per tile
+  constexpr int PART_COLS = ST_BN / CP;
+  constexpr int NCH = PART_COLS / 32;      // 32-column chunks per thread per tile (>= 2)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -234,7 +273,7 @@ sim_topk_kernel(const SimParams p) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < ST_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], CL); }
     mbar_init(bar_a, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], EPW); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -309,45 +348,59 @@ sim_topk_kernel(const SimParams p) {
   } else {
     // ------------------------------------------------------------ epilogue: threshold filter
     const int quad = warp & 3;
+    const int part = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const int64_t q = (int64_t)qb * 128 + row;
     const bool q_valid = q < p.Q;
-    uint2* my_buf = p.cand + ((size_t)q * p.S + s) * CAP;
+    const int SS = p.S * CP;
+    const int stream = s * CP + part;
+    uint2* my_buf = p.cand + ((size_t)q * SS + stream) * CAP;
+    uint32_t* my_gthr = p.gthr + q;
     const float rs_max = __uint_as_float(p.bank_stats[0]);
     const float rq = q_valid ? p.q_resid[q] : 0.f;
-    const float eps = 1.002f * (rq + rs_max) + E_ACC + 2e-7f;
-    const float e2 = 2.02f * eps;
+    const float e2 = 2.02f * pair_eps(rq, rs_max);
     float thr = q_valid ? __int_as_float(0xff800000) : __int_as_float(0x7f800000);
     int cnt = 0;
     int flagged = 0;
     const int k = p.k;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + part * PART_COLS;
     int it = 0;
 #pragma unroll 1
     for (int t = t0; t < t1; ++t, ++it) {
       const int buf = it & 1;
+      // adopt the best threshold any other stream of this query has published so far
+      const uint32_t gk = q_valid ? *reinterpret_cast<volatile uint32_t*>(my_gthr) : 0u;
       mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
       tc_fence_after();
+      if (gk != 0u) thr = fmaxf(thr, ord2f(gk));
       const uint32_t taddr = t_lane + buf * ST_BN;
-      const int64_t tile_base = (int64_t)t * ST_BN;
-      const int n_valid = (int)min((int64_t)ST_BN, p.N - tile_base);   // < 256 only in the last tile
+      const int64_t col_base = (int64_t)t * ST_BN + part * PART_COLS;
+      const int n_valid = (int)min((int64_t)PART_COLS, p.N - col_base);   // < PART_COLS only at the bank tail
       uint32_t va[32], vb[32];
+      if (p.ablate == 2) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[buf]);
+        continue;
+      }
       tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-      for (int c = 0; c < 8; c += 2) {
+      for (int c = 0; c < NCH; c += 2) {
         tmem_ld_wait();
         tmem_ld_32x32(taddr + (c + 1) * 32, vb);
         if (p.dump != nullptr && q_valid) {
           for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < n_valid) p.dump[q * p.dump_ld + tile_base + c * 32 + j] = __uint_as_float(va[j]);
+            if (c * 32 + j < n_valid) p.dump[q * p.dump_ld + col_base + c * 32 + j] = __uint_as_float(va[j]);
         }
-        filter_chunk<CAP>(va, my_buf, cnt, thr, flagged, (uint32_t)(tile_base + c * 32),
-                          n_valid - c * 32, k, e2);
+        if (p.ablate == 0)
+          filter_chunk<CAP>(va, my_buf, my_gthr, cnt, thr, flagged, (uint32_t)(col_base + c * 32),
+                            n_valid - c * 32, k, e2);
+        else if (va[lane] == 0x12345678u) cnt++;
         tmem_ld_wait();
-        if (c < 6) {
+        if (c + 2 < NCH) {
           tmem_ld_32x32(taddr + (c + 2) * 32, va);
         } else {
-          // all 256 columns are in registers: hand the accumulator back to the MMA warp
+          // this warp's columns are in registers: hand the accumulator back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_tempty[buf]);
@@ -355,13 +408,15 @@ sim_topk_kernel(const SimParams p) {
         if (p.dump != nullptr && q_valid) {
           for (int j = 0; j < 32; ++j)
             if ((c + 1) * 32 + j < n_valid)
-              p.dump[q * p.dump_ld + tile_base + (c + 1) * 32 + j] = __uint_as_float(vb[j]);
+              p.dump[q * p.dump_ld + col_base + (c + 1) * 32 + j] = __uint_as_float(vb[j]);
         }
-        filter_chunk<CAP>(vb, my_buf, cnt, thr, flagged, (uint32_t)(tile_base + (c + 1) * 32),
-                          n_valid - (c + 1) * 32, k, e2);
+        if (p.ablate == 0)
+          filter_chunk<CAP>(vb, my_buf, my_gthr, cnt, thr, flagged,
+                            (uint32_t)(col_base + (c + 1) * 32), n_valid - (c + 1) * 32, k, e2);
+        else if (vb[lane] == 0x12345678u) cnt++;
       }
     }
-    if (q_valid) p.cand_cnt[(size_t)q * p.S + s] = flagged ? -1 : cnt;
+    if (q_valid) p.cand_cnt[(size_t)q * SS + stream] = flagged ? -1 : cnt;
   }
 
   tc_fence_before();
@@ -376,17 +431,42 @@ constexpr int RR_MAX = 1024;     // most survivors re-ranked exactly per query
 struct RerankParams {
   const uint2* cand;
   const int* cand_cnt;
-  int S, cap, k;
+  int SS, cap, k;               // SS = candidate streams per query
   int64_t Q, N;
-  const float* bank; int64_t ldb; const float* bank_nrm;
-  const float* query; int64_t ldq; const float* q_nrm; const float* q_resid;
+  const float* bank; int64_t ldb; const double* bank_nrm;
+  const float* query; int64_t ldq; const double* q_nrm; const float* q_resid;
   const uint32_t* bank_stats; const uint32_t* q_stats;
+  const uint32_t* gthr;            // final shared threshold per query (valid lower bound of the band)
   int dim;
   int64_t index_offset;
   int64_t* out_idx; float* out_val;
   int* fb_list; int* counters;     // counters[0] = fallback count, [1] = resolved here
 };
 
+// exact cosine of one bank row against the query held in qh[] (raw values as doubles):
+// fp64 dot of the raw fp32 rows / (fp64 norm product), rounded once to fp32.
+template <bool VEC>
+__device__ __forceinline__ double row_dot(const float* __restrict__ sp, const double (&qh)[8],
+                                          int dim, int lane) {
+  double acc = 0.0;
+  if (VEC) {                       // dim == 256, 16-byte aligned rows: d = 4*lane + 128*h + i
+    const float4 a = __ldg(reinterpret_cast<const float4*>(sp) + lane);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(sp) + 32 + lane);
+    acc = fma((double)a.x, qh[0], acc); acc = fma((double)a.y, qh[1], acc);
+    acc = fma((double)a.z, qh[2], acc); acc = fma((double)a.w, qh[3], acc);
+    acc = fma((double)b.x, qh[4], acc); acc = fma((double)b.y, qh[5], acc);
+    acc = fma((double)b.z, qh[6], acc); acc = fma((double)b.w, qh[7], acc);
+  } else {                         // d = lane + 32*t
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int d = lane + 32 * t;
+      if (d < dim) acc = fma((double)__ldg(sp + d), qh[t], acc);
+    }
+  }
+  return acc;
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(128)
 rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
   extern __shared__ __align__(16) unsigned char rr_smem[];
@@ -395,25 +475,35 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
   if (warp >= warps_per_block || q >= p.Q) return;
   unsigned long long* ent = reinterpret_cast<unsigned long long*>(rr_smem) +
                             (size_t)warp * per_warp_entries;   // (key << 32) | idx, later sort keys
-  // ---- gather the splits' candidates
+  // ---- gather the streams' candidates
   bool bad = (p.bank_stats[1] | p.q_stats[1]) != 0;    // non-finite input: exact path decides
   int M = 0;
-  for (int s = 0; s < p.S; ++s) {
-    const int c = p.cand_cnt[(size_t)q * p.S + s];
+  // Every stream dropped only scores at or below a threshold that was <= the final shared one,
+  // and the shared one is itself <= (k-th best) - 2 eps: stale entries below it go right away.
+  const uint32_t g_key = p.gthr[q];
+  for (int s = 0; s < p.SS && !bad; ++s) {
+    const int c = p.cand_cnt[(size_t)q * p.SS + s];
     if (c < 0) { bad = true; break; }
-    const uint2* src = p.cand + ((size_t)q * p.S + s) * p.cap;
-    for (int i = lane; i < c; i += 32) {
-      const uint2 e = src[i];
-      ent[M + i] = ((unsigned long long)f2ord(__uint_as_float(e.x)) << 32) | e.y;
+    const uint2* src = p.cand + ((size_t)q * p.SS + s) * p.cap;
+    for (int base = 0; base < c; base += 32) {
+      const int i = base + lane;
+      uint32_t key = 0, idx = 0;
+      if (i < c) { const uint2 e = src[i]; key = f2ord(__uint_as_float(e.x)); idx = e.y; }
+      const bool keep = (i < c) && key > g_key;
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      const int n_keep = __popc(bal);
+      if (M + n_keep > per_warp_entries) { bad = true; break; }
+      if (keep) ent[M + __popc(bal & ((1u << lane) - 1u))] = ((unsigned long long)key << 32) | idx;
+      M += n_keep;
     }
-    M += c;
   }
   __syncwarp();
+  if (M < p.k) bad = true;      // cannot happen for finite inputs; the exact path decides
   int n_s = 0;
   if (!bad) {
-    // ---- k-th best approximate score (exact, 32-bit radix descent)
+    // ---- lower bound of the k-th best approximate score (radix descent, 24 bits)
     uint32_t T = 0;
-    for (int bit = 31; bit >= 0; --bit) {
+    for (int bit = 31; bit >= 8; --bit) {
       const uint32_t candT = T | (1u << bit);
       int c = 0;
       for (int i = lane; i < M; i += 32) c += ((uint32_t)(ent[i] >> 32) >= candT) ? 1 : 0;
@@ -421,8 +511,7 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
       if (c >= p.k) T = candT;
     }
     const float rs_max = __uint_as_float(p.bank_stats[0]);
-    const float eps = 1.002f * (p.q_resid[q] + rs_max) + E_ACC + 2e-7f;
-    const float band = ord2f(T) - 2.02f * eps;
+    const float band = ord2f(T) - 2.02f * pair_eps(p.q_resid[q], rs_max);
     // ---- compact the band in place
     for (int base = 0; base < M; base += 32) {
       const int i = base + lane;
@@ -435,40 +524,54 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
       n_s += __popc(bal);
       __syncwarp();
     }
-    if (n_s > RR_MAX || n_s > per_warp_entries) bad = true;
+    if (n_s > RR_MAX) bad = true;
   }
   if (bad) {
     if (lane == 0) p.fb_list[atomicAdd(&p.counters[0], 1)] = (int)q;
     return;
   }
-  // ---- exact similarity of every survivor
+  // ---- exact cosine of every survivor
   double qh[8];
-  const float nq = p.q_nrm[q];
+  const double nq = p.q_nrm[q];
+  const float* qp = p.query + q * p.ldq;
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
-    const int d = lane + 32 * t;
-    qh[t] = d < p.dim ? (double)__fdiv_rn(__ldg(p.query + q * p.ldq + d), nq) : 0.0;
+    const int d = VEC ? (4 * lane + 128 * (t >> 2) + (t & 3)) : (lane + 32 * t);
+    qh[t] = d < p.dim ? (double)__ldg(qp + d) : 0.0;
   }
-  for (int i = 0; i < n_s; ++i) {
-    const uint32_t r = (uint32_t)ent[i];
-    const float* sp = p.bank + (int64_t)r * p.ldb;
-    const float bn = p.bank_nrm[r];
-    double acc = 0.0;
+  int i = 0;
+  for (; i + 4 <= n_s; i += 4) {          // 4 independent row gathers in flight
+    uint32_t r[4];
+    double acc[4];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int d = lane + 32 * t;
-      if (d < p.dim) acc = fma((double)__fdiv_rn(__ldg(sp + d), bn), qh[t], acc);
+    for (int u = 0; u < 4; ++u) r[u] = (uint32_t)ent[i + u];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = row_dot<VEC>(p.bank + (int64_t)r[u] * p.ldb, qh, p.dim, lane);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
+    __syncwarp();
+    if (lane < 4) {
+      const double a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+      const uint32_t rr = lane == 0 ? r[0] : lane == 1 ? r[1] : lane == 2 ? r[2] : r[3];
+      const float v = (float)(a / (nq * p.bank_nrm[rr]));
+      ent[i + lane] = ((unsigned long long)f2ord(v) << 32) | (unsigned long long)(0xffffffffu - rr);
     }
+  }
+  for (; i < n_s; ++i) {
+    const uint32_t r = (uint32_t)ent[i];
+    double acc = row_dot<VEC>(p.bank + (int64_t)r * p.ldb, qh, p.dim, lane);
     acc = warp_sum(acc);
     __syncwarp();
-    if (lane == 0)
-      ent[i] = ((unsigned long long)f2ord((float)acc) << 32) | (unsigned long long)(0xffffffffu - r);
+    if (lane == 0) {
+      const float v = (float)(acc / (nq * p.bank_nrm[r]));
+      ent[i] = ((unsigned long long)f2ord(v) << 32) | (unsigned long long)(0xffffffffu - r);
+    }
   }
   __syncwarp();
   // ---- sort (value desc, index asc)
   int P = 1;
   while (P < n_s) P <<= 1;
-  for (int i = n_s + lane; i < P; i += 32) ent[i] = 0ull;
+  for (int j = n_s + lane; j < P; j += 32) ent[j] = 0ull;
   __syncwarp();
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -482,30 +585,39 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
       __syncwarp();
     }
   }
-  for (int i = lane; i < p.k; i += 32) {
-    const unsigned long long e = ent[i];
-    p.out_idx[q * p.k + i] = (int64_t)(0xffffffffu - (uint32_t)e) + p.index_offset;
-    if (p.out_val) p.out_val[q * p.k + i] = ord2f((uint32_t)(e >> 32));
+  for (int j = lane; j < p.k; j += 32) {
+    const unsigned long long e = ent[j];
+    p.out_idx[q * p.k + j] = (int64_t)(0xffffffffu - (uint32_t)e) + p.index_offset;
+    if (p.out_val) p.out_val[q * p.k + j] = ord2f((uint32_t)(e >> 32));
   }
   if (lane == 0) atomicAdd(&p.counters[1], 1);
 }
 
 // ============================================================================ host side
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 int sim_topk_cluster(int64_t n_query) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("MCLST_SIM_CLUSTER");
-    forced = e ? atoi(e) : 0;
-  }
+  static const int forced = env_int("MCLST_SIM_CLUSTER", 0);
   if (forced == 1 || forced == 2 || forced == 4) return forced;
-  const int64_t qblocks = ceil_div(n_query, 128);
-  return qblocks >= 8 ? 2 : 1;
+  (void)n_query;
+  return 1;        // measured on B200 (cfg4): multicast clusters do not pay (L2 is not the limiter)
+}
+
+int sim_topk_epw() {
+  static const int forced = env_int("MCLST_SIM_EPW", 0);
+  if (forced == 4 || forced == 8 || forced == 16) return forced;
+  return 8;
 }
 
 int sim_topk_splits(int64_t n_query, int64_t n_bank, int cluster) {
+  static const int forced = env_int("MCLST_SIM_SPLITS", 0);
   const int sms = sm_count();
   const int64_t qblocks = ceil_div(ceil_div(n_query, 128), cluster) * cluster;
   const int64_t tiles = ceil_div(n_bank, ST_BN);
+  if (forced > 0) return (int)std::min<int64_t>(forced, tiles);
   int best = 1;
   double best_eff = 0.0;
   const int smax = (int)std::min<int64_t>(16, tiles);
@@ -523,34 +635,40 @@ void tc_workspace(Arena& a, int64_t n_bank, int64_t n_query, int dim, int top_k,
   const int nkb = (dim + 63) / 64;
   w.nkb = nkb;
   w.cluster = sim_topk_cluster(n_query);
+  w.epw = sim_topk_epw();
+  if (tc_cap_for_k(top_k) == 1024 && w.epw == 16) w.epw = 8;   // only <1024, *, {4,8}> is built
   w.q_pad = (int64_t)align_up((size_t)n_query, 128 * w.cluster);
   w.n_pad = (int64_t)align_up((size_t)n_bank, ST_BN);
   w.S = sim_topk_splits(n_query, n_bank, w.cluster);
+  w.SS = w.S * (w.epw / 4);
   w.cap = tc_cap_for_k(top_k);
   w.stats = a.take<uint32_t>(16);
   w.qpack = a.take<uint8_t>(tilepack_bytes(w.q_pad, nkb * 64));
   w.bpack = a.take<uint8_t>(tilepack_bytes(w.n_pad, nkb * 64));
-  w.q_nrm = a.take<float>((size_t)w.q_pad);
+  w.q_nrm = a.take<double>((size_t)w.q_pad);
   w.q_resid = a.take<float>((size_t)w.q_pad);
-  w.b_nrm = a.take<float>((size_t)w.n_pad);
+  w.b_nrm = a.take<double>((size_t)w.n_pad);
   w.b_resid = a.take<float>((size_t)w.n_pad);
-  w.cand = a.take<uint2>((size_t)w.q_pad * w.S * w.cap);
-  w.cand_cnt = a.take<int>((size_t)w.q_pad * w.S);
+  w.gthr = a.take<uint32_t>((size_t)w.q_pad);
+  w.cand = a.take<uint2>((size_t)w.q_pad * w.SS * w.cap);
+  w.cand_cnt = a.take<int>((size_t)w.q_pad * w.SS);
   w.fb_list = a.take<int>((size_t)n_query);
 }
 
 int launch_pack_rows(const float* x, int64_t rows, int64_t rows_pad, int64_t ld, int dim, int nkb,
-                     uint8_t* packed, float* nrm, float* resid, uint32_t* stats, cudaStream_t st) {
+                     uint8_t* packed, double* nrm, float* resid, uint32_t* stats, cudaStream_t st) {
   const int wpb = 8;
-  pack_rows_kernel<<<(unsigned)ceil_div(rows_pad, wpb), wpb * 32, 0, st>>>(
-      x, rows, rows_pad, ld, dim, nkb, packed, nrm, resid, stats);
+  const bool vec = (dim % 8 == 0) && (ld % 4 == 0) && ((uintptr_t)x % 16 == 0);
+  const unsigned grid = (unsigned)ceil_div(rows_pad, wpb);
+  if (vec) pack_rows_kernel<true><<<grid, wpb * 32, 0, st>>>(x, rows, rows_pad, ld, dim, nkb, packed, nrm, resid, stats);
+  else pack_rows_kernel<false><<<grid, wpb * 32, 0, st>>>(x, rows, rows_pad, ld, dim, nkb, packed, nrm, resid, stats);
   MCLST_LAUNCH_CHECK();
   return 0;
 }
 
-template <int CAP, int CL>
+template <int CAP, int CL, int EPW>
 static int launch_sim_topk_t(const SimParams& p, dim3 grid, cudaStream_t st) {
-  auto kern = sim_topk_kernel<CAP, CL>;
+  auto kern = sim_topk_kernel<CAP, CL, EPW>;
   static bool attr_set = false;
   if (!attr_set) {
     MCLST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
@@ -558,7 +676,7 @@ static int launch_sim_topk_t(const SimParams& p, dim3 grid, cudaStream_t st) {
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(ST_THREADS);
+  cfg.blockDim = dim3(64 + 32 * EPW);
   cfg.dynamicSmemBytes = ST_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -573,22 +691,34 @@ static int launch_sim_topk_t(const SimParams& p, dim3 grid, cudaStream_t st) {
   return 0;
 }
 
+template <int CAP, int CL>
+static int launch_sim_topk_e(int epw, const SimParams& p, dim3 grid, cudaStream_t st) {
+  switch (epw) {
+    case 4: return launch_sim_topk_t<CAP, CL, 4>(p, grid, st);
+    case 8: return launch_sim_topk_t<CAP, CL, 8>(p, grid, st);
+    case 16: return launch_sim_topk_t<CAP, CL, 16>(p, grid, st);
+  }
+  MCLST_REQUIRE(false, MCLST_ERR_UNSUPPORTED, "sim_topk: epilogue warps %d", epw);
+}
+
 int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int top_k, float* dump,
                     int64_t dump_ld, cudaStream_t st) {
   SimParams p;
   p.qpack = w.qpack; p.bpack = w.bpack; p.nkb = w.nkb; p.Q = n_query; p.N = n_bank;
   p.tiles_total = (int)(w.n_pad / ST_BN); p.S = w.S; p.k = top_k;
   p.q_resid = w.q_resid; p.bank_stats = w.stats; p.cand = w.cand; p.cand_cnt = w.cand_cnt;
-  p.dump = dump; p.dump_ld = dump_ld;
+  p.gthr = w.gthr; p.dump = dump; p.dump_ld = dump_ld;
+  static const int ablate = env_int("MCLST_SIM_ABLATE", 0);
+  p.ablate = ablate;
+  MCLST_CUDA(cudaMemsetAsync(w.gthr, 0, (size_t)w.q_pad * sizeof(uint32_t), st));
   dim3 grid((unsigned)(w.q_pad / 128), (unsigned)w.S);
-  const int key = w.cap * 10 + w.cluster;
-  switch (key) {
-    case 2561: return launch_sim_topk_t<256, 1>(p, grid, st);
-    case 2562: return launch_sim_topk_t<256, 2>(p, grid, st);
-    case 2564: return launch_sim_topk_t<256, 4>(p, grid, st);
-    case 10241: return launch_sim_topk_t<1024, 1>(p, grid, st);
-    case 10242: return launch_sim_topk_t<1024, 2>(p, grid, st);
-    case 10244: return launch_sim_topk_t<1024, 4>(p, grid, st);
+  if (w.cap == 256) {
+    if (w.cluster == 1) return launch_sim_topk_e<256, 1>(w.epw, p, grid, st);
+    if (w.cluster == 2) return launch_sim_topk_e<256, 2>(w.epw, p, grid, st);
+    if (w.cluster == 4) return launch_sim_topk_e<256, 4>(w.epw, p, grid, st);
+  } else if (w.cap == 1024) {
+    // large-k configurations (reference k = 200 / 600) are small problems: one variant
+    if (w.cluster == 1) return launch_sim_topk_e<1024, 1>(w.epw, p, grid, st);
   }
   MCLST_REQUIRE(false, MCLST_ERR_UNSUPPORTED, "sim_topk: cap %d cluster %d", w.cap, w.cluster);
 }
@@ -598,26 +728,31 @@ int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64
                   int64_t index_offset, int64_t* out_idx, float* out_val, int* counters,
                   cudaStream_t st) {
   RerankParams p;
-  p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.S = w.S; p.cap = w.cap; p.k = top_k;
+  p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.SS = w.SS; p.cap = w.cap; p.k = top_k;
   p.Q = n_query; p.N = n_bank; p.bank = bank; p.ldb = ldb; p.bank_nrm = w.b_nrm;
   p.query = query; p.ldq = ldq; p.q_nrm = w.q_nrm; p.q_resid = w.q_resid;
-  p.bank_stats = w.stats; p.q_stats = w.stats + 8; p.dim = dim; p.index_offset = index_offset;
+  p.bank_stats = w.stats; p.q_stats = w.stats + 8; p.gthr = w.gthr; p.dim = dim;
+  p.index_offset = index_offset;
   p.out_idx = out_idx; p.out_val = out_val; p.fb_list = w.fb_list; p.counters = counters;
-  // shared memory: per warp max(S*cap, pow2 >= RR_MAX... ) entries of 8 bytes
+  // shared memory: per warp a power-of-two number of 8-byte entries (bitonic sort), at most 4096;
+  // a query whose streams hold more than that goes to the exact path
   int per_warp = 1;
-  while (per_warp < w.S * w.cap) per_warp <<= 1;      // bitonic sort needs a power of two
+  while (per_warp < w.SS * w.cap && per_warp < 4096) per_warp <<= 1;
+  if (per_warp < 2 * top_k) per_warp = 2048;
   int wpb = 4;
-  while (wpb > 1 && (size_t)wpb * per_warp * 8 > 160 * 1024) wpb >>= 1;
-  MCLST_REQUIRE((size_t)per_warp * 8 <= 200 * 1024, MCLST_ERR_UNSUPPORTED,
-                "rerank: S*cap = %d too large", per_warp);
+  while (wpb > 1 && (size_t)wpb * per_warp * 8 > 96 * 1024) wpb >>= 1;
   const size_t smem = (size_t)wpb * per_warp * 8;
-  static size_t attr = 0;
-  if (smem > attr) {
-    MCLST_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)std::max<size_t>(smem, 48 * 1024)));
-    attr = smem;
+  const bool vec = (dim == 256) && (ldb % 4 == 0) && (ldq % 4 == 0) && ((uintptr_t)bank % 16 == 0) &&
+                   ((uintptr_t)query % 16 == 0);
+  static size_t attr[2] = {0, 0};
+  if (smem > attr[vec]) {
+    if (vec) MCLST_CUDA(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    else MCLST_CUDA(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    attr[vec] = smem;
   }
-  rerank_kernel<<<(unsigned)ceil_div(n_query, wpb), 128, smem, st>>>(p, wpb, per_warp);
+  const unsigned grid = (unsigned)ceil_div(n_query, wpb);
+  if (vec) rerank_kernel<true><<<grid, 128, smem, st>>>(p, wpb, per_warp);
+  else rerank_kernel<false><<<grid, 128, smem, st>>>(p, wpb, per_warp);
   MCLST_LAUNCH_CHECK();
   return 0;
 }

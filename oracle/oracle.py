@@ -73,13 +73,24 @@ def normalize_spec(x: np.ndarray) -> np.ndarray:
     return (x / nrm[:, None]).astype(np.float32)
 
 
+def norms_spec(x: np.ndarray) -> np.ndarray:
+    """float64 L2 norms of float32 rows, clamped at F.normalize's eps 1e-12."""
+    x64 = np.ascontiguousarray(x, dtype=np.float32).astype(np.float64)
+    return np.maximum(np.sqrt(np.einsum("ij,ij->i", x64, x64)), 1e-12)
+
+
 def similarity_spec(spot_embeddings, query_embeddings) -> np.ndarray:
-    """[Q,N] float32 similarities: float32-normalised rows, dot product
-    accumulated in float64, rounded once to float32.  This is the ranking key of
-    the CUDA path (values returned by the cSCC flavour, evel_cscc.py:82-84)."""
-    qn = normalize_spec(query_embeddings).astype(np.float64)
-    sn = normalize_spec(spot_embeddings).astype(np.float64)
-    return (qn @ sn.T).astype(np.float32)
+    """[Q,N] float32 similarities: the float64 cosine of the raw float32 rows --
+    dot product accumulated in float64, divided by the float64 norm product
+    (norms clamped at 1e-12 like F.normalize, evel_her2st.py:78-79) -- rounded once
+    to float32.  This is the ranking key of the CUDA path and the value the cSCC
+    flavour returns (evel_cscc.py:82-84); it is independent of summation order up
+    to ~1e-16 before the single float32 rounding."""
+    q64 = np.ascontiguousarray(query_embeddings, dtype=np.float32).astype(np.float64)
+    s64 = np.ascontiguousarray(spot_embeddings, dtype=np.float32).astype(np.float64)
+    if q64.ndim == 1:
+        q64 = q64[None]
+    return ((q64 @ s64.T) / (norms_spec(q64)[:, None] * norms_spec(s64)[None, :])).astype(np.float32)
 
 
 def find_matches_spec(spot_embeddings, query_embeddings, top_k=1,
@@ -92,13 +103,11 @@ def find_matches_spec(spot_embeddings, query_embeddings, top_k=1,
     q = np.ascontiguousarray(query_embeddings, dtype=np.float32)
     if q.ndim == 1:
         q = q[None]
-    sn = normalize_spec(spot_embeddings).astype(np.float64)
-    qn = normalize_spec(q).astype(np.float64)
     Q = q.shape[0]
     vals = np.empty((Q, top_k), np.float32)
     idx = np.empty((Q, top_k), np.int64)
     for q0 in range(0, Q, chunk):
-        sim = (qn[q0:q0 + chunk] @ sn.T).astype(np.float32)
+        sim = similarity_spec(spot_embeddings, q[q0:q0 + chunk])
         order = np.argsort(-sim, axis=1, kind="stable")[:, :top_k]
         idx[q0:q0 + chunk] = order
         vals[q0:q0 + chunk] = np.take_along_axis(sim, order, axis=1)
@@ -110,9 +119,9 @@ def decidable_rows(spot_embeddings, query_embeddings, top_k, gap=DECIDABLE_GAP) 
     separated by more than ``gap`` -- on those rows ANY correct float32
     implementation (the reference's MKL sgemm + torch.topk included) must return
     exactly the spec's ordered indices."""
-    qn = normalize_spec(query_embeddings).astype(np.float64)
-    sn = normalize_spec(spot_embeddings).astype(np.float64)
-    sim = qn @ sn.T
+    q64 = np.ascontiguousarray(query_embeddings, dtype=np.float32).astype(np.float64)
+    s64 = np.ascontiguousarray(spot_embeddings, dtype=np.float32).astype(np.float64)
+    sim = (q64 @ s64.T) / (norms_spec(q64)[:, None] * norms_spec(s64)[None, :])
     kk = min(top_k + 1, sim.shape[1])
     top = -np.sort(-sim, axis=1)[:, :kk]
     return (np.diff(-top, axis=1) > gap).all(axis=1)
