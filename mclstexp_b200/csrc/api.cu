@@ -202,6 +202,11 @@ extern "C" int mclst_find_matches(const float* bank, int64_t n_bank, int64_t ld_
                              t.q_resid, t.stats + 8, st))) return rc;
   prof_mark(st, "sim_topk");
   if ((rc = launch_sim_topk(t, n_bank, n_query, top_k, nullptr, 0, st))) return rc;
+  if (sim_topk_ablate() != 0) {     // timing experiment, no results
+    MCLST_CUDA(cudaMemsetAsync(out_indices, 0, (size_t)n_query * top_k * sizeof(int64_t), st));
+    prof_mark(st, "end");
+    return 0;
+  }
   prof_mark(st, "rerank");
   if ((rc = launch_rerank(t, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k,
                           index_offset, out_indices, out_values, w.counters, st))) return rc;

@@ -30,6 +30,7 @@ struct TcWorkspace {
   int* fb_list;
 };
 int tc_cap_for_k(int k);
+int sim_topk_ablate();   // timing experiments only: results are garbage when non-zero
 void tc_workspace(Arena& a, int64_t n_bank, int64_t n_query, int dim, int top_k, TcWorkspace& w);
 int launch_pack_rows(const float* x, int64_t rows, int64_t rows_pad, int64_t ld, int dim, int nkb,
                      uint8_t* packed, double* nrm, float* resid, uint32_t* stats, cudaStream_t st);

@@ -395,7 +395,7 @@ sim_topk_kernel(const SimParams p) {
         if (p.ablate == 0)
           filter_chunk<CAP>(va, my_buf, my_gthr, cnt, thr, flagged, (uint32_t)(col_base + c * 32),
                             n_valid - c * 32, k, e2);
-        else if (va[lane] == 0x12345678u) cnt++;
+        else if ((va[0] ^ va[13] ^ va[31]) == 0x12345678u) cnt++;
         tmem_ld_wait();
         if (c + 2 < NCH) {
           tmem_ld_32x32(taddr + (c + 2) * 32, va);
@@ -413,7 +413,7 @@ sim_topk_kernel(const SimParams p) {
         if (p.ablate == 0)
           filter_chunk<CAP>(vb, my_buf, my_gthr, cnt, thr, flagged,
                             (uint32_t)(col_base + (c + 1) * 32), n_valid - (c + 1) * 32, k, e2);
-        else if (vb[lane] == 0x12345678u) cnt++;
+        else if ((vb[0] ^ vb[13] ^ vb[31]) == 0x12345678u) cnt++;
       }
     }
     if (q_valid) p.cand_cnt[(size_t)q * SS + stream] = flagged ? -1 : cnt;
@@ -539,33 +539,27 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
     const int d = VEC ? (4 * lane + 128 * (t >> 2) + (t & 3)) : (lane + 32 * t);
     qh[t] = d < p.dim ? (double)__ldg(qp + d) : 0.0;
   }
-  int i = 0;
-  for (; i + 4 <= n_s; i += 4) {          // 4 independent row gathers in flight
-    uint32_t r[4];
-    double acc[4];
+  // 8 independent row gathers in flight per warp: the phase is DRAM-latency bound otherwise
+  for (int i = 0; i < n_s; i += 8) {
+    uint32_t r[8];
+    double acc[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) r[u] = (uint32_t)ent[i + u];
+    for (int u = 0; u < 8; ++u) r[u] = (uint32_t)ent[min(i + u, n_s - 1)];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] = row_dot<VEC>(p.bank + (int64_t)r[u] * p.ldb, qh, p.dim, lane);
+    for (int u = 0; u < 8; ++u) acc[u] = row_dot<VEC>(p.bank + (int64_t)r[u] * p.ldb, qh, p.dim, lane);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
+    for (int u = 0; u < 8; ++u) acc[u] = warp_sum(acc[u]);
     __syncwarp();
-    if (lane < 4) {
-      const double a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
-      const uint32_t rr = lane == 0 ? r[0] : lane == 1 ? r[1] : lane == 2 ? r[2] : r[3];
+    double a = acc[0];
+    uint32_t rr = r[0];
+#pragma unroll
+    for (int u = 1; u < 8; ++u)
+      if (lane == u) { a = acc[u]; rr = r[u]; }
+    if (lane < 8 && i + lane < n_s) {
       const float v = (float)(a / (nq * p.bank_nrm[rr]));
       ent[i + lane] = ((unsigned long long)f2ord(v) << 32) | (unsigned long long)(0xffffffffu - rr);
     }
-  }
-  for (; i < n_s; ++i) {
-    const uint32_t r = (uint32_t)ent[i];
-    double acc = row_dot<VEC>(p.bank + (int64_t)r * p.ldb, qh, p.dim, lane);
-    acc = warp_sum(acc);
     __syncwarp();
-    if (lane == 0) {
-      const float v = (float)(acc / (nq * p.bank_nrm[r]));
-      ent[i] = ((unsigned long long)f2ord(v) << 32) | (unsigned long long)(0xffffffffu - r);
-    }
   }
   __syncwarp();
   // ---- sort (value desc, index asc)
@@ -599,11 +593,17 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+int sim_topk_epw();
 int sim_topk_cluster(int64_t n_query) {
   static const int forced = env_int("MCLST_SIM_CLUSTER", 0);
   if (forced == 1 || forced == 2 || forced == 4) return forced;
   (void)n_query;
   return 1;        // measured on B200 (cfg4): multicast clusters do not pay (L2 is not the limiter)
+}
+
+int sim_topk_ablate() {
+  static const int v = env_int("MCLST_SIM_ABLATE", 0);
+  return v;
 }
 
 int sim_topk_epw() {
@@ -620,7 +620,9 @@ int sim_topk_splits(int64_t n_query, int64_t n_bank, int cluster) {
   if (forced > 0) return (int)std::min<int64_t>(forced, tiles);
   int best = 1;
   double best_eff = 0.0;
-  const int smax = (int)std::min<int64_t>(16, tiles);
+  // at most 8 candidate streams per query (S * epw/4): the re-rank merges them in 16 KiB of
+  // shared memory per query
+  const int smax = (int)std::min<int64_t>(std::max(1, 8 / (sim_topk_epw() / 4)), tiles);
   for (int S = 1; S <= smax; ++S) {
     const int64_t ctas = qblocks * S;
     const double eff = (double)ctas / (double)(ceil_div(ctas, sms) * sms);
@@ -708,8 +710,7 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
   p.tiles_total = (int)(w.n_pad / ST_BN); p.S = w.S; p.k = top_k;
   p.q_resid = w.q_resid; p.bank_stats = w.stats; p.cand = w.cand; p.cand_cnt = w.cand_cnt;
   p.gthr = w.gthr; p.dump = dump; p.dump_ld = dump_ld;
-  static const int ablate = env_int("MCLST_SIM_ABLATE", 0);
-  p.ablate = ablate;
+  p.ablate = sim_topk_ablate();
   MCLST_CUDA(cudaMemsetAsync(w.gthr, 0, (size_t)w.q_pad * sizeof(uint32_t), st));
   dim3 grid((unsigned)(w.q_pad / 128), (unsigned)w.S);
   if (w.cap == 256) {
@@ -737,10 +738,10 @@ int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64
   // shared memory: per warp a power-of-two number of 8-byte entries (bitonic sort), at most 4096;
   // a query whose streams hold more than that goes to the exact path
   int per_warp = 1;
-  while (per_warp < w.SS * w.cap && per_warp < 4096) per_warp <<= 1;
+  while (per_warp < w.SS * w.cap && per_warp < 2048) per_warp <<= 1;
   if (per_warp < 2 * top_k) per_warp = 2048;
   int wpb = 4;
-  while (wpb > 1 && (size_t)wpb * per_warp * 8 > 96 * 1024) wpb >>= 1;
+  while (wpb > 1 && (size_t)wpb * per_warp * 8 > 64 * 1024) wpb >>= 1;
   const size_t smem = (size_t)wpb * per_warp * 8;
   const bool vec = (dim == 256) && (ldb % 4 == 0) && (ldq % 4 == 0) && ((uintptr_t)bank % 16 == 0) &&
                    ((uintptr_t)query % 16 == 0);
