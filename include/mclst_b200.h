@@ -130,6 +130,40 @@ int mclst_weighted_gather(const void* expression_key, int64_t n_bank, int64_t ld
                           float* out_partial /* [n_query, genes] float32, overwritten */,
                           mclst_stream_t stream);
 
+/* ---------------------------------------------------------------- contrastive loss ------ */
+
+/* Symmetric image<->spot contrastive loss, forward and backward in one call.
+ *   MCLST_T_EYE       model.py:242-247: logits = S I^T / T; identity targets;
+ *                     loss = (CE(logits, eye) + CE(logits^T, eye)) / 2
+ *   MCLST_T_SOFT_DIV  baselines/Bleep/models.py:34-43: targets = softmax((I I^T + S S^T)/2/T),
+ *   MCLST_T_SOFT_MUL  baselines/Bleep/models.py:70-79: ... /2*T; targets stay in the graph.
+ * spot_emb, image_emb: [batch, dim] float32.  loss_out: one float32 (device).  d_spot /
+ * d_image (both or neither): gradients of the loss w.r.t. the two inputs.  No batch x batch
+ * matrix is held beyond one row block (MCLST_LOSS_SCRATCH_MB, default 1024). */
+int mclst_contrastive_loss_workspace_bytes(int batch, int dim, int target_mode, int want_grad,
+                                           size_t* bytes);
+int mclst_contrastive_loss(const float* spot_emb, int64_t ld_s, const float* image_emb, int64_t ld_i,
+                           int batch, int dim, float temperature, int target_mode, float* loss_out,
+                           float* d_spot, int64_t ld_ds, float* d_image, int64_t ld_di,
+                           void* workspace, size_t workspace_bytes, mclst_stream_t stream);
+
+/* ---------------------------------------------------------------- dense contractions ---- */
+
+/* C_z[M,N] = act(alpha * op(A_z)[M,K] * op(B_z)[N,K]^T + bias[N]) + residual_z[M,N], z < batch
+ * (row-major float32).  The building block behind every nn.Linear / einsum of the path and
+ * their backward passes (model.py:25-27, :43-47, :51-57, :155-157).  a_trans = 0: A is stored
+ * [M,K]; a_trans = 1: A is stored [K,M]; likewise B ([N,K] or [K,N]).  *_batch_stride are in
+ * elements.  fp32 operands are split into fp16 hi/lo tiles and multiplied on the tensor cores
+ * in three passes (precise = 1, ~fp32 accuracy) or one (precise = 0).  bias / residual may be
+ * null (residual shares C's ld and batch stride); act: 0 none, 1 exact-erf GELU. */
+int mclst_matmul_workspace_bytes(int64_t M, int64_t N, int64_t K, int batch, size_t* bytes);
+int mclst_matmul(const float* A, int64_t lda, int a_trans, int64_t a_batch_stride,
+                 const float* B, int64_t ldb, int b_trans, int64_t b_batch_stride,
+                 float* C, int64_t ldc, int64_t c_batch_stride,
+                 int64_t M, int64_t N, int64_t K, int batch, float alpha,
+                 const float* bias, int act, const float* residual, int precise,
+                 void* workspace, size_t workspace_bytes, mclst_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,12 @@ def load() -> C.CDLL:
     lib.mclst_find_matches_workspace_bytes.argtypes = [i64, i64, i32, i32, i32, C.POINTER(sz)]
     lib.mclst_find_matches.argtypes = [p, i64, i64, p, i64, i64, i32, i32, i64, p, p, p, sz, i32, p]
     lib.mclst_debug_similarity.argtypes = [p, i64, i64, p, i64, i64, i32, p, i64, p, sz, p]
+    lib.mclst_contrastive_loss_workspace_bytes.argtypes = [i32, i32, i32, i32, C.POINTER(sz)]
+    lib.mclst_contrastive_loss.argtypes = [p, i64, p, i64, i32, i32, C.c_float, i32, p, p, i64, p, i64,
+                                           p, sz, p]
+    lib.mclst_matmul_workspace_bytes.argtypes = [i64, i64, i64, i32, C.POINTER(sz)]
+    lib.mclst_matmul.argtypes = [p, i64, i32, i64, p, i64, i32, i64, p, i64, i64, i64, i64, i64, i32,
+                                 C.c_float, p, i32, p, i32, p, sz, p]
     lib.mclst_weighted_average.argtypes = [p, i64, i64, p, i64, i32, i32, p, i64, i64, i32, p, p,
                                            i32, i64, i32, p, p, i32, p]
     lib.mclst_neighbor_distances.argtypes = [p, i64, i64, p, i64, i64, i32, p, i32, i64, i32, p, p]

@@ -1,0 +1,334 @@
+// Split-precision tcgen05 GEMM:  C[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T)
+//
+// The reference computes every contraction of the path in FP32 (cuBLAS sgemm with TF32
+// off).  Tensor cores take 16-bit operands, so each fp32 operand x is split
+// at pack time into two fp16 TilePack images hi = fp16(x), lo = fp16(x - hi) and the
+// product is accumulated over three K segments
+//       A_hi*B_hi + A_lo*B_hi + A_hi*B_lo        (the lo*lo term is < 2^-22 relative)
+// in the fp32 TMEM accumulator: ~fp32 accuracy at 3 tensor-core passes.  nseg = 1 gives a
+// plain fp16 product.
+//
+//   pack_split      fp32 row-major -> (hi, lo) TilePack, optionally transposed, written at a
+//                   K offset so operands can be concatenated along K
+//   gemm_tn         one CTA per 128 x 256 output tile: warp 0 streams A/B slices with
+//                   cp.async.bulk into a 4-stage ring, warp 1 issues tcgen05.mma, warps 2-5
+//                   run the epilogue out of TMEM (alpha, bias, exact-erf GELU, residual).
+//
+// Operand scale: fp16 overflows at 65504.  Operands on this path are LayerNorm outputs,
+// embeddings, probabilities and gradients thereof (|x| << 1e4); pack_split saturates and
+// flags anything larger so the caller can fail loudly instead of returning inf.
+#include <algorithm>
+#include "common.cuh"
+#include "gemm.cuh"
+#include "umma.cuh"
+
+namespace mclst {
+
+using namespace ptx;
+
+// ============================================================================ pack_split
+// Non-transposed: out row r = in row r, K index = in column.  One warp per row.
+__global__ void __launch_bounds__(256)
+pack_split_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                  float scale, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
+                  int64_t rows_pad, int nkb_total, int kb_offset, int nkb_mine,
+                  uint32_t* __restrict__ flags, int64_t x_batch, size_t out_batch) {
+  x += (int64_t)blockIdx.z * x_batch;
+  hi += (size_t)blockIdx.z * out_batch;
+  if (lo) lo += (size_t)blockIdx.z * out_batch;
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows_pad) return;
+  const int nchunks = nkb_mine * 8;
+  bool bad = false;
+  for (int c = lane; c < nchunks; c += 32) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t k = (int64_t)c * 8 + i;
+      v[i] = (r < rows && k < cols) ? __ldg(x + r * ld + k) * scale : 0.f;
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half a = __float2half_rn(v[2 * i]), b = __float2half_rn(v[2 * i + 1]);
+      const __half al = __float2half_rn(v[2 * i] - __half2float(a));
+      const __half bl = __float2half_rn(v[2 * i + 1] - __half2float(b));
+      bad |= !(fabsf(v[2 * i]) <= 65000.f) || !(fabsf(v[2 * i + 1]) <= 65000.f);
+      h[i] = (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+      l[i] = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
+    }
+    const size_t off = tilepack_chunk_offset(r, kb_offset * 8 + c, nkb_total);
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+  if (bad) atomicOr(flags, 1u);
+}
+
+// Transposed: out row r = in column r, K index = in row.  Lane <-> out row (contiguous in
+// the input), each thread gathers 8 consecutive K (8 input rows) for one 16-byte chunk.
+__global__ void __launch_bounds__(256)
+pack_split_t_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                    float scale, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
+                    int64_t out_rows_pad, int nkb_total, int kb_offset, int nkb_mine,
+                    uint32_t* __restrict__ flags, int64_t x_batch, size_t out_batch) {
+  x += (int64_t)blockIdx.z * x_batch;
+  hi += (size_t)blockIdx.z * out_batch;
+  if (lo) lo += (size_t)blockIdx.z * out_batch;
+  const int64_t r = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);      // out row = in column
+  const int cgroup = threadIdx.x >> 5;                                  // 8 chunk lanes per block
+  if (r >= out_rows_pad) return;
+  const int nchunks = nkb_mine * 8;
+  bool bad = false;
+  for (int c = blockIdx.y * 8 + cgroup; c < nchunks; c += gridDim.y * 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t k = (int64_t)c * 8 + i;                             // in row
+      v[i] = (r < cols && k < rows) ? __ldg(x + k * ld + r) * scale : 0.f;
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half a = __float2half_rn(v[2 * i]), b = __float2half_rn(v[2 * i + 1]);
+      const __half al = __float2half_rn(v[2 * i] - __half2float(a));
+      const __half bl = __float2half_rn(v[2 * i + 1] - __half2float(b));
+      bad |= !(fabsf(v[2 * i]) <= 65000.f) || !(fabsf(v[2 * i + 1]) <= 65000.f);
+      h[i] = (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+      l[i] = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
+    }
+    const size_t off = tilepack_chunk_offset(r, kb_offset * 8 + c, nkb_total);
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+  if (bad) atomicOr(flags, 1u);
+}
+
+int launch_pack_split(const float* x, int64_t rows, int64_t cols, int64_t ld, bool transpose,
+                      float scale, const PackedOperand& dst, int kb_offset, int nkb_mine,
+                      uint32_t* flags, cudaStream_t st, int batch, int64_t x_batch_elems) {
+  if (!transpose) {
+    const int wpb = 8;
+    dim3 grid((unsigned)ceil_div(dst.rows_pad, wpb), 1, (unsigned)batch);
+    pack_split_kernel<<<grid, wpb * 32, 0, st>>>(x, rows, cols, ld, scale, dst.hi, dst.lo,
+                                                 dst.rows_pad, dst.nkb, kb_offset, nkb_mine, flags,
+                                                 x_batch_elems, dst.bytes);
+  } else {
+    dim3 grid((unsigned)ceil_div(dst.rows_pad, 32), (unsigned)std::min<int64_t>(64, nkb_mine),
+              (unsigned)batch);
+    pack_split_t_kernel<<<grid, 256, 0, st>>>(x, rows, cols, ld, scale, dst.hi, dst.lo,
+                                              dst.rows_pad, dst.nkb, kb_offset, nkb_mine, flags,
+                                              x_batch_elems, dst.bytes);
+  }
+  MCLST_LAUNCH_CHECK();
+  return 0;
+}
+
+// ============================================================================ gemm_tn
+constexpr int GM_THREADS = 192;
+constexpr int GM_BM = 128, GM_BN = 256;
+constexpr int GM_STAGES = 4;
+constexpr int GM_STAGE_BYTES = 3 * TP_SLICE_BYTES;     // A slice (128 rows) + B slice (256 rows)
+constexpr int GM_SMEM = GM_STAGES * GM_STAGE_BYTES + 1024 + 1024;
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__global__ void __launch_bounds__(GM_THREADS, 1)
+gemm_tn_kernel(const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + GM_STAGES * GM_STAGE_BYTES);
+  uint64_t* bar_empty = bar_full + GM_STAGES;
+  uint64_t* bar_done = bar_empty + GM_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mb = blockIdx.x, nb = blockIdx.y, z = blockIdx.z;
+  const int nkb = p.nkb;
+  const int iters = p.nseg * nkb;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GM_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    mbar_init(bar_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint8_t* a_hi = p.a_hi + (size_t)z * p.a_batch_bytes;
+      const uint8_t* a_lo = p.a_lo ? p.a_lo + (size_t)z * p.a_batch_bytes : nullptr;
+      const uint8_t* b_hi = p.b_hi + (size_t)z * p.b_batch_bytes;
+      const uint8_t* b_lo = p.b_lo ? p.b_lo + (size_t)z * p.b_batch_bytes : nullptr;
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        const int seg = it / nkb, kb = it - seg * nkb;
+        // segment 0: hi*hi, 1: lo*hi, 2: hi*lo
+        const uint8_t* a = (seg == 1) ? a_lo : a_hi;
+        const uint8_t* b = (seg == 2) ? b_lo : b_hi;
+        mbar_wait(&bar_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&bar_full[stage], GM_STAGE_BYTES);
+        uint8_t* dst = smem + stage * GM_STAGE_BYTES;
+        bulk_g2s(dst, a + ((size_t)mb * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES, &bar_full[stage]);
+        bulk_g2s(dst + TP_SLICE_BYTES, b + ((size_t)(2 * nb) * nkb + kb) * TP_SLICE_BYTES,
+                 TP_SLICE_BYTES, &bar_full[stage]);
+        bulk_g2s(dst + 2 * TP_SLICE_BYTES, b + ((size_t)(2 * nb + 1) * nkb + kb) * TP_SLICE_BYTES,
+                 TP_SLICE_BYTES, &bar_full[stage]);
+        if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(GM_BM, GM_BN, false);
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&bar_full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * GM_STAGE_BYTES);
+        const uint32_t b_addr = a_addr + TP_SLICE_BYTES;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          mma_f16_ss(tmem_base, make_smem_desc_sw128(a_addr + k4 * 32),
+                     make_smem_desc_sw128(b_addr + k4 * 32), idesc, (it | k4) != 0 ? 1u : 0u);
+        mma_commit(&bar_empty[stage]);
+        if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(bar_done);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    const int quad = warp & 3;
+    const int64_t m = (int64_t)mb * GM_BM + quad * 32 + lane;
+    const bool m_ok = m < p.M;
+    float* crow = p.c + (size_t)z * p.c_batch_elems + m * p.ldc;
+    const float* rrow = p.residual ? p.residual + (size_t)z * p.c_batch_elems + m * p.ldc : nullptr;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int64_t n0 = (int64_t)nb * GM_BN;
+    const bool vec_ok = (p.ldc % 4 == 0) && ((uintptr_t)p.c % 16 == 0) &&
+                        (!p.residual || (uintptr_t)p.residual % 16 == 0);
+#pragma unroll 1
+    for (int c = 0; c < GM_BN / 32; ++c) {
+      if (n0 + c * 32 >= p.N) break;             // uniform
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      tmem_ld_wait();
+      if (!m_ok) continue;
+      const int64_t nbase = n0 + c * 32;
+      float o[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]) * p.alpha;
+        if (p.bias && nbase + j < p.N) x += __ldg(p.bias + nbase + j);
+        if (p.act == 1) x = gelu_erf(x);
+        o[j] = x;
+      }
+      if (vec_ok && nbase + 32 <= p.N) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 w = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          if (rrow) {
+            const float4 rr = *reinterpret_cast<const float4*>(rrow + nbase + j);
+            w.x += rr.x; w.y += rr.y; w.z += rr.z; w.w += rr.w;
+          }
+          *reinterpret_cast<float4*>(crow + nbase + j) = w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nbase + j < p.N) crow[nbase + j] = o[j] + (rrow ? rrow[nbase + j] : 0.f);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+int launch_gemm_tn(const GemmParams& p, cudaStream_t st) {
+  MCLST_REQUIRE(p.M > 0 && p.N > 0 && p.nkb > 0 && (p.nseg == 1 || p.nseg == 3), MCLST_ERR_INVALID,
+                "gemm: bad shape M=%lld N=%lld nkb=%d nseg=%d", (long long)p.M, (long long)p.N, p.nkb, p.nseg);
+  MCLST_REQUIRE(p.nseg == 1 || (p.a_lo && p.b_lo), MCLST_ERR_INVALID, "gemm: split needs lo parts");
+  static bool attr_set = false;
+  if (!attr_set) {
+    MCLST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div(p.M, GM_BM), (unsigned)ceil_div(p.N, GM_BN), (unsigned)std::max(1, p.batch));
+  gemm_tn_kernel<<<grid, GM_THREADS, GM_SMEM, st>>>(p);
+  MCLST_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- operand bookkeeping --------------------------------------------------------------
+size_t packed_operand_bytes(int64_t rows, int64_t k, bool is_b, int64_t* rows_pad, int* nkb) {
+  const int64_t rp = (int64_t)align_up((size_t)rows, is_b ? GM_BN : GM_BM);
+  const int kb = (int)ceil_div(k, TP_K);
+  if (rows_pad) *rows_pad = rp;
+  if (nkb) *nkb = kb;
+  return (size_t)rp * kb * TP_K * 2;
+}
+
+PackedOperand take_operand(Arena& a, int64_t rows, int64_t k, bool is_b, bool split, int batch) {
+  PackedOperand o{};
+  o.bytes = packed_operand_bytes(rows, k, is_b, &o.rows_pad, &o.nkb);
+  o.hi = a.take<uint8_t>(o.bytes * batch);
+  o.lo = split ? a.take<uint8_t>(o.bytes * batch) : nullptr;
+  return o;
+}
+
+}  // namespace mclst
+
+using namespace mclst;
+
+// C-ABI: generic (batched) fp32 matmul through the split-precision tensor-core path -- the
+// building block behind every nn.Linear / einsum on the path and their backward passes.
+extern "C" int mclst_matmul_workspace_bytes(int64_t M, int64_t N, int64_t K, int batch, size_t* bytes) {
+  MCLST_REQUIRE(bytes && M > 0 && N > 0 && K > 0 && batch >= 1, MCLST_ERR_INVALID,
+                "matmul_workspace: bad args");
+  Arena a(nullptr, 0);
+  a.take<uint32_t>(16);
+  take_operand(a, M, K, false, true, batch);
+  take_operand(a, N, K, true, true, batch);
+  *bytes = align_up(a.off, 256);
+  return 0;
+}
+
+extern "C" int mclst_matmul(const float* A, int64_t lda, int a_trans, int64_t a_batch_stride,
+                            const float* B, int64_t ldb, int b_trans, int64_t b_batch_stride,
+                            float* C, int64_t ldc, int64_t c_batch_stride,
+                            int64_t M, int64_t N, int64_t K, int batch, float alpha,
+                            const float* bias, int act, const float* residual, int precise,
+                            void* workspace, size_t workspace_bytes, mclst_stream_t stream) {
+  MCLST_REQUIRE(A && B && C && workspace, MCLST_ERR_INVALID, "matmul: null pointer");
+  MCLST_REQUIRE(M > 0 && N > 0 && K > 0 && batch >= 1, MCLST_ERR_INVALID, "matmul: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena a(workspace, workspace_bytes);
+  uint32_t* flags = a.take<uint32_t>(16);
+  PackedOperand pa = take_operand(a, M, K, false, true, batch);
+  PackedOperand pb = take_operand(a, N, K, true, true, batch);
+  MCLST_REQUIRE(a.ok(), MCLST_ERR_WORKSPACE, "matmul: workspace too small");
+  int rc;
+  prof_mark(st, "pack_split");
+  // a_trans: A is stored [K, M] (operand rows are its columns); likewise b_trans: B stored [K, N]
+  if ((rc = launch_pack_split(A, a_trans ? K : M, a_trans ? M : K, lda, a_trans != 0, 1.f, pa, 0,
+                              pa.nkb, flags, st, batch, a_batch_stride))) return rc;
+  if ((rc = launch_pack_split(B, b_trans ? K : N, b_trans ? N : K, ldb, b_trans != 0, 1.f, pb, 0,
+                              pb.nkb, flags, st, batch, b_batch_stride))) return rc;
+  GemmParams g{};
+  g.a_hi = pa.hi; g.a_lo = pa.lo; g.b_hi = pb.hi; g.b_lo = pb.lo;
+  g.a_batch_bytes = pa.bytes; g.b_batch_bytes = pb.bytes;
+  g.nkb = pa.nkb; g.nseg = precise ? 3 : 1; g.M = M; g.N = N; g.c = C; g.ldc = ldc;
+  g.c_batch_elems = (size_t)c_batch_stride;
+  g.alpha = alpha; g.bias = bias; g.act = act; g.residual = residual; g.batch = batch;
+  prof_mark(st, "gemm_tn");
+  rc = launch_gemm_tn(g, st);
+  prof_mark(st, "end");
+  return rc;
+}

@@ -1,0 +1,40 @@
+// Split-precision tcgen05 GEMM building block (gemm.cu).
+#pragma once
+#include "common.cuh"
+
+namespace mclst {
+
+// fp16 TilePack image(s) of one operand: hi = fp16(x), lo = fp16(x - hi) (lo may be null).
+struct PackedOperand {
+  uint8_t* hi;
+  uint8_t* lo;
+  int64_t rows_pad;   // multiple of 128 (A operand) or 256 (B operand)
+  int nkb;            // K / 64 (padded)
+  size_t bytes;       // bytes of one image (per batch entry)
+};
+
+struct GemmParams {
+  const uint8_t *a_hi, *a_lo, *b_hi, *b_lo;
+  size_t a_batch_bytes, b_batch_bytes;   // stride between batch entries of the packed operands
+  int nkb, nseg, batch;
+  int64_t M, N;
+  float* c;
+  int64_t ldc;
+  size_t c_batch_elems;
+  float alpha;
+  const float* bias;        // [N] or null
+  int act;                  // 0 none, 1 exact-erf GELU (applied after bias)
+  const float* residual;    // same layout as c, added after the activation, or null
+};
+
+size_t packed_operand_bytes(int64_t rows, int64_t k, bool is_b, int64_t* rows_pad, int* nkb);
+PackedOperand take_operand(Arena& a, int64_t rows, int64_t k, bool is_b, bool split, int batch);
+// x [rows, cols] fp32 (ld) scaled by `scale`; transpose = false: operand rows = x rows, K = x
+// cols; transpose = true: operand rows = x cols, K = x rows.  Written at K-block kb_offset of
+// dst (dst.nkb blocks in total), nkb_mine blocks wide, zero padded.
+int launch_pack_split(const float* x, int64_t rows, int64_t cols, int64_t ld, bool transpose,
+                      float scale, const PackedOperand& dst, int kb_offset, int nkb_mine,
+                      uint32_t* flags, cudaStream_t st, int batch = 1, int64_t x_batch_elems = 0);
+int launch_gemm_tn(const GemmParams& p, cudaStream_t st);
+
+}  // namespace mclst

@@ -1,0 +1,375 @@
+// Symmetric contrastive loss, forward + backward, for identity targets (reference
+// model.py:242-247) and BLEEP soft targets (baselines/Bleep/models.py:34-43, :70-79 and
+// cross_entropy :228-234), without ever holding a B x B matrix for more than one row block.
+//
+// With Lg = S I^T / T,  A = (I I^T + S S^T) * a   (a = 1/(2T) "div" or T/2 "mul"),
+// Pt = softmax_row(A) (soft) or the identity (eye), rl/cl the row/column log-sum-exp of Lg,
+// za the row log-sum-exp of A:
+//     loss   = (1/2B) sum_ij Pt_ij (rl_i + cl_j - 2 Lg_ij)
+//     dLg_ij = (exp(Lg_ij - rl_i) + cs_j exp(Lg_ij - cl_j) - 2 Pt_ij) / 2B,  cs_j = sum_i Pt_ij
+//     dA_ij  = Pt_ij (rl_i + cl_j - 2 Lg_ij - wbar_i) / 2B,      wbar_i = sum_j Pt_ij W_ij
+//     dS = dLg I / T + (dA + dA^T) S a          dI = dLg^T S / T + (dA + dA^T) I a
+// (targets stay in the graph exactly as in the reference: the dA terms are their gradient).
+//
+// Execution: rows are processed in blocks of R (all of B when it fits the workspace).  Per
+// block three tensor-core products give the rows P1 = Lg_i., P2 = Lg_.i (= (I_i S^T)/T) and
+// P3 = A_i. ; three sweeps turn them into (1) rl, cl, za, (2) wbar, cs, loss, (3) the
+// gradient factors, which are written straight into TilePack operands and contracted with
+// [I;S]^T / [S;I]^T by two more tensor-core products.  All products use the 3-term fp16 split
+// (gemm.cu), i.e. fp32-level accuracy: logits reach +-256 here (LayerNorm'd embeddings have
+// norm 16), so single-pass fp16/bf16 operands cannot meet the 1e-3 gradient tolerance.
+#include <algorithm>
+#include "common.cuh"
+#include "gemm.cuh"
+#include "umma.cuh"
+
+namespace mclst {
+
+constexpr int LS_THREADS = 256;
+
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int w = 1; w < LS_THREADS / 32; ++w) r = fmaxf(r, sh[w]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int w = 0; w < LS_THREADS / 32; ++w) r += sh[w];
+  __syncthreads();
+  return r;
+}
+
+// lse[r] = log sum_j exp(P[r, j]) over j < ncols; optionally diag[r] = P[r, row0 + r].
+__global__ void __launch_bounds__(LS_THREADS)
+row_lse_kernel(const float* __restrict__ P, int64_t ld, int ncols, int64_t row0,
+               float* __restrict__ lse, float* __restrict__ diag) {
+  __shared__ float sh[LS_THREADS / 32];
+  const int64_t r = blockIdx.x;
+  const float* p = P + r * ld;
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < ncols; j += LS_THREADS) m = fmaxf(m, p[j]);
+  m = block_max(m, sh);
+  float s = 0.f;
+  for (int j = threadIdx.x; j < ncols; j += LS_THREADS) s += expf(p[j] - m);
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) {
+    lse[row0 + r] = m + logf(s);
+    if (diag) diag[row0 + r] = p[row0 + r];
+  }
+}
+
+// soft targets, sweep 2: wbar_r = sum_j Pt_rj W_rj ; cs_r = sum_j exp(A_rj - za_j)  (A symmetric)
+__global__ void __launch_bounds__(LS_THREADS)
+soft_pass2_kernel(const float* __restrict__ P1, const float* __restrict__ P3, int64_t ld, int ncols,
+                  int64_t row0, const float* __restrict__ rl, const float* __restrict__ cl,
+                  const float* __restrict__ za, float* __restrict__ wbar, float* __restrict__ cs) {
+  __shared__ float sh[LS_THREADS / 32];
+  const int64_t r = blockIdx.x, rg = row0 + r;
+  const float* p1 = P1 + r * ld;
+  const float* p3 = P3 + r * ld;
+  const float rl_r = rl[rg], za_r = za[rg];
+  float w = 0.f, c = 0.f;
+  for (int j = threadIdx.x; j < ncols; j += LS_THREADS) {
+    const float a = p3[j];
+    w += expf(a - za_r) * (rl_r + cl[j] - 2.f * p1[j]);
+    c += expf(a - za[j]);
+  }
+  w = block_sum(w, sh);
+  c = block_sum(c, sh);
+  if (threadIdx.x == 0) { wbar[rg] = w; cs[rg] = c; }
+}
+
+// loss = (1/2B) sum_r term_r; term = wbar (soft) or rl + cl - 2 diag (eye).  One block.
+__global__ void __launch_bounds__(LS_THREADS)
+loss_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                   const float* __restrict__ d, int B, float* __restrict__ out) {
+  __shared__ float sh[LS_THREADS / 32];
+  __shared__ double shd[LS_THREADS / 32];
+  (void)sh;
+  double acc = 0.0;
+  for (int r = threadIdx.x; r < B; r += LS_THREADS)
+    acc += b ? (double)a[r] + (double)b[r] - 2.0 * (double)d[r] : (double)a[r];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) shd[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < LS_THREADS / 32; ++w) t += shd[w];
+    *out = (float)(t / (2.0 * B));
+  }
+}
+
+struct GradParams {
+  const float *P1, *P2, *P3;
+  int64_t ld;
+  int B, rows, soft;           // rows = valid rows of this block
+  int64_t row0;
+  const float *rl, *cl, *za, *wbar, *cs;
+  float inv_t, a_scale;
+  uint8_t *ga_hi, *ga_lo, *gb_hi, *gb_lo;   // TilePack A operands, K = [B64 | B64] (soft) or [B64] (eye)
+  int nkb_total, nkb_half;
+};
+
+__device__ __forceinline__ void store_split(uint8_t* hi, uint8_t* lo, size_t off, const float (&v)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half a = __float2half_rn(v[2 * i]), b = __float2half_rn(v[2 * i + 1]);
+    const __half al = __float2half_rn(v[2 * i] - __half2float(a));
+    const __half bl = __float2half_rn(v[2 * i + 1] - __half2float(b));
+    h[i] = (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+    l[i] = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
+  }
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Gradient factors of one row block, written as split TilePack operands.  One thread per
+// (row, 8-column chunk).  Gradients of magnitude ~1/B are scaled by 2B before the fp16 split
+// (keeps them in fp16's normal range); the GEMM alpha undoes it.
+__global__ void __launch_bounds__(256)
+grad_factor_kernel(const GradParams p, int64_t rows_pad) {
+  const int chunks = p.nkb_half * 8;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = t / chunks;
+  const int c = (int)(t - r * chunks);
+  if (r >= rows_pad) return;
+  float g1[8], g2[8], gs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { g1[i] = 0.f; g2[i] = 0.f; gs[i] = 0.f; }
+  if (r < p.rows) {
+    const int64_t rg = p.row0 + r;
+    const float rl_r = p.rl[rg], cl_r = p.cl[rg];
+    const float za_r = p.soft ? p.za[rg] : 0.f, wb_r = p.soft ? p.wbar[rg] : 0.f;
+    const float cs_r = p.soft ? p.cs[rg] : 1.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = c * 8 + i;
+      if (j < p.B) {
+        const float p1 = p.P1[r * p.ld + j], p2 = p.P2[r * p.ld + j];
+        const float rl_j = p.rl[j], cl_j = p.cl[j];
+        float pt_rj, pt_jr, cs_j;
+        if (p.soft) {
+          const float a = p.P3[r * p.ld + j];
+          pt_rj = expf(a - za_r);
+          pt_jr = expf(a - p.za[j]);
+          cs_j = p.cs[j];
+          const float da_rj = pt_rj * (rl_r + cl_j - 2.f * p1 - wb_r);
+          const float da_jr = pt_jr * (rl_j + cl_r - 2.f * p2 - p.wbar[j]);
+          gs[i] = (da_rj + da_jr) * p.a_scale;
+        } else {
+          pt_rj = pt_jr = (rg == j) ? 1.f : 0.f;
+          cs_j = 1.f;
+        }
+        g1[i] = (expf(p1 - rl_r) + cs_j * expf(p1 - cl_j) - 2.f * pt_rj) * p.inv_t;   // 2B * dLg_rj / T
+        g2[i] = (expf(p2 - rl_j) + cs_r * expf(p2 - cl_r) - 2.f * pt_jr) * p.inv_t;   // 2B * dLg_jr / T
+      }
+    }
+  }
+  const size_t off = tilepack_chunk_offset(r, c, p.nkb_total);
+  store_split(p.ga_hi, p.ga_lo, off, g1);
+  store_split(p.gb_hi, p.gb_lo, off, g2);
+  if (p.soft) {
+    const size_t off2 = tilepack_chunk_offset(r, p.nkb_half * 8 + c, p.nkb_total);
+    store_split(p.ga_hi, p.ga_lo, off2, gs);
+    store_split(p.gb_hi, p.gb_lo, off2, gs);
+  }
+}
+
+// ---------------------------------------------------------------------------- host plan
+struct LossPlan {
+  int B, D, soft;
+  int64_t B64, R, nblocks;
+  uint32_t* flags;
+  PackedOperand Sp, Ip, ISp;       // rows padded to 256: usable as A and as B operands
+  PackedOperand XT_IS, XT_SI;      // [D, 2*B64] (soft) or [D, B64] (eye), transposed packs
+  PackedOperand GA, GB;            // [R, 2*B64] / [R, B64]
+  float *P1, *P2, *P3;
+  float *rl, *cl, *za, *wbar, *cs, *diag;
+  size_t bytes;
+};
+
+static LossPlan plan_loss(void* ws, size_t cap, int B, int D, int soft, int want_grad, size_t budget) {
+  LossPlan L{};
+  L.B = B; L.D = D; L.soft = soft;
+  L.B64 = (int64_t)align_up((size_t)B, 64);
+  // row-block size: P1,P2,P3 (12 B/elem) + GA,GB hi/lo (8 or 16 B/elem) per (row, column)
+  const size_t per_row = (size_t)L.B64 * (12 + (want_grad ? (soft ? 16 : 8) : 0));
+  int64_t R = (int64_t)(budget / std::max<size_t>(per_row, 1));
+  R = std::max<int64_t>(128, R / 128 * 128);
+  R = std::min<int64_t>(R, (int64_t)align_up((size_t)B, 128));
+  L.R = R;
+  L.nblocks = ceil_div(B, R);
+  Arena a(ws, cap);
+  L.flags = a.take<uint32_t>(16);
+  L.Sp = take_operand(a, B, D, true, true, 1);
+  L.Ip = take_operand(a, B, D, true, true, 1);
+  if (soft) L.ISp = take_operand(a, B, 2 * (int64_t)align_up((size_t)D, 64), true, true, 1);
+  const int64_t kx = (soft ? 2 : 1) * L.B64;
+  if (want_grad) {
+    L.XT_IS = take_operand(a, D, kx, true, true, 1);
+    L.XT_SI = take_operand(a, D, kx, true, true, 1);
+    L.GA = take_operand(a, R, kx, false, true, 1);
+    L.GB = take_operand(a, R, kx, false, true, 1);
+  }
+  L.P1 = a.take<float>((size_t)R * L.B64);
+  L.P2 = a.take<float>((size_t)R * L.B64);
+  L.P3 = soft ? a.take<float>((size_t)R * L.B64) : nullptr;
+  L.rl = a.take<float>((size_t)B); L.cl = a.take<float>((size_t)B); L.za = a.take<float>((size_t)B);
+  L.wbar = a.take<float>((size_t)B); L.cs = a.take<float>((size_t)B); L.diag = a.take<float>((size_t)B);
+  L.bytes = align_up(a.off, 256);
+  return L;
+}
+
+static size_t loss_budget() {
+  const char* e = getenv("MCLST_LOSS_SCRATCH_MB");
+  return (size_t)(e ? atoll(e) : 1024) << 20;
+}
+
+// rows [i0, i0+rows) of P1 = S I^T / T, P2 = I S^T / T, P3 = [I|S][I|S]^T * a
+static int compute_blocks(const LossPlan& L, int64_t i0, int64_t rows, float inv_t, float a_scale,
+                          bool need_p2, cudaStream_t st) {
+  const int nkbD = L.Sp.nkb;
+  GemmParams g{};
+  g.nseg = 3; g.batch = 1; g.M = rows; g.N = L.B; g.ldc = L.B64;
+  const size_t a_off = (size_t)(i0 / 128) * nkbD * TP_SLICE_BYTES;
+  int rc;
+  g.nkb = nkbD;
+  g.a_hi = L.Sp.hi + a_off; g.a_lo = L.Sp.lo + a_off; g.b_hi = L.Ip.hi; g.b_lo = L.Ip.lo;
+  g.c = L.P1; g.alpha = inv_t;
+  if ((rc = launch_gemm_tn(g, st))) return rc;
+  if (need_p2) {
+    g.a_hi = L.Ip.hi + a_off; g.a_lo = L.Ip.lo + a_off; g.b_hi = L.Sp.hi; g.b_lo = L.Sp.lo;
+    g.c = L.P2;
+    if ((rc = launch_gemm_tn(g, st))) return rc;
+  }
+  if (L.soft) {
+    const size_t a2 = (size_t)(i0 / 128) * L.ISp.nkb * TP_SLICE_BYTES;
+    g.nkb = L.ISp.nkb;
+    g.a_hi = L.ISp.hi + a2; g.a_lo = L.ISp.lo + a2; g.b_hi = L.ISp.hi; g.b_lo = L.ISp.lo;
+    g.c = L.P3; g.alpha = a_scale;
+    if ((rc = launch_gemm_tn(g, st))) return rc;
+  }
+  return 0;
+}
+
+}  // namespace mclst
+
+using namespace mclst;
+
+extern "C" int mclst_contrastive_loss_workspace_bytes(int batch, int dim, int target_mode,
+                                                      int want_grad, size_t* bytes) {
+  MCLST_REQUIRE(bytes && batch >= 1 && dim >= 1 && target_mode >= 0 && target_mode <= 2,
+                MCLST_ERR_INVALID, "contrastive_loss_workspace: bad args");
+  *bytes = plan_loss(nullptr, 0, batch, dim, target_mode != MCLST_T_EYE, want_grad, loss_budget()).bytes;
+  return 0;
+}
+
+extern "C" int mclst_contrastive_loss(const float* spot_emb, int64_t ld_s, const float* image_emb,
+                                      int64_t ld_i, int batch, int dim, float temperature,
+                                      int target_mode, float* loss_out, float* d_spot,
+                                      int64_t ld_ds, float* d_image, int64_t ld_di,
+                                      void* workspace, size_t workspace_bytes,
+                                      mclst_stream_t stream) {
+  MCLST_REQUIRE(spot_emb && image_emb && loss_out && workspace, MCLST_ERR_INVALID,
+                "contrastive_loss: null pointer");
+  MCLST_REQUIRE(batch >= 1 && dim >= 1 && temperature > 0.f, MCLST_ERR_INVALID,
+                "contrastive_loss: bad batch/dim/temperature");
+  MCLST_REQUIRE(target_mode >= 0 && target_mode <= 2, MCLST_ERR_INVALID, "contrastive_loss: bad target mode");
+  MCLST_REQUIRE((d_spot == nullptr) == (d_image == nullptr), MCLST_ERR_INVALID,
+                "contrastive_loss: pass both gradients or neither");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = batch, D = dim;
+  const int soft = target_mode != MCLST_T_EYE;
+  const int want_grad = d_spot != nullptr;
+  const float inv_t = 1.0f / temperature;
+  const float a_scale = target_mode == MCLST_T_SOFT_DIV ? 0.5f / temperature
+                      : target_mode == MCLST_T_SOFT_MUL ? 0.5f * temperature : 0.f;
+  LossPlan L = plan_loss(workspace, workspace_bytes, B, D, soft, want_grad, loss_budget());
+  MCLST_REQUIRE(L.bytes <= workspace_bytes, MCLST_ERR_WORKSPACE, "contrastive_loss: workspace %zu < %zu",
+                workspace_bytes, L.bytes);
+  int rc;
+  MCLST_CUDA(cudaMemsetAsync(L.flags, 0, 64, st));
+  prof_mark(st, "loss_pack");
+  const int nkbD = L.Sp.nkb;
+  if ((rc = launch_pack_split(spot_emb, B, D, ld_s, false, 1.f, L.Sp, 0, nkbD, L.flags, st))) return rc;
+  if ((rc = launch_pack_split(image_emb, B, D, ld_i, false, 1.f, L.Ip, 0, nkbD, L.flags, st))) return rc;
+  if (soft) {
+    if ((rc = launch_pack_split(image_emb, B, D, ld_i, false, 1.f, L.ISp, 0, nkbD, L.flags, st))) return rc;
+    if ((rc = launch_pack_split(spot_emb, B, D, ld_s, false, 1.f, L.ISp, nkbD, nkbD, L.flags, st))) return rc;
+  }
+  if (want_grad) {
+    const int nkbB = (int)(L.B64 / 64);
+    if ((rc = launch_pack_split(image_emb, B, D, ld_i, true, 1.f, L.XT_IS, 0, nkbB, L.flags, st))) return rc;
+    if ((rc = launch_pack_split(spot_emb, B, D, ld_s, true, 1.f, L.XT_SI, 0, nkbB, L.flags, st))) return rc;
+    if (soft) {
+      if ((rc = launch_pack_split(spot_emb, B, D, ld_s, true, 1.f, L.XT_IS, nkbB, nkbB, L.flags, st))) return rc;
+      if ((rc = launch_pack_split(image_emb, B, D, ld_i, true, 1.f, L.XT_SI, nkbB, nkbB, L.flags, st))) return rc;
+    }
+  }
+  const bool single = L.nblocks == 1;
+  // ---- sweep 1: rl, cl, za (+ diagonal for the identity targets)
+  prof_mark(st, "loss_stats");
+  for (int64_t b = 0; b < L.nblocks; ++b) {
+    const int64_t i0 = b * L.R, rows = std::min<int64_t>(L.R, B - i0);
+    if ((rc = compute_blocks(L, i0, rows, inv_t, a_scale, true, st))) return rc;
+    row_lse_kernel<<<(unsigned)rows, LS_THREADS, 0, st>>>(L.P1, L.B64, B, i0, L.rl, L.diag);
+    MCLST_LAUNCH_CHECK();
+    row_lse_kernel<<<(unsigned)rows, LS_THREADS, 0, st>>>(L.P2, L.B64, B, i0, L.cl, nullptr);
+    MCLST_LAUNCH_CHECK();
+    if (soft) {
+      row_lse_kernel<<<(unsigned)rows, LS_THREADS, 0, st>>>(L.P3, L.B64, B, i0, L.za, nullptr);
+      MCLST_LAUNCH_CHECK();
+    }
+  }
+  // ---- sweep 2: wbar, cs, loss
+  prof_mark(st, "loss_value");
+  if (soft) {
+    for (int64_t b = 0; b < L.nblocks; ++b) {
+      const int64_t i0 = b * L.R, rows = std::min<int64_t>(L.R, B - i0);
+      if (!single && (rc = compute_blocks(L, i0, rows, inv_t, a_scale, false, st))) return rc;
+      soft_pass2_kernel<<<(unsigned)rows, LS_THREADS, 0, st>>>(L.P1, L.P3, L.B64, B, i0, L.rl, L.cl,
+                                                               L.za, L.wbar, L.cs);
+      MCLST_LAUNCH_CHECK();
+    }
+    loss_reduce_kernel<<<1, LS_THREADS, 0, st>>>(L.wbar, nullptr, nullptr, B, loss_out);
+  } else {
+    loss_reduce_kernel<<<1, LS_THREADS, 0, st>>>(L.rl, L.cl, L.diag, B, loss_out);
+  }
+  MCLST_LAUNCH_CHECK();
+  // ---- sweep 3: gradients
+  if (want_grad) {
+    prof_mark(st, "loss_grad");
+    for (int64_t b = 0; b < L.nblocks; ++b) {
+      const int64_t i0 = b * L.R, rows = std::min<int64_t>(L.R, B - i0);
+      if (!single && (rc = compute_blocks(L, i0, rows, inv_t, a_scale, true, st))) return rc;
+      GradParams gp{};
+      gp.P1 = L.P1; gp.P2 = L.P2; gp.P3 = L.P3; gp.ld = L.B64; gp.B = B; gp.rows = (int)rows;
+      gp.soft = soft; gp.row0 = i0; gp.rl = L.rl; gp.cl = L.cl; gp.za = L.za; gp.wbar = L.wbar;
+      gp.cs = L.cs; gp.inv_t = inv_t; gp.a_scale = a_scale;
+      gp.ga_hi = L.GA.hi; gp.ga_lo = L.GA.lo; gp.gb_hi = L.GB.hi; gp.gb_lo = L.GB.lo;
+      gp.nkb_total = L.GA.nkb; gp.nkb_half = (int)(L.B64 / 64);
+      const int64_t rows_pad = (int64_t)align_up((size_t)rows, 128);
+      const int64_t threads = rows_pad * gp.nkb_half * 8;
+      grad_factor_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, st>>>(gp, rows_pad);
+      MCLST_LAUNCH_CHECK();
+      GemmParams g{};
+      g.nseg = 3; g.batch = 1; g.M = rows; g.N = D; g.nkb = L.GA.nkb; g.alpha = 0.5f / (float)B;
+      g.a_hi = L.GA.hi; g.a_lo = L.GA.lo; g.b_hi = L.XT_IS.hi; g.b_lo = L.XT_IS.lo;
+      g.c = d_spot + i0 * ld_ds; g.ldc = ld_ds;
+      if ((rc = launch_gemm_tn(g, st))) return rc;
+      g.a_hi = L.GB.hi; g.a_lo = L.GB.lo; g.b_hi = L.XT_SI.hi; g.b_lo = L.XT_SI.lo;
+      g.c = d_image + i0 * ld_di; g.ldc = ld_di;
+      if ((rc = launch_gemm_tn(g, st))) return rc;
+    }
+  }
+  prof_mark(st, "end");
+  return 0;
+}
