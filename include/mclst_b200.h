@@ -147,6 +147,44 @@ int mclst_contrastive_loss(const float* spot_emb, int64_t ld_s, const float* ima
                            float* d_spot, int64_t ld_ds, float* d_image, int64_t ld_di,
                            void* workspace, size_t workspace_bytes, mclst_stream_t stream);
 
+/* ---------------------------------------------------------------- spot encoder pieces --- */
+
+/* model.py:230-235: out[b,:] = expression[b,:] + x_table[long(position[b,0]),:]
+ *                                              + y_table[long(position[b,1]),:]
+ * (.long() truncation).  *error_flag (device uint32) is OR-ed with 1 when an index falls
+ * outside [0, table_rows) -- nn.Embedding raises there; the caller checks it. */
+int mclst_embed_add(const float* expression, int64_t ld_e, const float* position, int64_t ld_p,
+                    const float* x_table, const float* y_table, int table_rows, int batch, int genes,
+                    float* out, int64_t ld_o, uint32_t* error_flag, mclst_stream_t stream);
+/* Backward of the gathers: DENSE [table_rows, genes] gradients (zero-filled, then
+ * scatter-added), the layout torch.optim.Adam(weight_decay) of train.py:118-120 expects. */
+int mclst_embed_add_backward(const float* d_out, int64_t ld_d, const float* position, int64_t ld_p,
+                             int table_rows, int batch, int genes, float* d_x_table,
+                             float* d_y_table, mclst_stream_t stream);
+
+/* nn.LayerNorm over the last dimension (model.py:13, :159): biased variance, eps inside the
+ * square root; mean / rstd [rows] are kept for the backward. */
+int mclst_layernorm_forward(const float* x, int64_t ld_x, const float* gamma, const float* beta,
+                            int64_t rows, int cols, float eps, float* y, int64_t ld_y, float* mean,
+                            float* rstd, mclst_stream_t stream);
+int mclst_layernorm_backward(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x,
+                             const float* gamma, const float* mean, const float* rstd, int64_t rows,
+                             int cols, float* dx, int64_t ld_dx, float* dgamma, float* dbeta,
+                             float* scratch, size_t scratch_floats, mclst_stream_t stream);
+
+/* nn.GELU() (exact erf form, model.py:25, :155) on n contiguous elements. */
+int mclst_gelu_forward(const float* x, float* y, int64_t n, mclst_stream_t stream);
+int mclst_gelu_backward(const float* dy, const float* x, float* dx, int64_t n, mclst_stream_t stream);
+
+/* nn.Softmax(dim=-1) of model.py:41/:54 over `rows` rows of `cols` scores, in place; backward
+ * overwrites d_probs with d_scores = probs * (d_probs - sum(d_probs * probs)). */
+int mclst_softmax_forward(float* scores, int64_t ld, int64_t rows, int cols, mclst_stream_t stream);
+int mclst_softmax_backward(const float* probs, float* d_probs_to_d_scores, int64_t ld, int64_t rows,
+                           int cols, mclst_stream_t stream);
+
+/* out[c] = sum_r x[r,c] (bias gradients), deterministic order. */
+int mclst_col_sum(const float* x, int64_t ld, int64_t rows, int cols, float* out, mclst_stream_t stream);
+
 /* ---------------------------------------------------------------- dense contractions ---- */
 
 /* C_z[M,N] = act(alpha * op(A_z)[M,K] * op(B_z)[N,K]^T + bias[N]) + residual_z[M,N], z < batch

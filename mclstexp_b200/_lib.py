@@ -58,6 +58,16 @@ def load() -> C.CDLL:
     lib.mclst_contrastive_loss_workspace_bytes.argtypes = [i32, i32, i32, i32, C.POINTER(sz)]
     lib.mclst_contrastive_loss.argtypes = [p, i64, p, i64, i32, i32, C.c_float, i32, p, p, i64, p, i64,
                                            p, sz, p]
+    f32 = C.c_float
+    lib.mclst_embed_add.argtypes = [p, i64, p, i64, p, p, i32, i32, i32, p, i64, p, p]
+    lib.mclst_embed_add_backward.argtypes = [p, i64, p, i64, i32, i32, i32, p, p, p]
+    lib.mclst_layernorm_forward.argtypes = [p, i64, p, p, i64, i32, f32, p, i64, p, p, p]
+    lib.mclst_layernorm_backward.argtypes = [p, i64, p, i64, p, p, p, i64, i32, p, i64, p, p, p, sz, p]
+    lib.mclst_gelu_forward.argtypes = [p, p, i64, p]
+    lib.mclst_gelu_backward.argtypes = [p, p, p, i64, p]
+    lib.mclst_softmax_forward.argtypes = [p, i64, i64, i32, p]
+    lib.mclst_softmax_backward.argtypes = [p, p, i64, i64, i32, p]
+    lib.mclst_col_sum.argtypes = [p, i64, i64, i32, p, p]
     lib.mclst_matmul_workspace_bytes.argtypes = [i64, i64, i64, i32, C.POINTER(sz)]
     lib.mclst_matmul.argtypes = [p, i64, i32, i64, p, i64, i32, i64, p, i64, i64, i64, i64, i64, i32,
                                  C.c_float, p, i32, p, i32, p, sz, p]

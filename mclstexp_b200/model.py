@@ -1,0 +1,476 @@
+"""Drop-in mirror of the reference's ``model.py`` surface for the hot path.
+
+Same class names, constructor arguments, attribute names and ``state_dict`` keys as
+/root/reference/model.py, so checkpoints written by the reference's
+``train.py:87-95`` load unchanged and ``evel_*.py:get_embeddings`` can keep addressing
+``model.image_projection / x_embed / y_embed / spot_encoder / spot_projection``.  The
+parameters live in ordinary ``nn.Linear`` / ``nn.LayerNorm`` / ``nn.Embedding`` holders (that
+is what fixes the key names); ``forward`` never calls them -- every number comes from the
+sm_100a kernels behind libmclst_b200.so through the autograd functions below.
+
+  PreNorm / FeedForward / Attention / attn_block   model.py:10-69
+  ProjectionHead                                   model.py:151-168
+  mclSTExp_Attention (+ mclSTExp_MLP)              model.py:171-247
+  image encoders                                   model.py:72-148 (stock torchvision, off the path)
+
+There is no CPU fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from ._lib import MclstError, check, load, ptr, require_cuda, stream_ptr
+from .loss import contrastive_loss
+
+__all__ = ["PreNorm", "FeedForward", "Attention", "attn_block", "ProjectionHead", "ImageEncoder",
+           "ImageEncoder_Resnet", "ImageEncoder_VIT", "ImageEncdoer_res18", "ImageEncdoer_res101",
+           "mclSTExp_MLP", "mclSTExp_Attention", "linear", "gelu", "layer_norm", "attention_core",
+           "embed_add"]
+
+
+# ----------------------------------------------------------------------------- primitives
+def _c2d(t: torch.Tensor) -> torch.Tensor:
+    return t if (t.dim() == 2 and t.stride(1) == 1) else t.contiguous()
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b (+ residual), all contractions on the split-precision tensor-core GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual):
+        x = _c2d(x)
+        y = ops.matmul(x, weight, bias=bias, residual=None if residual is None else _c2d(residual))
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _c2d(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.matmul(dy, weight, b_trans=True)               # [M,out] x [out,in]
+        if ctx.needs_input_grad[1]:
+            dw = ops.matmul(dy, x, a_trans=True, b_trans=True)      # dY^T X -> [out,in]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = col_sum(dy)
+        return dx, dw, db, (dy if ctx.has_res else None)
+
+
+def linear(x, weight, bias=None, residual=None):
+    return _Linear.apply(x, weight, bias, residual)
+
+
+def col_sum(x: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().mclst_col_sum(ptr(x), x.stride(0), x.shape[0], x.shape[1], ptr(out), stream_ptr()),
+              "col_sum")
+    return out
+
+
+class _Gelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(load().mclst_gelu_forward(ptr(x), ptr(y), x.numel(), stream_ptr()), "gelu_forward")
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(load().mclst_gelu_backward(ptr(dy), ptr(x), ptr(dx), x.numel(), stream_ptr()),
+                  "gelu_backward")
+        return dx
+
+
+def gelu(x):
+    return _Gelu.apply(x)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x = _c2d(x)
+        R, Cc = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(R, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(R, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(load().mclst_layernorm_forward(ptr(x), x.stride(0), ptr(weight), ptr(bias), R, Cc,
+                                                 float(eps), ptr(y), y.stride(0), ptr(mean), ptr(rstd),
+                                                 stream_ptr()), "layernorm_forward")
+        ctx.save_for_backward(x, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dy = _c2d(dy)
+        R, Cc = x.shape
+        dx = torch.empty_like(x)
+        dg = torch.empty_like(weight)
+        db = torch.empty_like(weight)
+        scratch = torch.empty(64 * 2 * Cc, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(load().mclst_layernorm_backward(ptr(dy), dy.stride(0), ptr(x), x.stride(0), ptr(weight),
+                                                  ptr(mean), ptr(rstd), R, Cc, ptr(dx), dx.stride(0),
+                                                  ptr(dg), ptr(db), ptr(scratch), scratch.numel(),
+                                                  stream_ptr()), "layernorm_backward")
+        return dx, dg, db, None
+
+
+def layer_norm(x, weight, bias, eps=1e-5):
+    return _LayerNorm.apply(x, weight, bias, eps)
+
+
+class _AttentionCore(torch.autograd.Function):
+    """softmax(q k^T * scale) v for all heads of one token sequence (model.py:52-56).
+
+    qkv: [n, 3*heads*dh] as produced by ``to_qkv`` (q | k | v, each head-major); returns
+    [n, heads*dh] ('b h n d -> b n (h d)')."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, scale):
+        qkv = _c2d(qkv)
+        n, three_inner = qkv.shape
+        inner = three_inner // 3
+        dh = inner // heads
+        q, k, v = (qkv[:, i * inner:(i + 1) * inner].view(n, heads, dh).permute(1, 0, 2) for i in range(3))
+        probs = ops.matmul(q, k, alpha=scale)                       # [h, n, n] dots
+        with torch.cuda.device(qkv.device):
+            check(load().mclst_softmax_forward(ptr(probs), n, heads * n, n, stream_ptr()), "softmax_forward")
+        out = torch.empty((n, inner), dtype=torch.float32, device=qkv.device)
+        ops.matmul(probs, v, b_trans=True, out=out.view(n, heads, dh).permute(1, 0, 2))
+        ctx.save_for_backward(qkv, probs)
+        ctx.heads, ctx.scale = heads, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qkv, probs = ctx.saved_tensors
+        heads, scale = ctx.heads, ctx.scale
+        n, three_inner = qkv.shape
+        inner = three_inner // 3
+        dh = inner // heads
+        d_out = _c2d(d_out)
+        q, k, v = (qkv[:, i * inner:(i + 1) * inner].view(n, heads, dh).permute(1, 0, 2) for i in range(3))
+        do = d_out.view(n, heads, dh).permute(1, 0, 2)
+        dqkv = torch.empty_like(qkv)
+        dq, dk, dv = (dqkv[:, i * inner:(i + 1) * inner].view(n, heads, dh).permute(1, 0, 2) for i in range(3))
+        ops.matmul(probs, do, a_trans=True, b_trans=True, out=dv)    # P^T dO
+        ds = ops.matmul(do, v)                                       # dP = dO V^T
+        with torch.cuda.device(qkv.device):
+            check(load().mclst_softmax_backward(ptr(probs), ptr(ds), n, heads * n, n, stream_ptr()),
+                  "softmax_backward")
+        ops.matmul(ds, k, b_trans=True, alpha=scale, out=dq)         # dS K
+        ops.matmul(ds, q, a_trans=True, b_trans=True, alpha=scale, out=dk)   # dS^T Q
+        return dqkv, None, None
+
+
+def attention_core(qkv, heads, scale):
+    return _AttentionCore.apply(qkv, heads, scale)
+
+
+class _EmbedAdd(torch.autograd.Function):
+    """expression + x_embed[long(pos[:,0])] + y_embed[long(pos[:,1])]  (model.py:230-235)."""
+
+    @staticmethod
+    def forward(ctx, expression, position, x_table, y_table):
+        require_cuda(expression, position, x_table, y_table)
+        expression = _c2d(expression.float())
+        position = _c2d(position.float())
+        B, G = expression.shape
+        out = torch.empty((B, G), dtype=torch.float32, device=expression.device)
+        err = torch.zeros(1, dtype=torch.int32, device=expression.device)
+        with torch.cuda.device(expression.device):
+            check(load().mclst_embed_add(ptr(expression), expression.stride(0), ptr(position),
+                                         position.stride(0), ptr(x_table), ptr(y_table), x_table.shape[0],
+                                         B, G, ptr(out), out.stride(0), ptr(err), stream_ptr()), "embed_add")
+        ctx.save_for_backward(position)
+        ctx.table_rows = x_table.shape[0]
+        ctx.err = err
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (position,) = ctx.saved_tensors
+        if int(ctx.err.item()):
+            raise IndexError("position index out of range for x_embed / y_embed (nn.Embedding(65536, dim))")
+        d_out = _c2d(d_out)
+        B, G = d_out.shape
+        dwx = dwy = None
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            dwx = torch.empty((ctx.table_rows, G), dtype=torch.float32, device=d_out.device)
+            dwy = torch.empty_like(dwx)
+            with torch.cuda.device(d_out.device):
+                check(load().mclst_embed_add_backward(ptr(d_out), d_out.stride(0), ptr(position),
+                                                      position.stride(0), ctx.table_rows, B, G, ptr(dwx),
+                                                      ptr(dwy), stream_ptr()), "embed_add_backward")
+        return (d_out if ctx.needs_input_grad[0] else None), None, dwx, dwy
+
+
+def embed_add(expression, position, x_table, y_table, check_range: bool = True):
+    out = _EmbedAdd.apply(expression, position, x_table, y_table)
+    return out
+
+
+def _as_rows(x: torch.Tensor):
+    """[..., dim] -> ([rows, dim], leading shape)."""
+    lead = x.shape[:-1]
+    return x.reshape(-1, x.shape[-1]), lead
+
+
+# ----------------------------------------------------------------------------- modules
+class PreNorm(nn.Module):
+    """model.py:10-17."""
+
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.fn = fn
+
+    def forward(self, x, **kwargs):
+        x2, lead = _as_rows(x)
+        h = layer_norm(x2, self.norm.weight, self.norm.bias, self.norm.eps)
+        return self.fn(h.reshape(*lead, -1), **kwargs)
+
+
+class FeedForward(nn.Module):
+    """model.py:20-32: Linear -> GELU -> Dropout -> Linear -> Dropout."""
+
+    def __init__(self, dim, hidden_dim, dropout=0.):
+        super().__init__()
+        self.net = nn.Sequential(
+            nn.Linear(dim, hidden_dim),
+            nn.GELU(),
+            nn.Dropout(dropout),
+            nn.Linear(hidden_dim, dim),
+            nn.Dropout(dropout)
+        )
+
+    def forward(self, x, residual=None):
+        x2, lead = _as_rows(x)
+        h = gelu(linear(x2, self.net[0].weight, self.net[0].bias))
+        h = self.net[2](h)
+        res = None if residual is None else residual.reshape(-1, residual.shape[-1])
+        if self.net[4].p > 0 and self.training and res is not None:
+            y = self.net[4](linear(h, self.net[3].weight, self.net[3].bias)) + res
+        else:
+            y = self.net[4](linear(h, self.net[3].weight, self.net[3].bias, res))
+        return y.reshape(*lead, -1)
+
+
+class Attention(nn.Module):
+    """model.py:35-57."""
+
+    def __init__(self, dim, heads=8, dim_head=64, dropout=0.):
+        super().__init__()
+        inner_dim = dim_head * heads
+        project_out = not (heads == 1 and dim_head == dim)
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        self.attend = nn.Softmax(dim=-1)
+        self.to_qkv = nn.Linear(dim, inner_dim * 3, bias=False)
+        self.to_out = nn.Sequential(
+            nn.Linear(inner_dim, dim),
+            nn.Dropout(dropout)
+        ) if project_out else nn.Identity()
+
+    def forward(self, x, residual=None):
+        if x.dim() == 2:
+            x = x[None]
+        b, n, _ = x.shape
+        outs = []
+        for i in range(b):                      # b is 1 on this path (model.py:236 unsqueeze(0))
+            qkv = linear(x[i], self.to_qkv.weight)
+            o = attention_core(qkv, self.heads, self.scale)
+            res = None if residual is None else residual.reshape(b, n, -1)[i]
+            if isinstance(self.to_out, nn.Identity):
+                o = o if res is None else o + res
+            elif self.to_out[1].p > 0 and self.training and res is not None:
+                o = self.to_out[1](linear(o, self.to_out[0].weight, self.to_out[0].bias)) + res
+            else:
+                o = self.to_out[1](linear(o, self.to_out[0].weight, self.to_out[0].bias, res))
+            outs.append(o)
+        return outs[0][None] if b == 1 else torch.stack(outs)
+
+
+class attn_block(nn.Module):
+    """model.py:60-69: x = attn(x) + x; x = ff(x) + x (residuals fused into the GEMM epilogues)."""
+
+    def __init__(self, dim, heads, dim_head, mlp_dim, dropout=0.):
+        super().__init__()
+        self.attn = PreNorm(dim, Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout))
+        self.ff = PreNorm(dim, FeedForward(dim, mlp_dim, dropout=dropout))
+
+    def forward(self, x):
+        x = self.attn(x, residual=x)
+        x = self.ff(x, residual=x)
+        return x
+
+
+class ProjectionHead(nn.Module):
+    """model.py:151-168."""
+
+    def __init__(self, embedding_dim, projection_dim, dropout=0.):
+        super().__init__()
+        self.projection = nn.Linear(embedding_dim, projection_dim)
+        self.gelu = nn.GELU()
+        self.fc = nn.Linear(projection_dim, projection_dim)
+        self.dropout = nn.Dropout(dropout)
+        self.layer_norm = nn.LayerNorm(projection_dim)
+
+    def forward(self, x):
+        x2, lead = _as_rows(x)
+        projected = linear(x2, self.projection.weight, self.projection.bias)
+        h = gelu(projected)
+        if self.dropout.p > 0 and self.training:
+            y = self.dropout(linear(h, self.fc.weight, self.fc.bias)) + projected
+        else:
+            y = linear(h, self.fc.weight, self.fc.bias, projected)
+        y = layer_norm(y, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
+        return y.reshape(*lead, -1)
+
+
+# ---- image encoders: stock torchvision / timm, outside the hot path (model.py:72-148) ------
+def _tv(name, weights_enum=None, **kw):
+    import torchvision.models as models
+    ctor = getattr(models, name)
+    try:
+        if weights_enum is not None:
+            return ctor(weights=getattr(getattr(models, weights_enum), "DEFAULT"))
+        return ctor(**kw)
+    except Exception as e:              # no network: fall back to random init, like a fresh clone
+        warnings.warn(f"{name}: pretrained weights unavailable ({type(e).__name__}); using random init")
+        return ctor(weights=None)
+
+
+class _TorchvisionTrunk(nn.Module):
+    def __init__(self, net):
+        super().__init__()
+        self.model = nn.Sequential(*list(net.children())[:-1])
+        for p in self.model.parameters():
+            p.requires_grad = True
+
+    def forward(self, x):
+        x = self.model(x)
+        x = F.adaptive_avg_pool2d(x, (1, 1))
+        return x.view(x.size(0), -1)
+
+
+class ImageEncoder(_TorchvisionTrunk):
+    """model.py:72-84 (DenseNet121 -> 1024-d)."""
+
+    def __init__(self):
+        super().__init__(_tv("densenet121", "DenseNet121_Weights"))
+
+
+class ImageEncoder_Resnet(_TorchvisionTrunk):
+    """model.py:87-99 (ResNet50 -> 2048-d)."""
+
+    def __init__(self):
+        super().__init__(_tv("resnet50", "ResNet50_Weights"))
+
+
+class ImageEncdoer_res18(_TorchvisionTrunk):
+    """model.py:117-129."""
+
+    def __init__(self):
+        super().__init__(_tv("resnet18", "ResNet18_Weights"))
+
+
+class ImageEncdoer_res101(_TorchvisionTrunk):
+    """model.py:132-144."""
+
+    def __init__(self):
+        super().__init__(_tv("resnet101", "ResNet101_Weights"))
+
+
+class ImageEncoder_VIT(nn.Module):
+    """model.py:102-114 (needs timm, which the reference imports unconditionally)."""
+
+    def __init__(self, model_name="vit_base_patch32_224", pretrained=True, trainable=True):
+        super().__init__()
+        import timm
+        self.model = timm.create_model(model_name, pretrained, num_classes=0, global_pool="avg")
+        for p in self.model.parameters():
+            p.requires_grad = trainable
+
+    def forward(self, x):
+        return self.model(x)
+
+
+_ENCODERS = {"resnet50": ImageEncoder_Resnet, "densenet121": ImageEncoder, "vit": ImageEncoder_VIT,
+             "res18": ImageEncdoer_res18, "res101": ImageEncdoer_res101}
+
+
+class mclSTExp_MLP(nn.Module):
+    """model.py:171-198 (attention-less variant; never instantiated by the reference)."""
+
+    def __init__(self, temperature, image_embedding, spot_embedding, projection_dim, dropout=0.):
+        super().__init__()
+        self.x_embed = nn.Embedding(65536, spot_embedding)
+        self.y_embed = nn.Embedding(65536, spot_embedding)
+        self.image_ecode = ImageEncoder()
+        self.image_projection = ProjectionHead(embedding_dim=image_embedding, projection_dim=projection_dim)
+        self.spot_projection = ProjectionHead(embedding_dim=spot_embedding, projection_dim=projection_dim)
+        self.temperature = temperature
+
+    def forward(self, batch):
+        image_embeddings = self.image_projection(self.image_ecode(batch["image"]))
+        spot_features = embed_add(batch["expression"], batch["position"], self.x_embed.weight,
+                                  self.y_embed.weight)
+        spot_embeddings = self.spot_projection(spot_features)
+        return contrastive_loss(spot_embeddings, image_embeddings, self.temperature, "eye")
+
+
+class mclSTExp_Attention(nn.Module):
+    """model.py:201-247.  ``targets`` / ``soft_scale`` (not in the reference signature, default
+    the reference's identity targets) select the BLEEP soft-target loss the north star names."""
+
+    def __init__(self, encoder_name, temperature, image_dim, spot_dim, projection_dim, heads_num,
+                 heads_dim, head_layers, dropout=0., targets="eye", soft_scale="div"):
+        super().__init__()
+        self.x_embed = nn.Embedding(65536, spot_dim)
+        self.y_embed = nn.Embedding(65536, spot_dim)
+        if encoder_name in _ENCODERS:
+            self.image_encoder = _ENCODERS[encoder_name]()
+        self.spot_encoder = nn.Sequential(
+            *[attn_block(spot_dim, heads=heads_num, dim_head=heads_dim, mlp_dim=spot_dim, dropout=0.)
+              for _ in range(head_layers)])
+        self.image_projection = ProjectionHead(embedding_dim=image_dim, projection_dim=projection_dim)
+        self.spot_projection = ProjectionHead(embedding_dim=spot_dim, projection_dim=projection_dim)
+        self.temperature = temperature
+        self.targets = targets
+        self.soft_scale = soft_scale
+
+    def embed_spots(self, expression, position):
+        """model.py:230-240 (== evel_her2st.py:52-69): spot embeddings [B, projection_dim]."""
+        h = embed_add(expression, position, self.x_embed.weight, self.y_embed.weight)
+        h = h.unsqueeze(dim=0)
+        h = self.spot_encoder(h)
+        h = self.spot_projection(h)
+        return h.squeeze(dim=0)
+
+    def forward(self, batch):
+        image_features = self.image_encoder(batch["image"])
+        image_embeddings = self.image_projection(image_features)
+        spot_embeddings = self.embed_spots(batch["expression"], batch["position"])
+        return contrastive_loss(spot_embeddings, image_embeddings, self.temperature, self.targets,
+                                self.soft_scale)

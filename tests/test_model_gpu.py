@@ -1,0 +1,129 @@
+"""The drop-in module surface (mclstexp_b200.model) against the reference's own forward /
+backward (tests/golden/model.npz, produced by running /root/reference/model.py) and the oracle."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from mclstexp_b200 import model as mm, synth
+from oracle import oracle
+from conftest import golden_checksum
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-3
+
+
+def _build(m, targets="eye"):
+    net = mm.mclSTExp_Attention(encoder_name="none", temperature=m["T"], image_dim=m["E"],
+                                spot_dim=m["G"], projection_dim=256, heads_num=m["heads"],
+                                heads_dim=m["dim_head"], head_layers=m["layers"], dropout=0.,
+                                targets=targets)
+    net.image_encoder = nn.Identity()          # the CNN is outside the path: features go straight in
+    sd = oracle.make_state_dict(m["G"], m["E"], 256, m["heads"], m["dim_head"], m["layers"], m["seed"])
+    res = net.load_state_dict(sd, strict=True)           # identical keys and shapes as the reference
+    assert not res.missing_keys and not res.unexpected_keys
+    return net.cuda(), sd
+
+
+def _inputs(m):
+    feats = torch.tensor(synth.image_features(m["B"], m["E"], m["seed"] + 1))
+    expr = torch.tensor(synth.expression(m["B"], m["G"], m["seed"] + 2))
+    pos = torch.tensor(synth.positions(m["B"], m["seed"] + 3, m["kind"]))
+    return feats, expr, pos
+
+
+def _close(got, want, name, rtol=RTOL):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else got
+    scale = np.abs(want).max() + 1e-30
+    assert np.linalg.norm(got - want) <= rtol * np.linalg.norm(want) + 1e-9, name
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=rtol * scale, err_msg=name)
+
+
+@pytest.mark.parametrize("case", ["small", "odd"])
+def test_full_path_forward_backward_vs_reference(golden_model, case):
+    z, meta = golden_model
+    m = meta[case]
+    net, sd = _build(m)
+    feats, expr, pos = _inputs(m)
+    assert golden_checksum(feats, expr, pos, sd["x_embed.weight"][:64],
+                           sd["spot_projection.fc.weight"]) == m["checksum"]
+    loss = net({"image": feats.cuda(), "expression": expr.cuda(), "position": pos.cuda()})
+    assert loss.dim() == 0
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), z[f"{case}/loss"], rtol=RTOL)
+    names = {k for k, _ in net.named_parameters()}
+    ref_names = {k.split("/grad/")[1] for k in z.files if k.startswith(f"{case}/grad/")}
+    assert names == ref_names
+    for k, p in net.named_parameters():
+        g = z[f"{case}/grad/{k}"]
+        if k in ("x_embed.weight", "y_embed.weight"):
+            rows = torch.tensor(z[f"{case}/grad_rows/{k}"].astype(np.int64))
+            mine = p.grad[rows.cuda()]
+            mask = torch.ones(p.shape[0], dtype=torch.bool)
+            mask[rows] = False
+            assert float(p.grad[mask.cuda()].abs().sum()) == 0.0       # dense grad, zero elsewhere
+            assert p.grad.shape == p.shape
+        else:
+            mine = p.grad
+        _close(mine, g, k)
+
+
+@pytest.mark.parametrize("case", ["small", "odd"])
+def test_eval_attribute_surface_vs_reference(golden_model, case):
+    """What evel_her2st.py:48-69 does with the model's attributes, under no_grad."""
+    z, meta = golden_model
+    m = meta[case]
+    net, _ = _build(m)
+    net.eval()
+    feats, expr, pos = (t.cuda() for t in _inputs(m))
+    with torch.no_grad():
+        image_embeddings = net.image_projection(net.image_encoder(feats))
+        x = pos[:, 0].long()
+        y = pos[:, 1].long()
+        spot_feature = expr + net.x_embed(x) + net.y_embed(y)          # the caller's own torch ops
+        spot_features = spot_feature.unsqueeze(dim=0)
+        attn0 = net.spot_encoder[0].attn(spot_features)
+        blk0 = net.spot_encoder[0](spot_features)
+        enc = net.spot_encoder(spot_features)
+        spot_embedding = net.spot_projection(enc).squeeze(dim=0)
+        fused = net.embed_spots(expr, pos)
+    _close(image_embeddings, z[f"{case}/image_embeddings"], "image_embeddings")
+    _close(attn0, z[f"{case}/attn0"], "attn0")
+    _close(blk0, z[f"{case}/block0"], "block0")
+    _close(enc, z[f"{case}/encoder"], "encoder")
+    _close(spot_embedding, z[f"{case}/spot_embeddings"], "spot_embeddings")
+    _close(fused, z[f"{case}/spot_embeddings"], "embed_spots")
+
+
+@pytest.mark.parametrize("targets", ["eye", "soft"])
+def test_cfg2_shaped_step_vs_oracle(targets):
+    """BASELINE cfg2 shape at reduced batch (B=256, G=171 cSCC genes): loss + grads vs the oracle."""
+    m = dict(G=171, E=1024, heads=8, dim_head=64, layers=2, B=256, T=1.0, kind="st", seed=21)
+    net, sd = _build(m, targets)
+    feats, expr, pos = _inputs(m)
+    loss = net({"image": feats.cuda(), "expression": expr.cuda(), "position": pos.cuda()})
+    loss.backward()
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = oracle.path_loss_ref(params, feats, expr, pos, m["T"], m["heads"], m["layers"], targets)
+    ref.backward()
+    np.testing.assert_allclose(loss.item(), ref.item(), rtol=RTOL)
+    for k, p in net.named_parameters():
+        want = params[k].grad.numpy()
+        _close(p.grad, want, k, rtol=2e-3)
+
+
+def test_position_out_of_range_raises():
+    m = dict(G=16, E=8, heads=2, dim_head=8, layers=1, B=4, T=1.0, kind="st", seed=3)
+    net, _ = _build(m)
+    feats, expr, pos = _inputs(m)
+    pos[1, 0] = 70000.0
+    loss = net({"image": feats.cuda(), "expression": expr.cuda(), "position": pos.cuda()})
+    with pytest.raises(IndexError):
+        loss.backward()
+
+
+def test_cpu_tensors_are_rejected():
+    from mclstexp_b200._lib import MclstError
+    head = mm.ProjectionHead(8, 256)
+    with pytest.raises(MclstError):
+        head(torch.zeros(2, 8))
