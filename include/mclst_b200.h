@@ -130,6 +130,35 @@ int mclst_weighted_gather(const void* expression_key, int64_t n_bank, int64_t ld
                           float* out_partial /* [n_query, genes] float32, overwritten */,
                           mclst_stream_t stream);
 
+/* Row-sharded form (embedding all-gather over NVLink): spot_emb /
+ * image_emb are the ALL-GATHERED [batch, dim] embeddings; this rank owns the rows
+ * [row0, row0 + rows) (row0 a multiple of 128).  `stats` is a caller-owned device block
+ * [6][batch] float32 (rl, cl, za, wbar, cs, diag) whose local slices each phase fills and
+ * which the caller all-gathers between phases:
+ *   phase 1 packs the operands and writes rl, cl, za, diag of the local rows;
+ *   phase 2 (after gathering rl, cl, za) writes wbar, cs of the local rows (soft targets);
+ *   phase 3 (after gathering wbar, cs) writes this rank's additive loss contribution to
+ *           *loss_out and, if d_spot/d_image are given, the gradients of the LOCAL rows
+ *           ([rows, dim]); no gradient exchange is needed afterwards.
+ * The same workspace must be passed to all three phases. */
+int mclst_contrastive_loss_phase(const float* spot_emb, int64_t ld_s, const float* image_emb,
+                                 int64_t ld_i, int batch, int dim, float temperature, int target_mode,
+                                 int64_t row0, int64_t rows, int phase, float* stats, float* loss_out,
+                                 float* d_spot, int64_t ld_ds, float* d_image, int64_t ld_di,
+                                 void* workspace, size_t workspace_bytes, mclst_stream_t stream);
+
+/* Sharded-bank merge (no reference counterpart: the reference is single-process).  `values`,
+ * `indices`, `distances` are the per-shard results gathered as [n_lists, n_query, top_k];
+ * the output is the global top_k by (value descending, index ascending) with the distances
+ * carried along (distances / out_distances may both be null). */
+int mclst_merge_topk(const float* values, const int64_t* indices, const float* distances,
+                     int n_lists, int64_t n_query, int top_k, float* out_values,
+                     int64_t* out_indices, float* out_distances, mclst_stream_t stream);
+/* Normalised weights [n_query, top_k] from neighbour distances (L1 for MCLST_W_INV_SQ_L1, L2
+ * otherwise) or similarities -- the weight formulas of mclst_weighted_average. */
+int mclst_neighbor_weights(const float* distances, const float* values, int64_t n_query, int top_k,
+                           int weight_mode, float* out_weights, mclst_stream_t stream);
+
 /* ---------------------------------------------------------------- contrastive loss ------ */
 
 /* Symmetric image<->spot contrastive loss, forward and backward in one call.
@@ -139,8 +168,9 @@ int mclst_weighted_gather(const void* expression_key, int64_t n_bank, int64_t ld
  *   MCLST_T_SOFT_MUL  baselines/Bleep/models.py:70-79: ... /2*T; targets stay in the graph.
  * spot_emb, image_emb: [batch, dim] float32.  loss_out: one float32 (device).  d_spot /
  * d_image (both or neither): gradients of the loss w.r.t. the two inputs.  No batch x batch
- * matrix is held beyond one row block (MCLST_LOSS_SCRATCH_MB, default 1024). */
-int mclst_contrastive_loss_workspace_bytes(int batch, int dim, int target_mode, int want_grad,
+ * matrix is held beyond one row block (MCLST_LOSS_SCRATCH_MB, default 1024).  The workspace
+ * query takes the number of rows this call owns (= batch here). */
+int mclst_contrastive_loss_workspace_bytes(int batch, int dim, int target_mode, int64_t rows_local,
                                            size_t* bytes);
 int mclst_contrastive_loss(const float* spot_emb, int64_t ld_s, const float* image_emb, int64_t ld_i,
                            int batch, int dim, float temperature, int target_mode, float* loss_out,

@@ -89,12 +89,11 @@ soft_pass2_kernel(const float* __restrict__ P1, const float* __restrict__ P3, in
 // loss = (1/2B) sum_r term_r; term = wbar (soft) or rl + cl - 2 diag (eye).  One block.
 __global__ void __launch_bounds__(LS_THREADS)
 loss_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                   const float* __restrict__ d, int B, float* __restrict__ out) {
-  __shared__ float sh[LS_THREADS / 32];
+                   const float* __restrict__ d, int r_begin, int r_end, int B,
+                   float* __restrict__ out) {
   __shared__ double shd[LS_THREADS / 32];
-  (void)sh;
   double acc = 0.0;
-  for (int r = threadIdx.x; r < B; r += LS_THREADS)
+  for (int r = r_begin + threadIdx.x; r < r_end; r += LS_THREADS)
     acc += b ? (double)a[r] + (double)b[r] - 2.0 * (double)d[r] : (double)a[r];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) shd[threadIdx.x >> 5] = acc;
@@ -192,11 +191,13 @@ struct LossPlan {
   PackedOperand XT_IS, XT_SI;      // [D, 2*B64] (soft) or [D, B64] (eye), transposed packs
   PackedOperand GA, GB;            // [R, 2*B64] / [R, B64]
   float *P1, *P2, *P3;
-  float *rl, *cl, *za, *wbar, *cs, *diag;
+  float *rl, *cl, *za, *wbar, *cs, *diag;   // views into the stats block [6][B]
+  float* stats_ws;
   size_t bytes;
 };
 
-static LossPlan plan_loss(void* ws, size_t cap, int B, int D, int soft, int want_grad, size_t budget) {
+static LossPlan plan_loss(void* ws, size_t cap, int B, int D, int soft, int want_grad, size_t budget,
+                          int64_t rows_local) {
   LossPlan L{};
   L.B = B; L.D = D; L.soft = soft;
   L.B64 = (int64_t)align_up((size_t)B, 64);
@@ -204,9 +205,9 @@ static LossPlan plan_loss(void* ws, size_t cap, int B, int D, int soft, int want
   const size_t per_row = (size_t)L.B64 * (12 + (want_grad ? (soft ? 16 : 8) : 0));
   int64_t R = (int64_t)(budget / std::max<size_t>(per_row, 1));
   R = std::max<int64_t>(128, R / 128 * 128);
-  R = std::min<int64_t>(R, (int64_t)align_up((size_t)B, 128));
+  R = std::min<int64_t>(R, (int64_t)align_up((size_t)rows_local, 128));
   L.R = R;
-  L.nblocks = ceil_div(B, R);
+  L.nblocks = ceil_div(rows_local, R);
   Arena a(ws, cap);
   L.flags = a.take<uint32_t>(16);
   L.Sp = take_operand(a, B, D, true, true, 1);
@@ -222,8 +223,7 @@ static LossPlan plan_loss(void* ws, size_t cap, int B, int D, int soft, int want
   L.P1 = a.take<float>((size_t)R * L.B64);
   L.P2 = a.take<float>((size_t)R * L.B64);
   L.P3 = soft ? a.take<float>((size_t)R * L.B64) : nullptr;
-  L.rl = a.take<float>((size_t)B); L.cl = a.take<float>((size_t)B); L.za = a.take<float>((size_t)B);
-  L.wbar = a.take<float>((size_t)B); L.cs = a.take<float>((size_t)B); L.diag = a.take<float>((size_t)B);
+  L.stats_ws = a.take<float>((size_t)6 * B);
   L.bytes = align_up(a.off, 256);
   return L;
 }
@@ -260,15 +260,129 @@ static int compute_blocks(const LossPlan& L, int64_t i0, int64_t rows, float inv
   return 0;
 }
 
+static void bind_stats(LossPlan& L, float* stats) {
+  const size_t B = (size_t)L.B;
+  L.rl = stats; L.cl = stats + B; L.za = stats + 2 * B; L.wbar = stats + 3 * B; L.cs = stats + 4 * B;
+  L.diag = stats + 5 * B;
+}
+
+// One phase of the loss for the rows [row0, row0 + rows) of the (all-gathered) batch.
+//   phase 1: pack operands; rl, cl, za (+ diag) of the local rows
+//   phase 2: wbar, cs of the local rows (soft targets; needs every rank's rl, cl, za)
+//   phase 3: local loss contribution and the gradients of the local rows (needs all stats)
+static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_emb, int64_t ld_i,
+                      int B, int D, float temperature, int target_mode, int64_t row0, int64_t rows,
+                      int phase, float* stats, float* loss_out, float* d_spot, int64_t ld_ds,
+                      float* d_image, int64_t ld_di, void* workspace, size_t workspace_bytes,
+                      cudaStream_t st) {
+  const int soft = target_mode != MCLST_T_EYE;
+  const int want_grad = 1;     // the layout always reserves the gradient operands (phase 3 may need them)
+  const float inv_t = 1.0f / temperature;
+  const float a_scale = target_mode == MCLST_T_SOFT_DIV ? 0.5f / temperature
+                      : target_mode == MCLST_T_SOFT_MUL ? 0.5f * temperature : 0.f;
+  LossPlan L = plan_loss(workspace, workspace_bytes, B, D, soft, want_grad, loss_budget(), rows);
+  MCLST_REQUIRE(L.bytes <= workspace_bytes, MCLST_ERR_WORKSPACE, "contrastive_loss: workspace %zu < %zu",
+                workspace_bytes, L.bytes);
+  bind_stats(L, stats ? stats : L.stats_ws);
+  int rc;
+  const int nkbD = L.Sp.nkb;
+  const bool single = L.nblocks == 1 && rows == B;     // P1/P2/P3 survive between phases
+  if (phase == 1) {
+    MCLST_CUDA(cudaMemsetAsync(L.flags, 0, 64, st));
+    prof_mark(st, "loss_pack");
+    if ((rc = launch_pack_split(spot_emb, B, D, ld_s, false, 1.f, L.Sp, 0, nkbD, L.flags, st))) return rc;
+    if ((rc = launch_pack_split(image_emb, B, D, ld_i, false, 1.f, L.Ip, 0, nkbD, L.flags, st))) return rc;
+    if (soft) {
+      if ((rc = launch_pack_split(image_emb, B, D, ld_i, false, 1.f, L.ISp, 0, nkbD, L.flags, st))) return rc;
+      if ((rc = launch_pack_split(spot_emb, B, D, ld_s, false, 1.f, L.ISp, nkbD, nkbD, L.flags, st))) return rc;
+    }
+    if (d_spot) {
+      const int nkbB = (int)(L.B64 / 64);
+      if ((rc = launch_pack_split(image_emb, B, D, ld_i, true, 1.f, L.XT_IS, 0, nkbB, L.flags, st))) return rc;
+      if ((rc = launch_pack_split(spot_emb, B, D, ld_s, true, 1.f, L.XT_SI, 0, nkbB, L.flags, st))) return rc;
+      if (soft) {
+        if ((rc = launch_pack_split(spot_emb, B, D, ld_s, true, 1.f, L.XT_IS, nkbB, nkbB, L.flags, st))) return rc;
+        if ((rc = launch_pack_split(image_emb, B, D, ld_i, true, 1.f, L.XT_SI, nkbB, nkbB, L.flags, st))) return rc;
+      }
+    }
+    prof_mark(st, "loss_stats");
+    for (int64_t b = 0; b < L.nblocks; ++b) {
+      const int64_t i0 = row0 + b * L.R, nr = std::min<int64_t>(L.R, row0 + rows - i0);
+      if ((rc = compute_blocks(L, i0, nr, inv_t, a_scale, true, st))) return rc;
+      row_lse_kernel<<<(unsigned)nr, LS_THREADS, 0, st>>>(L.P1, L.B64, B, i0, L.rl, L.diag);
+      MCLST_LAUNCH_CHECK();
+      row_lse_kernel<<<(unsigned)nr, LS_THREADS, 0, st>>>(L.P2, L.B64, B, i0, L.cl, nullptr);
+      MCLST_LAUNCH_CHECK();
+      if (soft) {
+        row_lse_kernel<<<(unsigned)nr, LS_THREADS, 0, st>>>(L.P3, L.B64, B, i0, L.za, nullptr);
+        MCLST_LAUNCH_CHECK();
+      }
+    }
+  } else if (phase == 2) {
+    if (soft) {
+      prof_mark(st, "loss_value");
+      for (int64_t b = 0; b < L.nblocks; ++b) {
+        const int64_t i0 = row0 + b * L.R, nr = std::min<int64_t>(L.R, row0 + rows - i0);
+        if (!single && (rc = compute_blocks(L, i0, nr, inv_t, a_scale, false, st))) return rc;
+        soft_pass2_kernel<<<(unsigned)nr, LS_THREADS, 0, st>>>(L.P1, L.P3, L.B64, B, i0, L.rl, L.cl,
+                                                             L.za, L.wbar, L.cs);
+        MCLST_LAUNCH_CHECK();
+      }
+    }
+  } else {
+    prof_mark(st, "loss_value");
+    if (soft) loss_reduce_kernel<<<1, LS_THREADS, 0, st>>>(L.wbar, nullptr, nullptr, (int)row0, (int)(row0 + rows), B, loss_out);
+    else loss_reduce_kernel<<<1, LS_THREADS, 0, st>>>(L.rl, L.cl, L.diag, (int)row0, (int)(row0 + rows), B, loss_out);
+    MCLST_LAUNCH_CHECK();
+    if (d_spot) {
+      prof_mark(st, "loss_grad");
+      for (int64_t b = 0; b < L.nblocks; ++b) {
+        const int64_t i0 = row0 + b * L.R, nr = std::min<int64_t>(L.R, row0 + rows - i0);
+        if (!single && (rc = compute_blocks(L, i0, nr, inv_t, a_scale, true, st))) return rc;
+        GradParams gp{};
+        gp.P1 = L.P1; gp.P2 = L.P2; gp.P3 = L.P3; gp.ld = L.B64; gp.B = B; gp.rows = (int)nr;
+        gp.soft = soft; gp.row0 = i0; gp.rl = L.rl; gp.cl = L.cl; gp.za = L.za; gp.wbar = L.wbar;
+        gp.cs = L.cs; gp.inv_t = inv_t; gp.a_scale = a_scale;
+        gp.ga_hi = L.GA.hi; gp.ga_lo = L.GA.lo; gp.gb_hi = L.GB.hi; gp.gb_lo = L.GB.lo;
+        gp.nkb_total = L.GA.nkb; gp.nkb_half = (int)(L.B64 / 64);
+        const int64_t rows_pad = (int64_t)align_up((size_t)nr, 128);
+        const int64_t threads = rows_pad * gp.nkb_half * 8;
+        grad_factor_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, st>>>(gp, rows_pad);
+        MCLST_LAUNCH_CHECK();
+        GemmParams g{};
+        g.nseg = 3; g.batch = 1; g.M = nr; g.N = D; g.nkb = L.GA.nkb; g.alpha = 0.5f / (float)B;
+        g.a_hi = L.GA.hi; g.a_lo = L.GA.lo; g.b_hi = L.XT_IS.hi; g.b_lo = L.XT_IS.lo;
+        g.c = d_spot + (i0 - row0) * ld_ds; g.ldc = ld_ds;
+        if ((rc = launch_gemm_tn(g, st))) return rc;
+        g.a_hi = L.GB.hi; g.a_lo = L.GB.lo; g.b_hi = L.XT_SI.hi; g.b_lo = L.XT_SI.lo;
+        g.c = d_image + (i0 - row0) * ld_di; g.ldc = ld_di;
+        if ((rc = launch_gemm_tn(g, st))) return rc;
+      }
+    }
+    prof_mark(st, "end");
+  }
+  return 0;
+}
+
 }  // namespace mclst
 
 using namespace mclst;
 
 extern "C" int mclst_contrastive_loss_workspace_bytes(int batch, int dim, int target_mode,
-                                                      int want_grad, size_t* bytes) {
-  MCLST_REQUIRE(bytes && batch >= 1 && dim >= 1 && target_mode >= 0 && target_mode <= 2,
-                MCLST_ERR_INVALID, "contrastive_loss_workspace: bad args");
-  *bytes = plan_loss(nullptr, 0, batch, dim, target_mode != MCLST_T_EYE, want_grad, loss_budget()).bytes;
+                                                      int64_t rows_local, size_t* bytes) {
+  MCLST_REQUIRE(bytes && batch >= 1 && dim >= 1 && target_mode >= 0 && target_mode <= 2 &&
+                rows_local >= 1 && rows_local <= batch, MCLST_ERR_INVALID,
+                "contrastive_loss_workspace: bad args");
+  *bytes = plan_loss(nullptr, 0, batch, dim, target_mode != MCLST_T_EYE, 1, loss_budget(), rows_local).bytes;
+  return 0;
+}
+
+static int check_loss_args(const float* s, const float* i, int batch, int dim, float t, int mode,
+                           const void* ws) {
+  MCLST_REQUIRE(s && i && ws, MCLST_ERR_INVALID, "contrastive_loss: null pointer");
+  MCLST_REQUIRE(batch >= 1 && dim >= 1 && t > 0.f, MCLST_ERR_INVALID,
+                "contrastive_loss: bad batch/dim/temperature");
+  MCLST_REQUIRE(mode >= 0 && mode <= 2, MCLST_ERR_INVALID, "contrastive_loss: bad target mode");
   return 0;
 }
 
@@ -278,98 +392,34 @@ extern "C" int mclst_contrastive_loss(const float* spot_emb, int64_t ld_s, const
                                       int64_t ld_ds, float* d_image, int64_t ld_di,
                                       void* workspace, size_t workspace_bytes,
                                       mclst_stream_t stream) {
-  MCLST_REQUIRE(spot_emb && image_emb && loss_out && workspace, MCLST_ERR_INVALID,
-                "contrastive_loss: null pointer");
-  MCLST_REQUIRE(batch >= 1 && dim >= 1 && temperature > 0.f, MCLST_ERR_INVALID,
-                "contrastive_loss: bad batch/dim/temperature");
-  MCLST_REQUIRE(target_mode >= 0 && target_mode <= 2, MCLST_ERR_INVALID, "contrastive_loss: bad target mode");
+  int rc;
+  if ((rc = check_loss_args(spot_emb, image_emb, batch, dim, temperature, target_mode, workspace))) return rc;
+  MCLST_REQUIRE(loss_out, MCLST_ERR_INVALID, "contrastive_loss: null loss_out");
   MCLST_REQUIRE((d_spot == nullptr) == (d_image == nullptr), MCLST_ERR_INVALID,
                 "contrastive_loss: pass both gradients or neither");
   cudaStream_t st = (cudaStream_t)stream;
-  const int B = batch, D = dim;
-  const int soft = target_mode != MCLST_T_EYE;
-  const int want_grad = d_spot != nullptr;
-  const float inv_t = 1.0f / temperature;
-  const float a_scale = target_mode == MCLST_T_SOFT_DIV ? 0.5f / temperature
-                      : target_mode == MCLST_T_SOFT_MUL ? 0.5f * temperature : 0.f;
-  LossPlan L = plan_loss(workspace, workspace_bytes, B, D, soft, want_grad, loss_budget());
-  MCLST_REQUIRE(L.bytes <= workspace_bytes, MCLST_ERR_WORKSPACE, "contrastive_loss: workspace %zu < %zu",
-                workspace_bytes, L.bytes);
-  int rc;
-  MCLST_CUDA(cudaMemsetAsync(L.flags, 0, 64, st));
-  prof_mark(st, "loss_pack");
-  const int nkbD = L.Sp.nkb;
-  if ((rc = launch_pack_split(spot_emb, B, D, ld_s, false, 1.f, L.Sp, 0, nkbD, L.flags, st))) return rc;
-  if ((rc = launch_pack_split(image_emb, B, D, ld_i, false, 1.f, L.Ip, 0, nkbD, L.flags, st))) return rc;
-  if (soft) {
-    if ((rc = launch_pack_split(image_emb, B, D, ld_i, false, 1.f, L.ISp, 0, nkbD, L.flags, st))) return rc;
-    if ((rc = launch_pack_split(spot_emb, B, D, ld_s, false, 1.f, L.ISp, nkbD, nkbD, L.flags, st))) return rc;
-  }
-  if (want_grad) {
-    const int nkbB = (int)(L.B64 / 64);
-    if ((rc = launch_pack_split(image_emb, B, D, ld_i, true, 1.f, L.XT_IS, 0, nkbB, L.flags, st))) return rc;
-    if ((rc = launch_pack_split(spot_emb, B, D, ld_s, true, 1.f, L.XT_SI, 0, nkbB, L.flags, st))) return rc;
-    if (soft) {
-      if ((rc = launch_pack_split(spot_emb, B, D, ld_s, true, 1.f, L.XT_IS, nkbB, nkbB, L.flags, st))) return rc;
-      if ((rc = launch_pack_split(image_emb, B, D, ld_i, true, 1.f, L.XT_SI, nkbB, nkbB, L.flags, st))) return rc;
-    }
-  }
-  const bool single = L.nblocks == 1;
-  // ---- sweep 1: rl, cl, za (+ diagonal for the identity targets)
-  prof_mark(st, "loss_stats");
-  for (int64_t b = 0; b < L.nblocks; ++b) {
-    const int64_t i0 = b * L.R, rows = std::min<int64_t>(L.R, B - i0);
-    if ((rc = compute_blocks(L, i0, rows, inv_t, a_scale, true, st))) return rc;
-    row_lse_kernel<<<(unsigned)rows, LS_THREADS, 0, st>>>(L.P1, L.B64, B, i0, L.rl, L.diag);
-    MCLST_LAUNCH_CHECK();
-    row_lse_kernel<<<(unsigned)rows, LS_THREADS, 0, st>>>(L.P2, L.B64, B, i0, L.cl, nullptr);
-    MCLST_LAUNCH_CHECK();
-    if (soft) {
-      row_lse_kernel<<<(unsigned)rows, LS_THREADS, 0, st>>>(L.P3, L.B64, B, i0, L.za, nullptr);
-      MCLST_LAUNCH_CHECK();
-    }
-  }
-  // ---- sweep 2: wbar, cs, loss
-  prof_mark(st, "loss_value");
-  if (soft) {
-    for (int64_t b = 0; b < L.nblocks; ++b) {
-      const int64_t i0 = b * L.R, rows = std::min<int64_t>(L.R, B - i0);
-      if (!single && (rc = compute_blocks(L, i0, rows, inv_t, a_scale, false, st))) return rc;
-      soft_pass2_kernel<<<(unsigned)rows, LS_THREADS, 0, st>>>(L.P1, L.P3, L.B64, B, i0, L.rl, L.cl,
-                                                               L.za, L.wbar, L.cs);
-      MCLST_LAUNCH_CHECK();
-    }
-    loss_reduce_kernel<<<1, LS_THREADS, 0, st>>>(L.wbar, nullptr, nullptr, B, loss_out);
-  } else {
-    loss_reduce_kernel<<<1, LS_THREADS, 0, st>>>(L.rl, L.cl, L.diag, B, loss_out);
-  }
-  MCLST_LAUNCH_CHECK();
-  // ---- sweep 3: gradients
-  if (want_grad) {
-    prof_mark(st, "loss_grad");
-    for (int64_t b = 0; b < L.nblocks; ++b) {
-      const int64_t i0 = b * L.R, rows = std::min<int64_t>(L.R, B - i0);
-      if (!single && (rc = compute_blocks(L, i0, rows, inv_t, a_scale, true, st))) return rc;
-      GradParams gp{};
-      gp.P1 = L.P1; gp.P2 = L.P2; gp.P3 = L.P3; gp.ld = L.B64; gp.B = B; gp.rows = (int)rows;
-      gp.soft = soft; gp.row0 = i0; gp.rl = L.rl; gp.cl = L.cl; gp.za = L.za; gp.wbar = L.wbar;
-      gp.cs = L.cs; gp.inv_t = inv_t; gp.a_scale = a_scale;
-      gp.ga_hi = L.GA.hi; gp.ga_lo = L.GA.lo; gp.gb_hi = L.GB.hi; gp.gb_lo = L.GB.lo;
-      gp.nkb_total = L.GA.nkb; gp.nkb_half = (int)(L.B64 / 64);
-      const int64_t rows_pad = (int64_t)align_up((size_t)rows, 128);
-      const int64_t threads = rows_pad * gp.nkb_half * 8;
-      grad_factor_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, st>>>(gp, rows_pad);
-      MCLST_LAUNCH_CHECK();
-      GemmParams g{};
-      g.nseg = 3; g.batch = 1; g.M = rows; g.N = D; g.nkb = L.GA.nkb; g.alpha = 0.5f / (float)B;
-      g.a_hi = L.GA.hi; g.a_lo = L.GA.lo; g.b_hi = L.XT_IS.hi; g.b_lo = L.XT_IS.lo;
-      g.c = d_spot + i0 * ld_ds; g.ldc = ld_ds;
-      if ((rc = launch_gemm_tn(g, st))) return rc;
-      g.a_hi = L.GB.hi; g.a_lo = L.GB.lo; g.b_hi = L.XT_SI.hi; g.b_lo = L.XT_SI.lo;
-      g.c = d_image + i0 * ld_di; g.ldc = ld_di;
-      if ((rc = launch_gemm_tn(g, st))) return rc;
-    }
-  }
-  prof_mark(st, "end");
+  for (int phase = 1; phase <= 3; ++phase)
+    if ((rc = loss_phase(spot_emb, ld_s, image_emb, ld_i, batch, dim, temperature, target_mode, 0, batch,
+                         phase, nullptr, loss_out, d_spot, ld_ds, d_image, ld_di, workspace,
+                         workspace_bytes, st))) return rc;
   return 0;
+}
+
+extern "C" int mclst_contrastive_loss_phase(const float* spot_emb, int64_t ld_s,
+                                            const float* image_emb, int64_t ld_i, int batch, int dim,
+                                            float temperature, int target_mode, int64_t row0,
+                                            int64_t rows, int phase, float* stats, float* loss_out,
+                                            float* d_spot, int64_t ld_ds, float* d_image,
+                                            int64_t ld_di, void* workspace, size_t workspace_bytes,
+                                            mclst_stream_t stream) {
+  int rc;
+  if ((rc = check_loss_args(spot_emb, image_emb, batch, dim, temperature, target_mode, workspace))) return rc;
+  MCLST_REQUIRE(stats && phase >= 1 && phase <= 3, MCLST_ERR_INVALID, "contrastive_loss_phase: bad phase/stats");
+  MCLST_REQUIRE(row0 >= 0 && rows >= 1 && row0 + rows <= batch && row0 % 128 == 0, MCLST_ERR_INVALID,
+                "contrastive_loss_phase: row range [%lld, +%lld) must start on a multiple of 128",
+                (long long)row0, (long long)rows);
+  MCLST_REQUIRE(phase != 3 || loss_out, MCLST_ERR_INVALID, "contrastive_loss_phase: null loss_out");
+  return loss_phase(spot_emb, ld_s, image_emb, ld_i, batch, dim, temperature, target_mode, row0, rows,
+                    phase, stats, loss_out, d_spot, ld_ds, d_image, ld_di, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
 }

@@ -316,3 +316,144 @@ extern "C" int mclst_weighted_gather(const void* expression_key, int64_t n_bank,
   MCLST_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------- sharded-bank merge
+// Candidate lists gathered from R ranks -> global top-k by (value desc, index asc), carrying
+// the neighbour distance along.  One warp per query; entries sorted in shared memory.
+namespace mclst {
+
+__global__ void __launch_bounds__(128)
+merge_topk_kernel(const float* __restrict__ vals, const int64_t* __restrict__ idx,
+                  const float* __restrict__ dist, int R, int64_t Q, int k,
+                  float* __restrict__ out_val, int64_t* __restrict__ out_idx,
+                  float* __restrict__ out_dist, int per_warp) {
+  extern __shared__ __align__(16) unsigned char mg_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (q >= Q) return;
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(mg_smem) + (size_t)warp * per_warp;
+  unsigned short* slot = reinterpret_cast<unsigned short*>(
+      reinterpret_cast<unsigned long long*>(mg_smem) + (size_t)(blockDim.x >> 5) * per_warp) +
+      (size_t)warp * per_warp;
+  const int M = R * k;
+  int P = 1;
+  while (P < M) P <<= 1;
+  for (int i = lane; i < P; i += 32) {
+    if (i < M) {
+      const int r = i / k, j = i - r * k;
+      const size_t src = ((size_t)r * Q + q) * k + j;
+      const float v = vals[src];
+      const uint32_t kv = (v != v) ? 0xffffffffu : f2ord(v);
+      key[i] = ((unsigned long long)kv << 32) | (unsigned long long)(0xffffffffu - (uint32_t)idx[src]);
+    } else {
+      key[i] = 0ull;
+    }
+    slot[i] = (unsigned short)i;
+  }
+  __syncwarp();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = lane; t < (P >> 1); t += 32) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = key[lo], b = key[hi];
+        if ((a < b) == desc) {
+          key[lo] = b; key[hi] = a;
+          const unsigned short s = slot[lo]; slot[lo] = slot[hi]; slot[hi] = s;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int j = lane; j < k; j += 32) {
+    const int i = slot[j];
+    const int r = i / k, jj = i - r * k;
+    const size_t src = ((size_t)r * Q + q) * k + jj;
+    out_val[q * k + j] = vals[src];
+    out_idx[q * k + j] = idx[src];
+    if (out_dist) out_dist[q * k + j] = dist[src];
+  }
+}
+
+// normalised weights [Q,k] from neighbour distances (L1 norm, or L2 norm) / similarities
+__global__ void __launch_bounds__(128)
+weights_kernel(const float* __restrict__ dist, const float* __restrict__ values, int64_t Q, int k,
+               int mode, float* __restrict__ w) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const float* d = dist ? dist + q * k : nullptr;
+  const float* v = values ? values + q * k : nullptr;
+  float* o = w + q * k;
+  float zero_cnt = 0.f;
+  if (mode == MCLST_W_INV_SQ_L1 || mode == MCLST_W_INV_SQ_L2)
+    for (int j = lane; j < k; j += 32) zero_cnt += (d[j] == 0.f) ? 1.f : 0.f;
+  zero_cnt = warp_sum(zero_cnt);
+  const float d_best = (mode == MCLST_W_BLEEP_EXP) ? d[0] : 0.f;
+  float sum = 0.f;
+  for (int j = lane; j < k; j += 32) {
+    float x;
+    if (mode == MCLST_W_INV_SQ_L1 || mode == MCLST_W_INV_SQ_L2) {
+      const float a = d[j];
+      x = zero_cnt > 0.f ? (a == 0.f ? 1.f : 0.f) : __frcp_rn(a * a);
+    } else if (mode == MCLST_W_SIMILARITY) {
+      x = v[j];
+    } else if (mode == MCLST_W_BLEEP_EXP) {
+      x = expf(-(d[j] * d[j] - d_best * d_best + 1.0f));
+    } else {
+      x = 1.f;
+    }
+    o[j] = x;
+    sum += x;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const float inv = 1.f / sum;
+  for (int j = lane; j < k; j += 32) o[j] *= inv;
+}
+
+}  // namespace mclst
+
+extern "C" int mclst_merge_topk(const float* values, const int64_t* indices, const float* distances,
+                                int n_lists, int64_t n_query, int top_k, float* out_values,
+                                int64_t* out_indices, float* out_distances, mclst_stream_t stream) {
+  MCLST_REQUIRE(values && indices && out_values && out_indices, MCLST_ERR_INVALID, "merge_topk: null");
+  MCLST_REQUIRE((distances == nullptr) == (out_distances == nullptr), MCLST_ERR_INVALID,
+                "merge_topk: distances in and out go together");
+  MCLST_REQUIRE(n_lists >= 1 && top_k >= 1 && (int64_t)n_lists * top_k <= 16384, MCLST_ERR_UNSUPPORTED,
+                "merge_topk: n_lists * top_k = %lld > 16384", (long long)n_lists * top_k);
+  if (n_query == 0) return 0;
+  int per_warp = 1;
+  while (per_warp < n_lists * top_k) per_warp <<= 1;
+  int wpb = 4;
+  while (wpb > 1 && (size_t)wpb * per_warp * 10 > 160 * 1024) wpb >>= 1;
+  const size_t smem = (size_t)wpb * per_warp * 10;
+  static size_t attr = 0;
+  if (smem > attr && smem > 48 * 1024) {
+    MCLST_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  prof_mark((cudaStream_t)stream, "merge_topk");
+  merge_topk_kernel<<<(unsigned)ceil_div(n_query, wpb), wpb * 32, smem, (cudaStream_t)stream>>>(
+      values, indices, distances, n_lists, n_query, top_k, out_values, out_indices, out_distances, per_warp);
+  MCLST_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mclst_neighbor_weights(const float* distances, const float* values, int64_t n_query,
+                                      int top_k, int weight_mode, float* out_weights,
+                                      mclst_stream_t stream) {
+  MCLST_REQUIRE(out_weights, MCLST_ERR_INVALID, "neighbor_weights: null");
+  MCLST_REQUIRE(weight_mode >= 0 && weight_mode <= MCLST_W_BLEEP_EXP, MCLST_ERR_INVALID, "neighbor_weights: mode");
+  const bool need_d = weight_mode == MCLST_W_INV_SQ_L1 || weight_mode == MCLST_W_INV_SQ_L2 ||
+                      weight_mode == MCLST_W_BLEEP_EXP;
+  MCLST_REQUIRE(!need_d || distances, MCLST_ERR_INVALID, "neighbor_weights: distances required");
+  MCLST_REQUIRE(weight_mode != MCLST_W_SIMILARITY || values, MCLST_ERR_INVALID, "neighbor_weights: values required");
+  if (n_query == 0) return 0;
+  prof_mark((cudaStream_t)stream, "neighbor_weights");
+  weights_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, (cudaStream_t)stream>>>(
+      distances, values, n_query, top_k, weight_mode, out_weights);
+  MCLST_LAUNCH_CHECK();
+  return 0;
+}

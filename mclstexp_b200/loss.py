@@ -28,7 +28,7 @@ def contrastive_loss_fwd_bwd(spot_emb: torch.Tensor, image_emb: torch.Tensor, te
     B, D = S.shape
     lib = load()
     nbytes = C.c_size_t()
-    check(lib.mclst_contrastive_loss_workspace_bytes(B, D, mode, int(want_grad), C.byref(nbytes)),
+    check(lib.mclst_contrastive_loss_workspace_bytes(B, D, mode, B, C.byref(nbytes)),
           "contrastive_loss_workspace_bytes")
     ws = _workspace(nbytes.value, S.device)
     loss = torch.empty((), dtype=torch.float32, device=S.device)

@@ -1,0 +1,64 @@
+"""Multi-GPU parity check, launched as:  torchrun --nproc-per-node R tests/dist_gpu_check.py
+R-rank sharded retrieval / loss must equal the single-GPU result on the concatenated inputs
+(index-exact for top-k, 1e-3 for the rest)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mclstexp_b200 import retrieval, synth, loss as mloss                      # noqa: E402
+from mclstexp_b200.distributed import BankShard, contrastive_loss_sharded, retrieve_sharded   # noqa: E402
+
+
+def main():
+    rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    for mode, k in (("inv_sq_l2", 50), ("inv_sq_l1", 50), ("similarity", 200), ("bleep_exp", 50)):
+        N, Q, D, G = 40000, 1500, 256, 1000
+        bank = torch.tensor(synth.embeddings(N, D, 11, "clustered"), device=dev)
+        expr = torch.tensor(synth.expression(N, G, 12), device=dev)
+        qry = torch.tensor(synth.embeddings(Q, D, 13, "clustered"), device=dev)
+        shard = BankShard.from_full(bank, expr, rank, world)
+        idx, val, emb, ex = retrieve_sharded(shard, qry, k, mode, want_emb=True)
+        idx1, val1, emb1, ex1 = retrieval.retrieve_device(bank, expr, qry, k, mode, want_emb=True)
+        same = torch.equal(idx, idx1) and torch.equal(val, val1)
+        e1 = float((ex - ex1).abs().max() / ex1.abs().max())
+        e2 = float((emb - emb1).abs().max() / emb1.abs().max())
+        ok &= same and e1 < 1e-3 and e2 < 1e-3
+        if rank == 0:
+            print(f"retrieval {mode} k={k}: indices/values identical={same}, expr rel err {e1:.2e}, emb {e2:.2e}")
+    for targets in ("eye", "soft"):
+        B, D = 128 * world * 2, 256
+        S = torch.tensor(synth.embeddings(B, D, 21, "clustered", centres=9) * 0.5, device=dev)
+        I = torch.tensor(synth.embeddings(B, D, 22, "clustered", centres=9) * 0.5, device=dev)
+        S1, I1 = S.clone().requires_grad_(True), I.clone().requires_grad_(True)
+        l1 = mloss.contrastive_loss(S1, I1, 1.0, targets)
+        l1.backward()
+        rows = B // world
+        Sl = S[rank * rows:(rank + 1) * rows].clone().requires_grad_(True)
+        Il = I[rank * rows:(rank + 1) * rows].clone().requires_grad_(True)
+        l = contrastive_loss_sharded(Sl, Il, 1.0, targets)
+        l.backward()
+        eS = float((Sl.grad - S1.grad[rank * rows:(rank + 1) * rows]).norm() / S1.grad.norm())
+        eI = float((Il.grad - I1.grad[rank * rows:(rank + 1) * rows]).norm() / I1.grad.norm())
+        el = abs(l.item() - l1.item()) / abs(l1.item())
+        ok &= el < 1e-4 and eS < 1e-3 and eI < 1e-3
+        if rank == 0:
+            print(f"loss {targets}: sharded {l.item():.6f} vs single {l1.item():.6f}, grad err {eS:.2e} {eI:.2e}")
+    t = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_CHECK", "PASS" if t.item() == 1.0 else "FAIL")
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
