@@ -85,7 +85,7 @@ def make_inputs_device(cfg, seed, device, flavour="clustered"):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    def __init__(self, index=0, period=0.1):
+    def __init__(self, index=0, period=0.02):
         self.samples, self.reasons, self.period, self.index = [], set(), period, index
         self._stop = threading.Event()
         self.max_mhz = None
@@ -149,7 +149,7 @@ def cpu_reference_time(cfg, mode, budget_s=20.0, seed=7, threads=None):
     bank = rng.standard_normal((N, D), dtype=np.float32)
     expr = rng.random((N, G), dtype=np.float32)
     done, t_total, chunk = 0, 0.0, 64
-    cap = min(cfg["Q"], 2048)
+    cap = min(cfg["Q"], 16384)
     while True:
         qry = rng.standard_normal((chunk, D), dtype=np.float32)
         t0 = time.perf_counter()
@@ -167,6 +167,83 @@ def cpu_reference_time(cfg, mode, budget_s=20.0, seed=7, threads=None):
                 torch=torch.__version__, numpy=np.__version__), t_total, done
 
 
+# --------------------------------------------------------------------------- second metric
+def _time_cuda(fn, iters=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def loss_sweep(dev, peaks, world, rank, quick):
+    """Contrastive-loss fwd+bwd steps/s (soft targets, D=256) over the BASELINE cfg5 batch sweep;
+    at world > 1 the batch is the GLOBAL batch, sharded by rows with embedding all-gather."""
+    from mclstexp_b200 import loss as mloss
+    out = {}
+    sizes = [256, 1024, 4096] if quick else synth.CONFIGS["cfg5"]["B_sweep"]
+    g = torch.Generator(device=dev)
+    g.manual_seed(99)
+    for B in sizes:
+        if B % (128 * world) != 0:
+            continue
+        x = torch.randn(B, 256, generator=g, device=dev)
+        S = ((x - x.mean(1, keepdim=True)) / x.std(1, keepdim=True)).requires_grad_(True)
+        y = torch.randn(B, 256, generator=g, device=dev)
+        I = ((y - y.mean(1, keepdim=True)) / y.std(1, keepdim=True)).requires_grad_(True)
+        if world > 1:
+            from mclstexp_b200.distributed import contrastive_loss_sharded
+            rows = B // world
+            Sl = S.detach()[rank * rows:(rank + 1) * rows].clone().requires_grad_(True)
+            Il = I.detach()[rank * rows:(rank + 1) * rows].clone().requires_grad_(True)
+
+            def step():
+                l = contrastive_loss_sharded(Sl, Il, 1.0, "soft")
+                l.backward()
+        else:
+            def step():
+                l = mloss.contrastive_loss(S, I, 1.0, "soft")
+                l.backward()
+        ms = _time_cuda(step)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        flops = 14.0 * B * B * 256
+        out[str(B)] = {"steps_per_s": 1e3 / ms, "ms": ms,
+                       "frac_of_bf16_sustained": flops / (ms * 1e-3) / (peaks["tf_sust"] * 1e12 * world)}
+    return out
+
+
+def train_step_cfg2(dev):
+    """BASELINE cfg2: spot self-attention + projection heads + soft-target loss, fwd+bwd, B=1024."""
+    from torch import nn
+    from mclstexp_b200 import model as mm
+    res = {}
+    for G in (171, 1000):
+        net = mm.mclSTExp_Attention("none", 1.0, 1024, G, 256, 8, 64, 2, targets="soft")
+        net.image_encoder = nn.Identity()
+        net = net.to(dev)
+        g = torch.Generator(device=dev)
+        g.manual_seed(7)
+        batch = {"image": torch.randn(1024, 1024, generator=g, device=dev),
+                 "expression": torch.rand(1024, G, generator=g, device=dev),
+                 "position": torch.randint(0, 64, (1024, 2), generator=g, device=dev).float()}
+
+        def step():
+            net.zero_grad(set_to_none=True)
+            net(batch).backward()
+        ms = _time_cuda(step, iters=5, warm=2)
+        res[f"G{G}"] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms}
+    return res
+
+
 # --------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -181,6 +258,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--exact-only", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the loss / train-step metrics")
+    ap.add_argument("--full-loss-sweep", action="store_true", help="cfg5 sweep up to B=32768")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == "reference", "timing rules: W >= 3"
     cfg = dict(synth.CONFIGS[args.workload])
@@ -274,6 +353,7 @@ def main():
         "sim_topk": ("tensor", 2.0 * Q * n_local * D),
         "exact_topk": ("tensor", 2.0 * Q * n_local * D),
         "weighted_average": ("hbm", Q * k * G * 4.0 + Q * k * D * 4.0 + Q * G * 4.0),
+        "weighted_gather": ("hbm", Q * k * G * 4.0 / world + Q * G * 4.0),
         "row_norms": ("hbm", (n_local + Q) * D * 4.0),
         "pack_rows": ("hbm", (n_local + Q) * D * 6.0),
     }
@@ -295,39 +375,62 @@ def main():
     t_roof = max(step_flops / (peaks["tf_sust"] * 1e12), step_bytes / (peaks["hbm"] * 1e9))
     step_roof = {"t_roof_ms": t_roof * 1e3, "frac": t_roof * 1e3 / ms}
 
-    # ---- end to end through the public host-array API
+    # ---- end to end through the public host-array API: host (pinned) buffers in, host arrays
+    # out, every H2D / D2H copy inside the timed region
     e2e = None
-    if not args.no_e2e and world == 1:
-        hb = torch.empty(bank.shape, dtype=torch.float32).pin_memory()
-        hq = torch.empty(qry.shape, dtype=torch.float32).pin_memory()
-        he = torch.empty(expr.shape, dtype=torch.float32).pin_memory()
-        hb.copy_(bank), hq.copy_(qry), he.copy_(expr)
-        del bank, expr
+    if not args.no_e2e:
+        if world == 1:
+            hb, he = bank.cpu().pin_memory(), expr.cpu().pin_memory()
+            del bank, expr
+        else:
+            hb, he = shard.spot_key.cpu().pin_memory(), shard.expression_key.cpu().pin_memory()
+            off, ntot = shard.index_offset, shard.n_total
+            del shard
+        hq = qry.cpu().pin_memory()
         torch.cuda.empty_cache()
-        ho_idx = torch.empty((Q, k), dtype=torch.int64).pin_memory()
-        ho_expr = torch.empty((Q, G), dtype=torch.float32).pin_memory()
 
         def e2e_step():
-            b = hb.to(dev, non_blocking=True)
-            q = hq.to(dev, non_blocking=True)
-            e = he.to(dev, non_blocking=True)
-            idx, val, _, ex = retrieval.retrieve_device(b, e, q, k, args.mode, want_emb=False,
-                                                        out_dtype=torch.float32,
-                                                        exact_only=args.exact_only)
-            ho_idx.copy_(idx, non_blocking=True)
-            ho_expr.copy_(ex, non_blocking=True)
+            if world == 1:
+                idx, emb, ex = retrieval.retrieve(hb, he, hq, top_k=k, mode=args.mode, want_emb=False,
+                                                  out_dtype=torch.float32)
+                return idx, ex
+            sh = mdist.BankShard(hb.to(dev, non_blocking=True), he.to(dev, non_blocking=True), off, ntot)
+            idx, val, _, ex = mdist.retrieve_sharded(sh, hq.to(dev, non_blocking=True), k, args.mode)
+            if rank == 0:
+                return idx.cpu().numpy(), ex.cpu().numpy()
             torch.cuda.synchronize()
+            return None
 
         e2e_step()
         n_e2e = max(1, min(args.steps, 3))
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            e2e_step()
+            r = e2e_step()
+        barrier()
         dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
         e2e = {"value": Q / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
-               "h2d_bytes_per_step": int(hb.numel() * 4 + hq.numel() * 4 + he.numel() * 4),
-               "d2h_bytes_per_step": int(ho_idx.numel() * 8 + ho_expr.numel() * 4)}
+               "h2d_bytes_per_step": int((N * (D + G) + Q * D * world) * 4),
+               "d2h_bytes_per_step": int(Q * k * 8 + Q * G * 4),
+               "api": "mclstexp_b200.retrieval.retrieve(host arrays) -> host arrays" if world == 1 else
+                      "mclstexp_b200.distributed.retrieve_sharded from pinned host shards; rank 0 reads back"}
+        del hb, he, hq
+
+    extra = None
+    if not args.no_extra:
+        if args.no_e2e:                      # (the e2e block already released them otherwise)
+            if world == 1:
+                del bank, expr
+            else:
+                del shard
+        torch.cuda.empty_cache()
+        extra = {"contrastive_loss_soft_fwd_bwd": loss_sweep(dev, peaks, world, rank, not args.full_loss_sweep)}
+        if world == 1:
+            extra["train_step_cfg2_B1024"] = train_step_cfg2(dev)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -336,11 +439,13 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f16 tensor-core candidates, "
-                "f64-accumulated f32 re-rank, f32 average", "data": "synthetic", "config": config,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f16",
+                "dtype_note": "fp16 tensor-core candidate scores; exact fp64-accumulated cosine re-rank "
+                              "(bit-exact top-k); fp32 weighted average",
+                "data": "synthetic", "config": config,
                 "clocks": clk.summary(), "gpu_launches": int(launches), "e2e": e2e,
                 "roofline": roofline, "step_roofline": step_roof, "cpu_baseline": cpu_baseline,
-                "path_counters": counters}
+                "path_counters": counters, "extra": extra}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

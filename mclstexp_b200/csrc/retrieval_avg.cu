@@ -287,6 +287,7 @@ extern "C" int mclst_neighbor_distances(const float* spot_key, int64_t n_bank, i
   MCLST_REQUIRE(top_k >= 1 && top_k <= AVG_KMAX && (p == 1 || p == 2), MCLST_ERR_UNSUPPORTED,
                 "neighbor_distances: bad top_k/p");
   if (n_query == 0) return 0;
+  prof_mark((cudaStream_t)stream, "neighbor_distances");
   neighbour_distance_kernel<<<(unsigned)n_query, AVG_THREADS, 0, (cudaStream_t)stream>>>(
       spot_key, n_bank, ld_key, image_query, ld_query, dim, indices, top_k, index_offset, p,
       out_dist);
@@ -307,12 +308,14 @@ extern "C" int mclst_weighted_gather(const void* expression_key, int64_t n_bank,
   const bool vec4 = !expr_is_f64 && (genes % 4 == 0) && (ld_expr % 4 == 0) &&
                     ((uintptr_t)expression_key % 16 == 0) && ((uintptr_t)out_partial % 16 == 0);
   dim3 grid((unsigned)n_query), block(AVG_THREADS);
+  prof_mark(st, "weighted_gather");
   if (expr_is_f64)
     weighted_gather_kernel<false, true><<<grid, block, 0, st>>>(expression_key, n_bank, ld_expr, genes, indices, weights, top_k, index_offset, out_partial);
   else if (vec4)
     weighted_gather_kernel<true, false><<<grid, block, 0, st>>>(expression_key, n_bank, ld_expr, genes, indices, weights, top_k, index_offset, out_partial);
   else
     weighted_gather_kernel<false, false><<<grid, block, 0, st>>>(expression_key, n_bank, ld_expr, genes, indices, weights, top_k, index_offset, out_partial);
+  prof_mark(st, "end");
   MCLST_LAUNCH_CHECK();
   return 0;
 }

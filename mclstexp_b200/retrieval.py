@@ -182,23 +182,31 @@ def retrieve_device(spot_key: torch.Tensor, expression_key: torch.Tensor, image_
     return idx, val, emb, expr
 
 
+def _to_dev(x: ArrayLike, device, dtypes=(torch.float32,)) -> torch.Tensor:
+    t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+    if t.dtype not in dtypes:
+        t = t.float()
+    return t.to(device, non_blocking=True)
+
+
 def retrieve(spot_key: ArrayLike, expression_key: ArrayLike, image_query: ArrayLike, top_k: int = 50,
-             p: int = 2, mode: Optional[str] = None):
+             p: int = 2, mode: Optional[str] = None, want_emb: bool = True, out_dtype=torch.float64):
     """The whole fold-loop body evel_her2st.py:174-187 in one call, host arrays in and out:
-    (indices [Q,k] int64, matched_spot_embeddings_pred [Q,D] f64,
-    matched_spot_expression_pred [Q,G] f64)."""
+    (indices [Q,k] int64, matched_spot_embeddings_pred [Q,D] | None, matched_spot_expression_pred
+    [Q,G]); float64 results by default, like the reference's ``np.zeros`` arrays.  Inputs may be
+    NumPy arrays or (pinned) CPU tensors; the copies to and from the device happen here."""
     if mode is None:
         mode = {1: "inv_sq_l1", 2: "inv_sq_l2"}[p]
-    sk = _dev_f32(spot_key)
-    iq = _dev_f32(image_query, sk.device)
-    ek = expression_key if isinstance(expression_key, torch.Tensor) else \
-        torch.from_numpy(np.ascontiguousarray(expression_key))
-    if ek.dtype not in (torch.float32, torch.float64):
-        ek = ek.float()
-    ek = ek.to(sk.device, non_blocking=True)
-    idx, val, emb, expr = retrieve_device(sk, ek, iq, top_k, mode, want_emb=True,
-                                          out_dtype=torch.float64)
-    return idx.cpu().numpy(), emb.cpu().numpy(), expr.cpu().numpy()
+    if not torch.cuda.is_available():
+        raise _lib.MclstError("no CUDA device: retrieve has no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    sk = _to_dev(spot_key, dev)
+    iq = _to_dev(image_query, dev)
+    ek = _to_dev(expression_key, dev, (torch.float32, torch.float64))
+    if iq.dim() == 1:
+        iq = iq[None]
+    idx, val, emb, expr = retrieve_device(sk, ek, iq, top_k, mode, want_emb=want_emb, out_dtype=out_dtype)
+    return idx.cpu().numpy(), (emb.cpu().numpy() if emb is not None else None), expr.cpu().numpy()
 
 
 def debug_similarity(spot_embeddings: ArrayLike, query_embeddings: ArrayLike) -> torch.Tensor:
