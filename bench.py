@@ -259,6 +259,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--exact-only", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the loss / train-step metrics")
+    ap.add_argument("--bank-shards", type=int, default=int(os.environ.get("MCLST_BANK_SHARDS", 0)),
+                    help="ranks per query group that split the bank (default: 2 when N >= 2); "
+                         "N = pure bank sharding, 1 = pure query sharding")
     ap.add_argument("--full-loss-sweep", action="store_true", help="cfg5 sweep up to B=32768")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == "reference", "timing rules: W >= 3"
@@ -300,13 +303,20 @@ def main():
     N, Q, D, G, k = cfg["N"], cfg["Q"], cfg["D"], cfg["G"], cfg["k"]
 
     bank, qry, expr = make_inputs_device(cfg, 1234 + 4, dev, args.flavour)
+    Q_job = Q
     if world > 1:
-        shard = mdist.BankShard.from_full(bank, expr, rank, world)
+        bshards = args.bank_shards if args.bank_shards > 0 else min(2, world)
+        grid = mdist.make_retrieval_grid(bshards, world, rank)
+        config["parallelism"] = (f"{grid.query_groups} query groups x {grid.bank_shards} bank shards "
+                                 "(candidate all-gather + merge inside a group)")
+        shard = mdist.BankShard.from_full(bank, expr, grid.b_index, grid.bank_shards)
+        q0, q1 = grid.query_slice(Q)
+        qry = qry[q0:q1].contiguous()
         del bank, expr
         torch.cuda.empty_cache()
 
         def step():
-            return mdist.retrieve_sharded(shard, qry, k, args.mode)
+            return mdist.retrieve_sharded(shard, qry, k, args.mode, group=grid.group)
     else:
         def step():
             return retrieval.retrieve_device(bank, expr, qry, k, args.mode, want_emb=False,
@@ -348,12 +358,13 @@ def main():
     kern = {n: float(np.mean(v)) for n, v in per.items()}
     share = {n: float(np.sum(v)) / args.steps for n, v in per.items()}
     top = max(share, key=share.get) if share else None
-    n_local = N // world
+    n_local = N // (grid.bank_shards if world > 1 else 1)
+    Q = qry.shape[0]                     # per-rank query count for the per-kernel figures
     alg = {   # algorithmic work per launch: FLOPs for the similarity kernels, bytes otherwise
         "sim_topk": ("tensor", 2.0 * Q * n_local * D),
         "exact_topk": ("tensor", 2.0 * Q * n_local * D),
         "weighted_average": ("hbm", Q * k * G * 4.0 + Q * k * D * 4.0 + Q * G * 4.0),
-        "weighted_gather": ("hbm", Q * k * G * 4.0 / world + Q * G * 4.0),
+        "weighted_gather": ("hbm", Q * k * G * 4.0 / (grid.bank_shards if world > 1 else 1) + Q * G * 4.0),
         "row_norms": ("hbm", (n_local + Q) * D * 4.0),
         "pack_rows": ("hbm", (n_local + Q) * D * 6.0),
     }
@@ -369,10 +380,11 @@ def main():
                     "frac": ach / peak, "traffic": None, "peak_source": peaks["source"],
                     "kernel_ms": kern[top], "share_of_step": share[top] / ms,
                     "kernels_ms_per_step": share}
-    # whole-step roofline: max(FLOPs / tensor peak, bytes / HBM peak)
-    step_flops = 2.0 * Q * n_local * D
-    step_bytes = Q * k * G * 4.0 + Q * G * 4.0 + (n_local + Q) * D * 4.0 + Q * k * D * 4.0
-    t_roof = max(step_flops / (peaks["tf_sust"] * 1e12), step_bytes / (peaks["hbm"] * 1e9))
+    # whole-job roofline over all GPUs: max(FLOPs / tensor peak, bytes / HBM peak)
+    Q = Q_job
+    step_flops = 2.0 * Q * N * D
+    step_bytes = Q * k * G * 4.0 + Q * G * 4.0 + (N + Q) * D * 4.0 + Q * k * D * 4.0
+    t_roof = max(step_flops / (peaks["tf_sust"] * 1e12), step_bytes / (peaks["hbm"] * 1e9)) / world
     step_roof = {"t_roof_ms": t_roof * 1e3, "frac": t_roof * 1e3 / ms}
 
     # ---- end to end through the public host-array API: host (pinned) buffers in, host arrays
@@ -395,8 +407,9 @@ def main():
                                                   out_dtype=torch.float32)
                 return idx, ex
             sh = mdist.BankShard(hb.to(dev, non_blocking=True), he.to(dev, non_blocking=True), off, ntot)
-            idx, val, _, ex = mdist.retrieve_sharded(sh, hq.to(dev, non_blocking=True), k, args.mode)
-            if rank == 0:
+            idx, val, _, ex = mdist.retrieve_sharded(sh, hq.to(dev, non_blocking=True), k, args.mode,
+                                                     group=grid.group)
+            if grid.b_index == 0:            # one rank of every query group reads its slice back
                 return idx.cpu().numpy(), ex.cpu().numpy()
             torch.cuda.synchronize()
             return None
@@ -414,10 +427,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": Q / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
-               "h2d_bytes_per_step": int((N * (D + G) + Q * D * world) * 4),
+               "h2d_bytes_per_step": int((N * (D + G) * (grid.query_groups if world > 1 else 1) + Q * D *
+                                          (grid.bank_shards if world > 1 else 1)) * 4),
                "d2h_bytes_per_step": int(Q * k * 8 + Q * G * 4),
                "api": "mclstexp_b200.retrieval.retrieve(host arrays) -> host arrays" if world == 1 else
-                      "mclstexp_b200.distributed.retrieve_sharded from pinned host shards; rank 0 reads back"}
+                      "mclstexp_b200.distributed.retrieve_sharded from pinned host shards; one rank per "
+                      "query group reads its slice back"}
         del hb, he, hq
 
     extra = None

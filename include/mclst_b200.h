@@ -92,6 +92,17 @@ int mclst_find_matches(const float* bank, int64_t n_bank, int64_t ld_bank,
                        void* workspace, size_t workspace_bytes, int flags,
                        mclst_stream_t stream);
 
+/* Same, additionally returning out_distances [n_query, top_k] float32: the L1 (dist_p = 1,
+ * evel_her2st.py:178) or L2 (dist_p = 2, evel_visium.py:197) norm of (bank row - query) on the
+ * UN-normalised vectors for every winner -- the quantity the weighted-average loop needs --
+ * computed while the re-rank has the rows in registers instead of gathering them again. */
+int mclst_find_matches_dist(const float* bank, int64_t n_bank, int64_t ld_bank,
+                            const float* query, int64_t n_query, int64_t ld_query,
+                            int dim, int top_k, int64_t index_offset,
+                            int64_t* out_indices, float* out_values, float* out_distances,
+                            int dist_p, void* workspace, size_t workspace_bytes, int flags,
+                            mclst_stream_t stream);
+
 /* Testing aid: the raw similarities of the tensor-core candidate pass (fp16-rounded
  * normalised operands, fp32 accumulation) written to out [n_query, ld_out]; workspace as for
  * mclst_find_matches with top_k = 1.  Not part of the reference surface. */
@@ -106,13 +117,15 @@ int mclst_debug_similarity(const float* bank, int64_t n_bank, int64_t ld_bank,
  * spot_key rows (out_emb, nullable) and of the matching expression_key rows (out_expr).
  * expression_key is [n_bank, genes] float32 (expr_is_f64 = 0) or float64 (= 1); outputs
  * are float64 (out_is_f64 = 1, the reference's np.zeros dtype) or float32.
- * indices [n_query, top_k] int64 are LOCAL row numbers (indices - index_offset).
- * values (only MCLST_W_SIMILARITY) [n_query, top_k] float32. */
+ * indices [n_query, top_k] int64 are global row numbers (local row = index - index_offset).
+ * values (only MCLST_W_SIMILARITY) [n_query, top_k] float32.  distances (nullable)
+ * [n_query, top_k] float32: neighbour distances already known (mclst_find_matches_dist); when
+ * null they are computed here from the gathered rows. */
 int mclst_weighted_average(const float* spot_key, int64_t n_bank, int64_t ld_key,
                            const void* expression_key, int64_t ld_expr, int genes, int expr_is_f64,
                            const float* image_query, int64_t n_query, int64_t ld_query, int dim,
-                           const int64_t* indices, const float* values, int top_k,
-                           int64_t index_offset, int weight_mode,
+                           const int64_t* indices, const float* values, const float* distances,
+                           int top_k, int64_t index_offset, int weight_mode,
                            void* out_emb, void* out_expr, int out_is_f64,
                            mclst_stream_t stream);
 

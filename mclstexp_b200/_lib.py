@@ -75,7 +75,9 @@ def load() -> C.CDLL:
     lib.mclst_matmul_workspace_bytes.argtypes = [i64, i64, i64, i32, C.POINTER(sz)]
     lib.mclst_matmul.argtypes = [p, i64, i32, i64, p, i64, i32, i64, p, i64, i64, i64, i64, i64, i32,
                                  C.c_float, p, i32, p, i32, p, sz, p]
-    lib.mclst_weighted_average.argtypes = [p, i64, i64, p, i64, i32, i32, p, i64, i64, i32, p, p,
+    lib.mclst_find_matches_dist.argtypes = [p, i64, i64, p, i64, i64, i32, i32, i64, p, p, p, i32, p, sz,
+                                            i32, p]
+    lib.mclst_weighted_average.argtypes = [p, i64, i64, p, i64, i32, i32, p, i64, i64, i32, p, p, p,
                                            i32, i64, i32, p, p, i32, p]
     lib.mclst_neighbor_distances.argtypes = [p, i64, i64, p, i64, i64, i32, p, i32, i64, i32, p, p]
     lib.mclst_weighted_gather.argtypes = [p, i64, i64, i32, i32, p, p, i64, i32, i64, p, p]

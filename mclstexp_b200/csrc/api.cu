@@ -161,11 +161,30 @@ extern "C" int mclst_find_matches_workspace_bytes(int64_t n_bank, int64_t n_quer
   return 0;
 }
 
+extern "C" int mclst_find_matches_dist(const float* bank, int64_t n_bank, int64_t ld_bank,
+                                       const float* query, int64_t n_query, int64_t ld_query,
+                                       int dim, int top_k, int64_t index_offset,
+                                       int64_t* out_indices, float* out_values,
+                                       float* out_distances, int dist_p, void* workspace,
+                                       size_t workspace_bytes, int flags, mclst_stream_t stream);
+
 extern "C" int mclst_find_matches(const float* bank, int64_t n_bank, int64_t ld_bank,
                                   const float* query, int64_t n_query, int64_t ld_query, int dim,
                                   int top_k, int64_t index_offset, int64_t* out_indices,
                                   float* out_values, void* workspace, size_t workspace_bytes,
                                   int flags, mclst_stream_t stream) {
+  return mclst_find_matches_dist(bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k,
+                                 index_offset, out_indices, out_values, nullptr, 2, workspace,
+                                 workspace_bytes, flags, stream);
+}
+
+extern "C" int mclst_find_matches_dist(const float* bank, int64_t n_bank, int64_t ld_bank,
+                                       const float* query, int64_t n_query, int64_t ld_query,
+                                       int dim, int top_k, int64_t index_offset,
+                                       int64_t* out_indices, float* out_values,
+                                       float* out_distances, int dist_p, void* workspace,
+                                       size_t workspace_bytes, int flags, mclst_stream_t stream) {
+  MCLST_REQUIRE(dist_p == 1 || dist_p == 2, MCLST_ERR_INVALID, "find_matches: dist_p must be 1 or 2");
   if (n_query == 0 && n_bank >= 0) return 0;
   MCLST_REQUIRE(bank && query && out_indices && workspace, MCLST_ERR_INVALID,
                 "find_matches: null pointer");
@@ -190,6 +209,9 @@ extern "C" int mclst_find_matches(const float* bank, int64_t n_bank, int64_t ld_
     rc = launch_exact_topk(bank, n_bank, ld_bank, w.bank_nrm, query, ld_query, w.q_nrm, dim,
                            nullptr, nullptr, (int)n_query, n_query, top_k, index_offset, w.scratch,
                            out_indices, out_values, st);
+    if (!rc && out_distances)
+      rc = launch_neighbor_distances(bank, n_bank, ld_bank, query, n_query, ld_query, dim, out_indices,
+                                     top_k, index_offset, dist_p, out_distances, nullptr, nullptr, st);
     prof_mark(st, "end");
     return rc;
   }
@@ -209,11 +231,15 @@ extern "C" int mclst_find_matches(const float* bank, int64_t n_bank, int64_t ld_
   }
   prof_mark(st, "rerank");
   if ((rc = launch_rerank(t, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k,
-                          index_offset, out_indices, out_values, w.counters, st))) return rc;
+                          index_offset, out_indices, out_values, out_distances, dist_p, w.counters,
+                          st))) return rc;
   prof_mark(st, "exact_fallback");
   rc = launch_exact_topk(bank, n_bank, ld_bank, w.bank_nrm, query, ld_query, w.q_nrm, dim,
                          t.fb_list, w.counters, 0, n_query, top_k, index_offset, w.scratch,
                          out_indices, out_values, st);
+  if (!rc && out_distances)      // rows the exact path recomputed: their distances too
+    rc = launch_neighbor_distances(bank, n_bank, ld_bank, query, n_query, ld_query, dim, out_indices,
+                                   top_k, index_offset, dist_p, out_distances, t.fb_list, w.counters, st);
   prof_mark(st, "end");
   return rc;
 }

@@ -38,7 +38,12 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
                     int64_t dump_ld, cudaStream_t st);
 int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64_t ldb,
                   const float* query, int64_t n_query, int64_t ldq, int dim, int top_k,
-                  int64_t index_offset, int64_t* out_idx, float* out_val, int* counters,
-                  cudaStream_t st);
+                  int64_t index_offset, int64_t* out_idx, float* out_val, float* out_dist, int dist_p,
+                  int* counters, cudaStream_t st);
+// distances of the winners of the queries in qlist (exact-fallback rows) or of all queries
+int launch_neighbor_distances(const float* spot_key, int64_t n_bank, int64_t ld_key, const float* query,
+                              int64_t n_query, int64_t ld_query, int dim, const int64_t* indices, int k,
+                              int64_t index_offset, int p, float* out_dist, const int* qlist,
+                              const int* qcount_ptr, cudaStream_t st);
 
 }  // namespace mclst

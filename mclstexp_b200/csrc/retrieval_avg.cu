@@ -52,6 +52,7 @@ weighted_average_kernel(const float* __restrict__ spot_key, int64_t n_bank, int6
                         const void* __restrict__ expr_, int64_t ld_expr, int genes,
                         const float* __restrict__ query, int64_t ld_query, int dim,
                         const int64_t* __restrict__ indices, const float* __restrict__ values,
+                        const float* __restrict__ distances,
                         int k, int64_t index_offset, int mode,
                         void* __restrict__ out_emb, void* __restrict__ out_expr, int out_is_f64) {
   __shared__ float w_sm[AVG_KMAX];
@@ -64,8 +65,15 @@ weighted_average_kernel(const float* __restrict__ spot_key, int64_t n_bank, int6
   const float* qrow = query + q * ld_query;
   // ---- phase A: un-normalised weights ------------------------------------------------
   if (mode == MCLST_W_INV_SQ_L1 || mode == MCLST_W_INV_SQ_L2 || mode == MCLST_W_BLEEP_EXP) {
-    neighbour_distances(spot_key, ld_key, qrow, dim, idx, k, index_offset, n_bank,
-                        mode == MCLST_W_INV_SQ_L1 ? 1 : 2, w_sm);
+    if (distances) {     // L1 norm (inv_sq_l1) or L2 norm, e.g. from mclst_find_matches_dist
+      for (int j = tid; j < k; j += AVG_THREADS) {
+        const float d = distances[q * k + j];
+        w_sm[j] = mode == MCLST_W_INV_SQ_L1 ? d : d * d;      // phase A keeps SQUARED L2 norms
+      }
+    } else {
+      neighbour_distances(spot_key, ld_key, qrow, dim, idx, k, index_offset, n_bank,
+                          mode == MCLST_W_INV_SQ_L1 ? 1 : 2, w_sm);
+    }
   } else if (mode == MCLST_W_SIMILARITY) {
     for (int j = tid; j < k; j += AVG_THREADS) w_sm[j] = values[q * k + j];
   } else {
@@ -176,9 +184,14 @@ __global__ void __launch_bounds__(AVG_THREADS)
 neighbour_distance_kernel(const float* __restrict__ spot_key, int64_t n_bank, int64_t ld_key,
                           const float* __restrict__ query, int64_t ld_query, int dim,
                           const int64_t* __restrict__ indices, int k, int64_t index_offset, int p,
-                          float* __restrict__ out_dist) {
+                          float* __restrict__ out_dist, const int* __restrict__ qlist,
+                          const int* __restrict__ qcount_ptr) {
   __shared__ float d_sm[AVG_KMAX];
-  const int64_t q = blockIdx.x;
+  int64_t q = blockIdx.x;
+  if (qlist) {                         // only the listed queries (exact-fallback rows)
+    if ((int)blockIdx.x >= *qcount_ptr) return;
+    q = qlist[blockIdx.x];
+  }
   neighbour_distances(spot_key, ld_key, query + q * ld_query, dim, indices + q * k, k,
                       index_offset, n_bank, p, d_sm);
   __syncthreads();
@@ -246,9 +259,9 @@ extern "C" int mclst_weighted_average(const float* spot_key, int64_t n_bank, int
                                       const void* expression_key, int64_t ld_expr, int genes,
                                       int expr_is_f64, const float* image_query, int64_t n_query,
                                       int64_t ld_query, int dim, const int64_t* indices,
-                                      const float* values, int top_k, int64_t index_offset,
-                                      int weight_mode, void* out_emb, void* out_expr,
-                                      int out_is_f64, mclst_stream_t stream) {
+                                      const float* values, const float* distances, int top_k,
+                                      int64_t index_offset, int weight_mode, void* out_emb,
+                                      void* out_expr, int out_is_f64, mclst_stream_t stream) {
   MCLST_REQUIRE(spot_key && expression_key && image_query && indices && out_expr, MCLST_ERR_INVALID,
                 "weighted_average: null pointer");
   MCLST_REQUIRE(top_k >= 1 && top_k <= AVG_KMAX, MCLST_ERR_UNSUPPORTED,
@@ -266,7 +279,7 @@ extern "C" int mclst_weighted_average(const float* spot_key, int64_t n_bank, int
 #define LAUNCH(V, F)                                                                         \
   weighted_average_kernel<V, F><<<grid, block, 0, st>>>(                                     \
       spot_key, n_bank, ld_key, expression_key, ld_expr, genes, image_query, ld_query, dim,  \
-      indices, values, top_k, index_offset, weight_mode, out_emb, out_expr, out_is_f64)
+      indices, values, distances, top_k, index_offset, weight_mode, out_emb, out_expr, out_is_f64)
   prof_mark(st, "weighted_average");
   if (expr_is_f64) LAUNCH(false, true);
   else if (vec4) LAUNCH(true, false);
@@ -290,7 +303,20 @@ extern "C" int mclst_neighbor_distances(const float* spot_key, int64_t n_bank, i
   prof_mark((cudaStream_t)stream, "neighbor_distances");
   neighbour_distance_kernel<<<(unsigned)n_query, AVG_THREADS, 0, (cudaStream_t)stream>>>(
       spot_key, n_bank, ld_key, image_query, ld_query, dim, indices, top_k, index_offset, p,
-      out_dist);
+      out_dist, nullptr, nullptr);
+  MCLST_LAUNCH_CHECK();
+  return 0;
+}
+
+int mclst::launch_neighbor_distances(const float* spot_key, int64_t n_bank, int64_t ld_key,
+                                     const float* query, int64_t n_query, int64_t ld_query, int dim,
+                                     const int64_t* indices, int k, int64_t index_offset, int p,
+                                     float* out_dist, const int* qlist, const int* qcount_ptr,
+                                     cudaStream_t st) {
+  if (n_query == 0) return 0;
+  neighbour_distance_kernel<<<(unsigned)n_query, AVG_THREADS, 0, st>>>(
+      spot_key, n_bank, ld_key, query, ld_query, dim, indices, k, index_offset, p, out_dist, qlist,
+      qcount_ptr);
   MCLST_LAUNCH_CHECK();
   return 0;
 }

@@ -437,6 +437,7 @@ struct RerankParams {
   int dim;
   int64_t index_offset;
   int64_t* out_idx; float* out_val;
+  float* out_dist; int dist_p;     // optional: L1 (p=1) / L2 (p=2) distance of each winner to the raw query
   int* fb_list; int* counters;     // counters[0] = fallback count, [1] = resolved here
 };
 
@@ -444,21 +445,27 @@ struct RerankParams {
 // fp64 dot of the raw fp32 rows / (fp64 norm product), rounded once to fp32.
 template <bool VEC>
 __device__ __forceinline__ double row_dot(const float* __restrict__ sp, const double (&qh)[8],
-                                          int dim, int lane) {
+                                          int dim, int lane, float* l1) {
   double acc = 0.0;
+  float v[8];
   if (VEC) {                       // dim == 256, 16-byte aligned rows: d = 4*lane + 128*h + i
     const float4 a = __ldg(reinterpret_cast<const float4*>(sp) + lane);
     const float4 b = __ldg(reinterpret_cast<const float4*>(sp) + 32 + lane);
-    acc = fma((double)a.x, qh[0], acc); acc = fma((double)a.y, qh[1], acc);
-    acc = fma((double)a.z, qh[2], acc); acc = fma((double)a.w, qh[3], acc);
-    acc = fma((double)b.x, qh[4], acc); acc = fma((double)b.y, qh[5], acc);
-    acc = fma((double)b.z, qh[6], acc); acc = fma((double)b.w, qh[7], acc);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {                         // d = lane + 32*t
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       const int d = lane + 32 * t;
-      if (d < dim) acc = fma((double)__ldg(sp + d), qh[t], acc);
+      v[t] = d < dim ? __ldg(sp + d) : 0.f;
     }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc = fma((double)v[t], qh[t], acc);
+  if (l1) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) s += fabsf(v[t] - (float)qh[t]);
+    *l1 = s;
   }
   return acc;
 }
@@ -472,6 +479,15 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
   if (warp >= warps_per_block || q >= p.Q) return;
   unsigned long long* ent = reinterpret_cast<unsigned long long*>(rr_smem) +
                             (size_t)warp * per_warp_entries;   // (key << 32) | idx, later sort keys
+  // distance payload of the survivors + the permutation the sort applies to them
+  float* pay = reinterpret_cast<float*>(reinterpret_cast<unsigned long long*>(rr_smem) +
+                                        (size_t)warps_per_block * per_warp_entries) + (size_t)warp * RR_MAX;
+  unsigned short* slot = reinterpret_cast<unsigned short*>(
+      reinterpret_cast<float*>(reinterpret_cast<unsigned long long*>(rr_smem) +
+                               (size_t)warps_per_block * per_warp_entries) + (size_t)warps_per_block * RR_MAX) +
+      (size_t)warp * RR_MAX;
+  const bool want_dist = p.out_dist != nullptr;
+  const bool want_l1 = want_dist && p.dist_p == 1;
   // ---- gather the streams' candidates
   bool bad = (p.bank_stats[1] | p.q_stats[1]) != 0;    // non-finite input: exact path decides
   int M = 0;
@@ -537,24 +553,42 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
     qh[t] = d < p.dim ? (double)__ldg(qp + d) : 0.0;
   }
   // 8 independent row gathers in flight per warp: the phase is DRAM-latency bound otherwise
+  const double ss_q = nq * nq;
   for (int i = 0; i < n_s; i += 8) {
     uint32_t r[8];
     double acc[8];
+    float l1[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) r[u] = (uint32_t)ent[min(i + u, n_s - 1)];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc[u] = row_dot<VEC>(p.bank + (int64_t)r[u] * p.ldb, qh, p.dim, lane);
+    for (int u = 0; u < 8; ++u)
+      acc[u] = row_dot<VEC>(p.bank + (int64_t)r[u] * p.ldb, qh, p.dim, lane, want_l1 ? &l1[u] : nullptr);
 #pragma unroll
     for (int u = 0; u < 8; ++u) acc[u] = warp_sum(acc[u]);
+    if (want_l1) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) l1[u] = warp_sum(l1[u]);
+    }
     __syncwarp();
     double a = acc[0];
     uint32_t rr = r[0];
+    float l1v = want_l1 ? l1[0] : 0.f;
 #pragma unroll
     for (int u = 1; u < 8; ++u)
-      if (lane == u) { a = acc[u]; rr = r[u]; }
+      if (lane == u) { a = acc[u]; rr = r[u]; if (want_l1) l1v = l1[u]; }
     if (lane < 8 && i + lane < n_s) {
-      const float v = (float)(a / (nq * p.bank_nrm[rr]));
+      const double ns = p.bank_nrm[rr];
+      const float v = (float)(a / (nq * ns));
       ent[i + lane] = ((unsigned long long)f2ord(v) << 32) | (unsigned long long)(0xffffffffu - rr);
+      if (want_dist) {
+        float d = l1v;
+        if (!want_l1) {               // ||s - q||^2 = |s|^2 + |q|^2 - 2 s.q, all in fp64
+          const double ss = ns * ns + ss_q;
+          const double d2 = ss - 2.0 * a;
+          d = d2 <= 1e-12 * ss ? 0.f : (float)sqrt(d2);
+        }
+        pay[i + lane] = d;
+      }
     }
     __syncwarp();
   }
@@ -563,6 +597,8 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
   int P = 1;
   while (P < n_s) P <<= 1;
   for (int j = n_s + lane; j < P; j += 32) ent[j] = 0ull;
+  if (want_dist)
+    for (int j = lane; j < P; j += 32) slot[j] = (unsigned short)j;
   __syncwarp();
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -571,7 +607,10 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
         const int hi = lo + stride;
         const bool desc = ((lo & size) == 0);
         const unsigned long long a = ent[lo], b = ent[hi];
-        if ((a < b) == desc) { ent[lo] = b; ent[hi] = a; }
+        if ((a < b) == desc) {
+          ent[lo] = b; ent[hi] = a;
+          if (want_dist) { const unsigned short t2 = slot[lo]; slot[lo] = slot[hi]; slot[hi] = t2; }
+        }
       }
       __syncwarp();
     }
@@ -580,6 +619,7 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
     const unsigned long long e = ent[j];
     p.out_idx[q * p.k + j] = (int64_t)(0xffffffffu - (uint32_t)e) + p.index_offset;
     if (p.out_val) p.out_val[q * p.k + j] = ord2f((uint32_t)(e >> 32));
+    if (want_dist) p.out_dist[q * p.k + j] = pay[slot[j]];
   }
   if (lane == 0) atomicAdd(&p.counters[1], 1);
 }
@@ -723,15 +763,16 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
 
 int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64_t ldb,
                   const float* query, int64_t n_query, int64_t ldq, int dim, int top_k,
-                  int64_t index_offset, int64_t* out_idx, float* out_val, int* counters,
-                  cudaStream_t st) {
+                  int64_t index_offset, int64_t* out_idx, float* out_val, float* out_dist, int dist_p,
+                  int* counters, cudaStream_t st) {
   RerankParams p;
   p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.SS = w.SS; p.cap = w.cap; p.k = top_k;
   p.Q = n_query; p.N = n_bank; p.bank = bank; p.ldb = ldb; p.bank_nrm = w.b_nrm;
   p.query = query; p.ldq = ldq; p.q_nrm = w.q_nrm; p.q_resid = w.q_resid;
   p.bank_stats = w.stats; p.q_stats = w.stats + 8; p.gthr = w.gthr; p.dim = dim;
   p.index_offset = index_offset;
-  p.out_idx = out_idx; p.out_val = out_val; p.fb_list = w.fb_list; p.counters = counters;
+  p.out_idx = out_idx; p.out_val = out_val; p.out_dist = out_dist; p.dist_p = dist_p;
+  p.fb_list = w.fb_list; p.counters = counters;
   // shared memory: per warp a power-of-two number of 8-byte entries (bitonic sort), at most 4096;
   // a query whose streams hold more than that goes to the exact path
   int per_warp = 1;
@@ -739,7 +780,7 @@ int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64
   if (per_warp < 2 * top_k) per_warp = 2048;
   int wpb = 4;
   while (wpb > 1 && (size_t)wpb * per_warp * 8 > 64 * 1024) wpb >>= 1;
-  const size_t smem = (size_t)wpb * per_warp * 8;
+  const size_t smem = (size_t)wpb * per_warp * 8 + (size_t)wpb * RR_MAX * 6;
   const bool vec = (dim == 256) && (ldb % 4 == 0) && (ldq % 4 == 0) && ((uintptr_t)bank % 16 == 0) &&
                    ((uintptr_t)query % 16 == 0);
   static size_t attr[2] = {0, 0};

@@ -31,7 +31,8 @@ import torch.distributed as dist
 from . import _lib
 from ._lib import WEIGHT_MODES, check, load, ptr, stream_ptr
 
-__all__ = ["shard_bounds", "BankShard", "CudaBackend", "retrieve_sharded", "contrastive_loss_sharded"]
+__all__ = ["shard_bounds", "BankShard", "CudaBackend", "retrieve_sharded", "contrastive_loss_sharded",
+           "RetrievalGrid", "make_retrieval_grid"]
 
 
 def shard_bounds(n: int, world: int) -> List[Tuple[int, int]]:
@@ -65,18 +66,16 @@ class CudaBackend:
         val = torch.full((Q, k), float("-inf"), dtype=torch.float32, device=dev)
         idx = torch.full((Q, k), 2 ** 31 - 1, dtype=torch.int64, device=dev)
         dst = torch.full((Q, k), float("inf"), dtype=torch.float32, device=dev) if need_dist else None
+        if kk == k:
+            r = find_matches_device(shard.spot_key, query, k, index_offset=shard.index_offset,
+                                    dist_p=p if need_dist else None)
+            return (r[0], r[1], r[2]) if need_dist else (r[0], r[1], None)
         if kk > 0:
-            v, i = find_matches_device(shard.spot_key, query, kk, index_offset=shard.index_offset)
-            val[:, :kk], idx[:, :kk] = v, i
+            r = find_matches_device(shard.spot_key, query, kk, index_offset=shard.index_offset,
+                                    dist_p=p if need_dist else None)
+            val[:, :kk], idx[:, :kk] = r[0], r[1]
             if need_dist:
-                d = torch.empty((Q, kk), dtype=torch.float32, device=dev)
-                ic = i.contiguous()
-                with torch.cuda.device(dev):
-                    check(load().mclst_neighbor_distances(
-                        ptr(shard.spot_key), n_loc, shard.spot_key.stride(0), ptr(query), Q,
-                        query.stride(0), query.shape[1], ptr(ic), kk, shard.index_offset, p, ptr(d),
-                        stream_ptr()), "neighbor_distances")
-                dst[:, :kk] = d
+                dst[:, :kk] = r[2]
         return val, idx, dst
 
     def merge(self, vals, idx, dst, k: int):
@@ -124,7 +123,7 @@ def retrieve_sharded(shard: BankShard, query: torch.Tensor, top_k: int = 50, mod
     need_dist = mode in ("inv_sq_l1", "inv_sq_l2", "bleep_exp")
     p = 1 if mode == "inv_sq_l1" else 2
     val, idx, dst = backend.local_topk(shard, query, top_k, p, need_dist)
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    world = dist.get_world_size(group) if (dist.is_initialized() and shard.n_total != shard.spot_key.shape[0]) else 1
     if world > 1:
         vals = _all_gather_stack(val, group)
         idxs = _all_gather_stack(idx, group)
@@ -138,6 +137,41 @@ def retrieve_sharded(shard: BankShard, query: torch.Tensor, top_k: int = 50, mod
         if emb is not None:
             dist.all_reduce(emb, group=group)
     return idx, val, emb, expr
+
+
+@dataclass
+class RetrievalGrid:
+    """2-D decomposition of a retrieval job over world = query_groups x bank_shards ranks.
+
+    Ranks [g*bank_shards, (g+1)*bank_shards) form query group g: they share one slice of the
+    queries and hold one bank shard each (candidate all-gather + merge inside the group).
+    Sharding the BANK multiplies the streaming top-k / re-rank work (every shard produces its
+    own k + band candidates for every query); sharding the QUERIES does not and needs no
+    exchange, but replicates the bank.  bank_shards is therefore a capacity knob: 1 when the
+    bank fits on a GPU, larger when it does not."""
+    query_groups: int
+    bank_shards: int
+    q_index: int
+    b_index: int
+    group: object          # process group of this rank's query group (None when bank_shards == 1)
+
+    def query_slice(self, n_query: int) -> Tuple[int, int]:
+        return shard_bounds(n_query, self.query_groups)[self.q_index]
+
+
+def make_retrieval_grid(bank_shards: int, world: Optional[int] = None, rank: Optional[int] = None) -> RetrievalGrid:
+    world = dist.get_world_size() if world is None else world
+    rank = dist.get_rank() if rank is None else rank
+    if world % bank_shards != 0:
+        raise ValueError(f"bank_shards={bank_shards} does not divide world={world}")
+    qg = world // bank_shards
+    mine = None
+    if bank_shards > 1:
+        for g in range(qg):                     # every rank must take part in every new_group call
+            h = dist.new_group(list(range(g * bank_shards, (g + 1) * bank_shards)))
+            if g == rank // bank_shards:
+                mine = h
+    return RetrievalGrid(qg, bank_shards, rank // bank_shards, rank % bank_shards, mine)
 
 
 # ----------------------------------------------------------------------------- loss

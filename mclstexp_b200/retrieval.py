@@ -50,9 +50,10 @@ def _dev_f32(x: ArrayLike, device=None) -> torch.Tensor:
 
 def find_matches_device(spot_embeddings: torch.Tensor, query_embeddings: torch.Tensor,
                         top_k: int = 1, index_offset: int = 0, exact_only: bool = False,
-                        need_values: bool = True) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
+                        need_values: bool = True, dist_p: Optional[int] = None):
     """Device-resident form: float32 CUDA [N,D], [Q,D] -> (values f32 [Q,k] | None,
-    indices int64 [Q,k]), rows sorted by (similarity desc, index asc)."""
+    indices int64 [Q,k]), rows sorted by (similarity desc, index asc).  With ``dist_p`` (1 or 2)
+    a third tensor is returned: the L1 / L2 distance of every winner to the raw query."""
     global _last_ws
     require_cuda(spot_embeddings, query_embeddings)
     lib = load()
@@ -69,12 +70,16 @@ def find_matches_device(spot_embeddings: torch.Tensor, query_embeddings: torch.T
     ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=bank.device)
     idx = torch.empty((Q, top_k), dtype=torch.int64, device=bank.device)
     val = torch.empty((Q, top_k), dtype=torch.float32, device=bank.device) if need_values else None
+    dst = torch.empty((Q, top_k), dtype=torch.float32, device=bank.device) if dist_p else None
+    if Q == 0:
+        return (val, idx, dst) if dist_p else (val, idx)
     with torch.cuda.device(bank.device):
-        check(lib.mclst_find_matches(ptr(bank), N, bank.stride(0), ptr(qry), Q, qry.stride(0), D,
-                                     top_k, index_offset, ptr(idx), ptr(val), ptr(ws),
-                                     ws.numel(), flags, stream_ptr()), "find_matches")
+        check(lib.mclst_find_matches_dist(ptr(bank), N, bank.stride(0), ptr(qry), Q, qry.stride(0), D,
+                                          top_k, index_offset, ptr(idx), ptr(val), ptr(dst),
+                                          dist_p or 2, ptr(ws), ws.numel(), flags, stream_ptr()),
+              "find_matches")
     _last_ws = ws
-    return val, idx
+    return (val, idx, dst) if dist_p else (val, idx)
 
 
 def last_counters() -> dict:
@@ -115,7 +120,8 @@ def find_matches_cscc(spot_embeddings, query_embeddings, top_k=1):
 def weighted_topk_average_device(spot_key: torch.Tensor, expression_key: torch.Tensor,
                                  image_query: torch.Tensor, indices: torch.Tensor,
                                  mode: str = "inv_sq_l2", values: Optional[torch.Tensor] = None,
-                                 want_emb: bool = True, out_dtype=torch.float64
+                                 want_emb: bool = True, out_dtype=torch.float64,
+                                 distances: Optional[torch.Tensor] = None
                                  ) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
     require_cuda(spot_key, expression_key, image_query, indices)
     lib = load()
@@ -137,7 +143,7 @@ def weighted_topk_average_device(spot_key: torch.Tensor, expression_key: torch.T
         check(lib.mclst_weighted_average(
             ptr(spot_key), N, spot_key.stride(0), ptr(expression_key), expression_key.stride(0), G,
             int(expression_key.dtype == torch.float64), ptr(image_query), Q, image_query.stride(0),
-            D, ptr(indices), ptr(values), k, 0, WEIGHT_MODES[mode], ptr(emb), ptr(expr),
+            D, ptr(indices), ptr(values), ptr(distances), k, 0, WEIGHT_MODES[mode], ptr(emb), ptr(expr),
             int(out_dtype == torch.float64), stream_ptr()), "weighted_average")
     return emb, expr
 
@@ -175,10 +181,16 @@ def retrieve_device(spot_key: torch.Tensor, expression_key: torch.Tensor, image_
                     out_dtype=torch.float32, exact_only: bool = False):
     """find_matches + weighted average with everything resident on the device.
     Returns (indices int64 [Q,k], values f32 [Q,k], emb_pred | None, expr_pred [Q,G])."""
-    val, idx = find_matches_device(spot_key, image_query, top_k, exact_only=exact_only)
+    need_dist = mode in ("inv_sq_l1", "inv_sq_l2", "bleep_exp")
+    dst = None
+    if need_dist:
+        val, idx, dst = find_matches_device(spot_key, image_query, top_k, exact_only=exact_only,
+                                            dist_p=1 if mode == "inv_sq_l1" else 2)
+    else:
+        val, idx = find_matches_device(spot_key, image_query, top_k, exact_only=exact_only)
     emb, expr = weighted_topk_average_device(spot_key, expression_key, image_query, idx, mode,
                                              val if mode == "similarity" else None, want_emb,
-                                             out_dtype)
+                                             out_dtype, distances=dst)
     return idx, val, emb, expr
 
 

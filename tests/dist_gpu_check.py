@@ -11,7 +11,8 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from mclstexp_b200 import retrieval, synth, loss as mloss                      # noqa: E402
-from mclstexp_b200.distributed import BankShard, contrastive_loss_sharded, retrieve_sharded   # noqa: E402
+from mclstexp_b200.distributed import (BankShard, contrastive_loss_sharded, make_retrieval_grid,   # noqa: E402
+                                       retrieve_sharded)
 
 
 def main():
@@ -34,6 +35,24 @@ def main():
         ok &= same and e1 < 1e-3 and e2 < 1e-3
         if rank == 0:
             print(f"retrieval {mode} k={k}: indices/values identical={same}, expr rel err {e1:.2e}, emb {e2:.2e}")
+    # 2-D grid: query groups x bank shards
+    for bshards in sorted({1, 2, world}):
+        if world % bshards:
+            continue
+        grid = make_retrieval_grid(bshards, world, rank)
+        N, Q, D, G, k = 30000, 1024, 256, 500, 50
+        bank = torch.tensor(synth.embeddings(N, D, 31, "clustered"), device=dev)
+        expr = torch.tensor(synth.expression(N, G, 32), device=dev)
+        qry = torch.tensor(synth.embeddings(Q, D, 33, "clustered"), device=dev)
+        shard = BankShard.from_full(bank, expr, grid.b_index, grid.bank_shards)
+        q0, q1 = grid.query_slice(Q)
+        idx, val, _, ex = retrieve_sharded(shard, qry[q0:q1].contiguous(), k, "inv_sq_l2", group=grid.group)
+        idx1, val1, _, ex1 = retrieval.retrieve_device(bank, expr, qry, k, "inv_sq_l2")
+        same = torch.equal(idx, idx1[q0:q1]) and torch.equal(val, val1[q0:q1])
+        e1 = float((ex - ex1[q0:q1]).abs().max() / ex1.abs().max())
+        ok &= same and e1 < 1e-3
+        if rank == 0:
+            print(f"grid {grid.query_groups}x{grid.bank_shards}: identical={same}, expr rel err {e1:.2e}")
     for targets in ("eye", "soft"):
         B, D = 128 * world * 2, 256
         S = torch.tensor(synth.embeddings(B, D, 21, "clustered", centres=9) * 0.5, device=dev)
