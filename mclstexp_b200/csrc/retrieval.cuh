@@ -18,7 +18,7 @@ int launch_exact_topk(const float* bank, int64_t N, int64_t ldb, const double* b
 
 // ---- tensor-core candidate path (sim_topk.cu)
 struct TcWorkspace {
-  int nkb, S, SS, cap, cluster, epw;   // SS = S * (epw / 4) candidate streams per query
+  int nkb, S, SS, cap, cluster, epw, ring;   // SS = S * (epw / 4) candidate streams per query
   int64_t q_pad, n_pad;
   uint32_t* stats;          // [0..7] bank: max residual bits, non-finite flag; [8..15] queries
   uint8_t *qpack, *bpack;
@@ -28,6 +28,8 @@ struct TcWorkspace {
   uint2* cand;
   int* cand_cnt;
   int* fb_list;
+  float* seed;      // chunk maxima of the seed pass [q_pad][n_seed * 8]
+  int n_seed;
 };
 int tc_cap_for_k(int k);
 int sim_topk_ablate();   // timing experiments only: results are garbage when non-zero

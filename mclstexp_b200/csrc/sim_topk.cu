@@ -39,63 +39,80 @@ using namespace ptx;
 constexpr float E_ACC = 2.0e-6f;
 
 // ============================================================================ pack_rows
-// One warp per row, dim <= 256: lane l owns elements 8l..8l+7 (one 16-byte fp16 chunk).
+// One warp per row (grid-stride), dim <= 256: lane l owns elements 8l..8l+7 (one 16-byte fp16
+// chunk).  Per-row statistics are reduced per block before touching the global maximum: one
+// atomic per row on a single address made the first version L2-atomic bound (1.3 ms for 1.06 M
+// rows, 14 % of DRAM bandwidth).
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t rows_pad, int64_t ld, int dim,
                  int nkb, uint8_t* __restrict__ packed, double* __restrict__ nrm,
                  float* __restrict__ resid, uint32_t* __restrict__ stats) {
-  const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= rows_pad) return;
+  __shared__ uint32_t s_max[8];
+  __shared__ uint32_t s_bad[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunks = nkb * 8;               // 16-byte chunks (8 halves) per row; <= 32
-  float v[8];
+  float run_max = 0.f;
+  uint32_t run_bad = 0u;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < rows_pad; r += (int64_t)gridDim.x * 8) {
+    float v[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = 0.f;
-  if (r < rows && lane < nchunks) {
-    const float* p = x + r * ld + lane * 8;
-    if (VEC) {                               // dim % 8 == 0, 16-byte aligned rows
-      if (lane * 8 < dim) {
-        const float4 a = ldg_stream(reinterpret_cast<const float4*>(p));
-        const float4 b = ldg_stream(reinterpret_cast<const float4*>(p) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (r < rows && lane < nchunks) {
+      const float* p = x + r * ld + lane * 8;
+      if (VEC) {                               // dim % 8 == 0, 16-byte aligned rows
+        if (lane * 8 < dim) {
+          const float4 a = ldg_stream(reinterpret_cast<const float4*>(p));
+          const float4 b = ldg_stream(reinterpret_cast<const float4*>(p) + 1);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+          v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (lane * 8 + i < dim) v[i] = __ldg(p + i);
       }
-    } else {
+    }
+    double ss = 0.0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (lane * 8 + i < dim) v[i] = __ldg(p + i);
+    for (int i = 0; i < 8; ++i) ss = fma((double)v[i], (double)v[i], ss);
+    ss = warp_sum(ss);
+    const double n64 = fmax(sqrt(ss), 1e-12);
+    // the fp16 operand only has to be an accurate normalisation (its rounding residual is
+    // measured below and the 1e-6 slack of pair_eps covers the 2-ulp reciprocal)
+    const float inv = (float)(1.0 / n64);
+    float res = 0.f;
+    uint32_t h2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = v[2 * i] * inv, b = v[2 * i + 1] * inv;
+      const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+      const float da = a - __half2float(ha), db = b - __half2float(hb);
+      res = fmaf(da, da, res);
+      res = fmaf(db, db, res);
+      h2[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+    }
+    res = warp_sum(res);
+    if (lane < nchunks)
+      *reinterpret_cast<uint4*>(packed + tilepack_chunk_offset(r, lane, nkb)) =
+          make_uint4(h2[0], h2[1], h2[2], h2[3]);
+    if (lane == 0) {
+      const float rr = (r < rows) ? sqrtf(res) * 1.00001f + 1e-12f : 0.f;
+      nrm[r] = n64;
+      resid[r] = rr;
+      if (r < rows) {
+        run_max = fmaxf(run_max, rr);
+        if (!(ss <= 1.0e300)) run_bad = 1u;          // inf / NaN input
+      }
     }
   }
-  double ss = 0.0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) ss = fma((double)v[i], (double)v[i], ss);
-  ss = warp_sum(ss);
-  const double n64 = fmax(sqrt(ss), 1e-12);
-  const float n = (float)n64;
-  float res = 0.f;
-  uint32_t h2[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float a = __fdiv_rn(v[2 * i], n), b = __fdiv_rn(v[2 * i + 1], n);
-    const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-    const float da = a - __half2float(ha), db = b - __half2float(hb);
-    res = fmaf(da, da, res);
-    res = fmaf(db, db, res);
-    h2[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
-  }
-  res = warp_sum(res);
-  if (lane < nchunks)
-    *reinterpret_cast<uint4*>(packed + tilepack_chunk_offset(r, lane, nkb)) =
-        make_uint4(h2[0], h2[1], h2[2], h2[3]);
-  if (lane == 0) {
-    const float rr = (r < rows) ? sqrtf(res) * 1.00001f + 1e-12f : 0.f;
-    nrm[r] = n64;
-    resid[r] = rr;
-    if (r < rows) {
-      atomicMax(&stats[0], __float_as_uint(rr));
-      if (!(ss <= 1.0e300)) atomicOr(&stats[1], 1u);       // inf / NaN input
-    }
+  if (lane == 0) { s_max[warp] = __float_as_uint(run_max); s_bad[warp] = run_bad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t m = 0u, bad = 0u;
+    for (int w = 0; w < 8; ++w) { m = max(m, s_max[w]); bad |= s_bad[w]; }
+    atomicMax(&stats[0], m);
+    if (bad) atomicOr(&stats[1], 1u);
   }
 }
 
@@ -120,6 +137,10 @@ struct SimParams {
   float* dump;          // debug: raw similarities [Q, dump_ld]
   int64_t dump_ld;
   int ablate;           // timing experiments only (MCLST_SIM_ABLATE): 1 = load TMEM but do not filter, 2 = do not even load
+  // seed pass: visit n_tiles tiles tile_begin + i * tile_stride and only record the maximum of
+  // every 32-score chunk into seed_out [q_pad][n_tiles * 8] (no candidates, no thresholds)
+  float* seed_out;
+  int tile_begin, tile_stride, n_tiles;     // used when seed_out != nullptr
 };
 
 // eps: |tensor-core score - exact cosine| for a pair with fp16 residual norms rq, rs
@@ -262,8 +283,11 @@ sim_topk_kernel(const SimParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, s = blockIdx.y;
   const int nkb = p.nkb;
-  const int t0 = (int)(((int64_t)p.tiles_total * s) / p.S);
-  const int t1 = (int)(((int64_t)p.tiles_total * (s + 1)) / p.S);
+  const bool seeding = p.seed_out != nullptr;
+  const int stride = seeding ? p.tile_stride : 1;
+  const int t0 = seeding ? p.tile_begin : (int)(((int64_t)p.tiles_total * s) / p.S);
+  const int t1 = seeding ? p.tile_begin + p.n_tiles * p.tile_stride
+                         : (int)(((int64_t)p.tiles_total * (s + 1)) / p.S);
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
@@ -290,7 +314,7 @@ sim_topk_kernel(const SimParams p) {
                  p.qpack + ((size_t)qb * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES, bar_a);
       uint32_t stage = 0, phase = 0;
       constexpr uint32_t kShare = ST_STAGE_BYTES / CL;          // bytes this CTA fetches per stage
-      for (int t = t0; t < t1; ++t) {
+      for (int t = t0; t < t1; t += stride) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bar_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bar_full[stage], ST_STAGE_BYTES);
@@ -321,7 +345,7 @@ sim_topk_kernel(const SimParams p) {
       const uint32_t b_base = smem_u32(sB);
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      for (int t = t0; t < t1; ++t, ++it) {
+      for (int t = t0; t < t1; t += stride, ++it) {
         const int buf = it & 1;
         mbar_wait(&bar_tempty[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -363,7 +387,7 @@ sim_topk_kernel(const SimParams p) {
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + part * PART_COLS;
     int it = 0;
 #pragma unroll 1
-    for (int t = t0; t < t1; ++t, ++it) {
+    for (int t = t0; t < t1; t += stride, ++it) {
       const int buf = it & 1;
       // adopt the best threshold any other stream of this query has published so far
       const uint32_t gk = q_valid ? *reinterpret_cast<volatile uint32_t*>(my_gthr) : 0u;
@@ -374,6 +398,24 @@ sim_topk_kernel(const SimParams p) {
       const int64_t col_base = (int64_t)t * ST_BN + part * PART_COLS;
       const int n_valid = (int)min((int64_t)PART_COLS, p.N - col_base);   // < PART_COLS only at the bank tail
       uint32_t va[32], vb[32];
+      if (seeding) {
+        // record the maximum of every 32-score chunk of this thread's columns
+        float* so = p.seed_out + (size_t)q * (p.n_tiles * 8) + (size_t)it * 8 + part * NCH;
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          tmem_ld_32x32(taddr + c * 32, va);
+          tmem_ld_wait();
+          float m = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            m = fmaxf(m, (col_base + c * 32 + j < p.N) ? __uint_as_float(va[j]) : -INFINITY);
+          if (q_valid) so[c] = m;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[buf]);
+        continue;
+      }
       if (p.ablate == 2) {
         tc_fence_before();
         __syncwarp();
@@ -422,8 +464,341 @@ sim_topk_kernel(const SimParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ============================================================================ sim_topk (event ring)
+// Same TMA -> tcgen05.mma -> TMEM pipeline, different drain.  ncu on the kernel above showed the
+// TMEM-critical warps spending half their time in single-lane append chains and L2 round trips
+// (prunes) between tcgen05.ld and the TMEM release.  Here the 8 DETECTOR warps only compute the
+// maximum of every 32-score chunk and, when it beats the row's threshold, dump the chunk
+// (8 x st.shared.v4 + header) into a shared-memory ring; 4 WORKER warps pop the records and do
+// the data-dependent part -- threshold test with all 32 lanes on the 32 scores, ballot
+// compaction, append, prune -- off the TMEM critical path.  A row is always handled by worker
+// (row % 4), so its candidate buffer, count and threshold have a single writer, and the two
+// column halves of a row share one stream (streams per query = S, not 2 S).
+constexpr int RG_DET = 8;                 // detector warps (2 per TMEM lane quadrant)
+constexpr int RG_WRK = 4;                 // worker warps
+constexpr int RG_THREADS = 64 + 32 * (RG_DET + RG_WRK);
+constexpr int RG_SLOTS = 44;              // records per worker ring
+constexpr int RG_REC_WORDS = 36;          // 32 scores + row + column base + 2 pad  (144 B)
+constexpr int RG_EXTRA = RG_WRK * RG_SLOTS * (RG_REC_WORDS + 1) * 4 + 128 * 16 + 256;
+constexpr int RG_SMEM = ST_A_BYTES + ST_STAGES * ST_STAGE_BYTES + 1024 + RG_EXTRA + 1024;
+static_assert(RG_SMEM <= 232448, "ring kernel exceeds the 227 KiB shared-memory limit");
+
+template <int CAP>
+__global__ void __launch_bounds__(RG_THREADS, 1)
+sim_topk_ring_kernel(const SimParams p) {
+  constexpr int PART_COLS = ST_BN / 2;
+  constexpr int NCH = PART_COLS / 32;
+  constexpr int EPL = CAP / 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + ST_A_BYTES;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + ST_STAGES * ST_STAGE_BYTES);
+  uint64_t* bar_empty = bar_full + ST_STAGES;
+  uint64_t* bar_a = bar_empty + ST_STAGES;
+  uint64_t* bar_tfull = bar_a + 1;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  // ---- ring + per-row state (after the 1 KiB barrier block)
+  uint32_t* ring = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bar_full) + 1024);
+  volatile int* ring_seq = reinterpret_cast<volatile int*>(ring + RG_WRK * RG_SLOTS * RG_REC_WORDS);
+  uint32_t* thr_sm = const_cast<uint32_t*>(reinterpret_cast<volatile uint32_t*>(ring_seq + RG_WRK * RG_SLOTS));
+  int* cnt_sm = reinterpret_cast<int*>(thr_sm + 128);
+  float* e2_sm = reinterpret_cast<float*>(cnt_sm + 128);
+  int* flag_sm = reinterpret_cast<int*>(e2_sm + 128);
+  int* ring_head = flag_sm + 128;                  // [RG_WRK] reserved records
+  volatile int* ring_tail = ring_head + RG_WRK;    // [RG_WRK] consumed records
+  int* det_done = const_cast<int*>(ring_tail) + RG_WRK;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, s = blockIdx.y;
+  const int nkb = p.nkb;
+  const int t0 = (int)(((int64_t)p.tiles_total * s) / p.S);
+  const int t1 = (int)(((int64_t)p.tiles_total * (s + 1)) / p.S);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ST_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    mbar_init(bar_a, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], RG_DET); }
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < RG_WRK * RG_SLOTS; i += RG_THREADS) ring_seq[i] = 0;
+  if (threadIdx.x < 128) {
+    const int64_t q = (int64_t)qb * 128 + threadIdx.x;
+    const bool ok = q < p.Q;
+    const float rs_max = __uint_as_float(p.bank_stats[0]);
+    e2_sm[threadIdx.x] = 2.02f * pair_eps(ok ? p.q_resid[q] : 0.f, rs_max);
+    const uint32_t g = ok ? p.gthr[q] : 0u;
+    // ordered key of the threshold: -inf for live rows, +inf for padding rows (never pass)
+    thr_sm[threadIdx.x] = ok ? (g != 0u ? g : f2ord(__int_as_float(0xff800000)))
+                             : f2ord(__int_as_float(0x7f800000));
+    cnt_sm[threadIdx.x] = 0;
+    flag_sm[threadIdx.x] = 0;
+  }
+  if (threadIdx.x < RG_WRK) { ring_head[threadIdx.x] = 0; ring_tail[threadIdx.x] = 0; }
+  if (threadIdx.x == 0) *det_done = 0;
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint64_t pol_keep = policy_evict_last();
+      mbar_arrive_expect_tx(bar_a, (uint32_t)(nkb * TP_SLICE_BYTES));
+      for (int kb = 0; kb < nkb; ++kb)
+        bulk_g2s(sA + kb * TP_SLICE_BYTES,
+                 p.qpack + ((size_t)qb * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES, bar_a);
+      uint32_t stage = 0, phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bar_full[stage], ST_STAGE_BYTES);
+          uint8_t* dst = sB + stage * ST_STAGE_BYTES;
+          bulk_g2s_hint(dst, p.bpack + ((size_t)(2 * t) * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES,
+                        &bar_full[stage], pol_keep);
+          bulk_g2s_hint(dst + TP_SLICE_BYTES, p.bpack + ((size_t)(2 * t + 1) * nkb + kb) * TP_SLICE_BYTES,
+                        TP_SLICE_BYTES, &bar_full[stage], pol_keep);
+          if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, ST_BN, false);
+      mbar_wait(bar_a, 0);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(sA);
+      const uint32_t b_base = smem_u32(sB);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&bar_tempty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * ST_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bar_full[stage], phase);
+          tc_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t ad = make_smem_desc_sw128(a_base + kb * TP_SLICE_BYTES + k4 * 32);
+            const uint64_t bd = make_smem_desc_sw128(b_base + stage * ST_STAGE_BYTES + k4 * 32);
+            mma_f16_ss(d_tmem, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+          }
+          mma_commit(&bar_empty[stage]);
+          if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(&bar_tfull[buf]);
+      }
+    }
+  } else if (warp < 2 + RG_DET) {
+    // ------------------------------------------------------------ detectors
+    const int quad = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int64_t q = (int64_t)qb * 128 + row;
+    const bool q_valid = q < p.Q;
+    const int wk = row & (RG_WRK - 1);
+    uint32_t* my_ring = ring + wk * RG_SLOTS * RG_REC_WORDS;
+    volatile int* my_seq = ring_seq + wk * RG_SLOTS;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + part * PART_COLS;
+    int it = 0;
+#pragma unroll 1
+    for (int t = t0; t < t1; ++t, ++it) {
+      const int buf = it & 1;
+      // another CTA / stream of this query may have published a better bound
+      const uint32_t gk = q_valid ? *reinterpret_cast<volatile uint32_t*>(p.gthr + q) : 0u;
+      mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t tk = *reinterpret_cast<volatile uint32_t*>(thr_sm + row);
+      if (gk > tk) { atomicMax(thr_sm + row, gk); tk = gk; }
+      const float thr = ord2f(tk);
+      const uint32_t taddr = t_lane + buf * ST_BN;
+      const uint32_t col_base = (uint32_t)t * ST_BN + part * PART_COLS;
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(taddr, va);
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t (&v)[32] = h ? vb : va;
+          tmem_ld_wait();
+          if (h == 0) {
+            tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+          } else if (c + 2 < NCH) {
+            tmem_ld_32x32(taddr + (c + 2) * 32, va);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[buf]);
+          }
+          if (p.dump != nullptr && q_valid) {
+            for (int j = 0; j < 32; ++j) {
+              const int64_t col = (int64_t)col_base + (c + h) * 32 + j;
+              if (col < p.N) p.dump[q * p.dump_ld + col] = __uint_as_float(v[j]);
+            }
+          }
+          float m = __uint_as_float(v[0]);
+#pragma unroll
+          for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+          if (p.ablate == 0 && m > thr) {
+            // hand the chunk to the row's worker
+            const int slot = atomicAdd(&ring_head[wk], 1);
+            if (slot - ring_tail[wk] >= RG_SLOTS) {
+              const uint64_t w0 = globaltimer();
+              while (slot - ring_tail[wk] >= RG_SLOTS)
+                if (globaltimer() - w0 > 4000000000ull) __trap();
+            }
+            uint32_t* rec = my_ring + (slot % RG_SLOTS) * RG_REC_WORDS;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(rec + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            rec[32] = (uint32_t)row;
+            rec[33] = col_base + (c + h) * 32;
+            __threadfence_block();
+            my_seq[slot % RG_SLOTS] = slot + 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); atomicAdd(det_done, 1); }
+  } else {
+    // ------------------------------------------------------------ workers
+    const int wk = warp - (2 + RG_DET);
+    const uint32_t* my_ring = ring + wk * RG_SLOTS * RG_REC_WORDS;
+    volatile int* my_seq = ring_seq + wk * RG_SLOTS;
+    const int k = p.k;
+    int t = 0;
+    for (;;) {
+      // wait for record t (or for the detectors to finish with nothing left)
+      bool have = false;
+      uint32_t spins = 0;
+      const uint64_t w_start = globaltimer();
+      for (;;) {
+        if (my_seq[t % RG_SLOTS] == t + 1) { have = true; break; }
+        if (*reinterpret_cast<volatile int*>(det_done) == RG_DET &&
+            *reinterpret_cast<volatile int*>(&ring_head[wk]) == t) break;
+        if ((++spins & 0xfffu) == 0 && globaltimer() - w_start > 20000000000ull) __trap();
+      }
+      if (!have) break;
+      __threadfence_block();
+      const uint32_t* rec = my_ring + (t % RG_SLOTS) * RG_REC_WORDS;
+      const uint32_t vbits = rec[lane];
+      const int row = (int)rec[32];
+      const uint32_t cb = rec[33];
+      __syncwarp();
+      if (lane == 0) ring_tail[wk] = t + 1;          // the slot may be reused
+      ++t;
+      const float v = __uint_as_float(vbits);
+      const float thr = ord2f(*reinterpret_cast<volatile uint32_t*>(thr_sm + row));
+      const bool pass = v > thr && (int64_t)cb + lane < p.N;
+      const unsigned bal = __ballot_sync(0xffffffffu, pass);
+      if (bal == 0u) continue;
+      const int64_t q = (int64_t)qb * 128 + row;
+      uint2* buf = p.cand + ((size_t)q * p.S + s) * CAP;
+      int cnt = cnt_sm[row];
+      if (pass) buf[cnt + __popc(bal & ((1u << lane) - 1u))] = make_uint2(vbits, cb + lane);
+      cnt += __popc(bal);
+      if (cnt > CAP - 32) {
+        // ---- prune the row: threshold = (lower bound of its k-th best) - e2
+        __syncwarp();
+        __threadfence_block();
+        uint32_t keys[EPL], vals[EPL], idxs[EPL];
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+          const int i = lane + 32 * j;
+          if (i < cnt) {
+            const uint2 e = buf[i];
+            vals[j] = e.x; idxs[j] = e.y; keys[j] = f2ord(__uint_as_float(e.x));
+          } else {
+            keys[j] = 0u; vals[j] = 0u; idxs[j] = 0u;
+          }
+        }
+        uint32_t T = 0;
+#pragma unroll 1
+        for (int bit = 31; bit >= 8; --bit) {
+          const uint32_t cand = T | (1u << bit);
+          int c = 0;
+#pragma unroll
+          for (int j = 0; j < EPL; ++j) c += (keys[j] >= cand) ? 1 : 0;
+          c = __reduce_add_sync(0xffffffffu, c);
+          if (c >= k) T = cand;
+        }
+        float new_thr = ord2f(T) - e2_sm[row];
+        uint32_t nk = f2ord(new_thr);
+        if (lane == 0) {
+          const uint32_t old = atomicMax(p.gthr + q, nk);     // publish; adopt a better global bound
+          if (old > nk) nk = old;
+        }
+        nk = __shfl_sync(0xffffffffu, nk, 0);
+        new_thr = ord2f(nk);
+        int out = 0;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+          const int i = lane + 32 * j;
+          const bool keep = (i < cnt) && (__uint_as_float(vals[j]) > new_thr);
+          const unsigned b2 = __ballot_sync(0xffffffffu, keep);
+          if (keep) buf[out + __popc(b2 & ((1u << lane) - 1u))] = make_uint2(vals[j], idxs[j]);
+          out += __popc(b2);
+        }
+        cnt = out;
+        if (lane == 0) {
+          if (out > CAP - 64) {            // band denser than the buffer: exact path takes the row
+            flag_sm[row] = 1;
+            atomicMax(thr_sm + row, f2ord(__int_as_float(0x7f800000)));
+          } else {
+            atomicMax(thr_sm + row, nk);
+          }
+        }
+      }
+      if (lane == 0) cnt_sm[row] = cnt;
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int64_t q = (int64_t)qb * 128 + threadIdx.x;
+    if (q < p.Q) p.cand_cnt[(size_t)q * p.S + s] = flag_sm[threadIdx.x] ? -1 : cnt_sm[threadIdx.x];
+  }
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ============================================================================ seed thresholds
+// gthr[q] = (24-bit lower bound of the k-th largest chunk maximum of the sample) - e2.  The k
+// largest chunk maxima are k distinct bank rows, so this is a valid lower bound of the k-th
+// best score of the whole bank, minus the band: every stream starts warm instead of with -inf.
+__global__ void __launch_bounds__(128)
+seed_threshold_kernel(const float* __restrict__ seed, int n_vals, int64_t Q, int k,
+                      const float* __restrict__ q_resid, const uint32_t* __restrict__ bank_stats,
+                      uint32_t* __restrict__ gthr) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const float* v = seed + (size_t)q * n_vals;
+  uint32_t T = 0;
+  for (int bit = 31; bit >= 8; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+    for (int i = lane; i < n_vals; i += 32) c += (f2ord(v[i]) >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= k) T = cand;
+  }
+  if (lane == 0 && T != 0u) {
+    const float e2 = 2.02f * pair_eps(q_resid[q], __uint_as_float(bank_stats[0]));
+    const float thr = ord2f(T) - e2;
+    if (thr == thr && thr > -INFINITY) gthr[q] = f2ord(thr);
+  }
+}
+
 // ============================================================================ rerank
-constexpr int RR_MAX = 1024;     // most survivors re-ranked exactly per query
+constexpr int RR_MAX = 512;      // most survivors re-ranked exactly per query (more -> exact path)
 
 struct RerankParams {
   const uint2* cand;
@@ -493,50 +868,60 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
   int M = 0;
   // Every stream dropped only scores at or below a threshold that was <= the final shared one,
   // and the shared one is itself <= (k-th best) - 2 eps: stale entries below it go right away.
-  const uint32_t g_key = p.gthr[q];
+  // If the buffer still fills up, the band is tightened from what has been gathered so far
+  // (the k-th best of any subset is a lower bound of the global k-th best) and gathering resumes.
+  uint32_t g_key = p.gthr[q];
+  const float rs_max = __uint_as_float(p.bank_stats[0]);
+  const float e2 = 2.02f * pair_eps(p.q_resid[q], rs_max);
+  auto tighten = [&](int count) -> int {      // radix descent (24 bits) + in-place band compaction
+    uint32_t T = 0;
+    for (int bit = 31; bit >= 8; --bit) {
+      const uint32_t candT = T | (1u << bit);
+      int c = 0;
+      for (int i = lane; i < count; i += 32) c += ((uint32_t)(ent[i] >> 32) >= candT) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= p.k) T = candT;
+    }
+    const uint32_t band_key = f2ord(ord2f(T) - e2);
+    if (band_key > g_key) g_key = band_key;
+    int kept = 0;
+    for (int base = 0; base < count; base += 32) {
+      const int i = base + lane;
+      unsigned long long e = 0;
+      bool keep = false;
+      if (i < count) { e = ent[i]; keep = (uint32_t)(e >> 32) > g_key; }
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      __syncwarp();
+      if (keep) ent[kept + __popc(bal & ((1u << lane) - 1u))] = e;
+      kept += __popc(bal);
+      __syncwarp();
+    }
+    return kept;
+  };
   for (int s = 0; s < p.SS && !bad; ++s) {
     const int c = p.cand_cnt[(size_t)q * p.SS + s];
     if (c < 0) { bad = true; break; }
     const uint2* src = p.cand + ((size_t)q * p.SS + s) * p.cap;
     for (int base = 0; base < c; base += 32) {
+      if (M + 32 > per_warp_entries) {
+        __syncwarp();
+        M = tighten(M);
+        if (M + 32 > per_warp_entries) { bad = true; break; }
+      }
       const int i = base + lane;
       uint32_t key = 0, idx = 0;
       if (i < c) { const uint2 e = src[i]; key = f2ord(__uint_as_float(e.x)); idx = e.y; }
       const bool keep = (i < c) && key > g_key;
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
-      const int n_keep = __popc(bal);
-      if (M + n_keep > per_warp_entries) { bad = true; break; }
       if (keep) ent[M + __popc(bal & ((1u << lane) - 1u))] = ((unsigned long long)key << 32) | idx;
-      M += n_keep;
+      M += __popc(bal);
     }
   }
   __syncwarp();
   if (M < p.k) bad = true;      // cannot happen for finite inputs; the exact path decides
   int n_s = 0;
   if (!bad) {
-    // ---- lower bound of the k-th best approximate score (radix descent, 24 bits)
-    uint32_t T = 0;
-    for (int bit = 31; bit >= 8; --bit) {
-      const uint32_t candT = T | (1u << bit);
-      int c = 0;
-      for (int i = lane; i < M; i += 32) c += ((uint32_t)(ent[i] >> 32) >= candT) ? 1 : 0;
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (c >= p.k) T = candT;
-    }
-    const float rs_max = __uint_as_float(p.bank_stats[0]);
-    const float band = ord2f(T) - 2.02f * pair_eps(p.q_resid[q], rs_max);
-    // ---- compact the band in place
-    for (int base = 0; base < M; base += 32) {
-      const int i = base + lane;
-      unsigned long long e = 0;
-      bool keep = false;
-      if (i < M) { e = ent[i]; keep = ord2f((uint32_t)(e >> 32)) > band; }
-      const unsigned bal = __ballot_sync(0xffffffffu, keep);
-      __syncwarp();
-      if (keep) ent[n_s + __popc(bal & ((1u << lane) - 1u))] = e;
-      n_s += __popc(bal);
-      __syncwarp();
-    }
+    n_s = tighten(M);
     if (n_s > RR_MAX) bad = true;
   }
   if (bad) {
@@ -643,6 +1028,14 @@ int sim_topk_ablate() {
   return v;
 }
 
+int sim_topk_use_ring() {
+  // Event-ring drain (sim_topk_ring_kernel): bit-exact and 2 % faster than the per-thread drain
+  // once thresholds are warm (26.1 vs 26.7 ms at cfg4), but its 4 worker warps fall behind while
+  // thresholds are still converging (38 vs 32 ms end to end) -- off until the seed pass is tighter.
+  static const int v = env_int("MCLST_SIM_RING", 0);
+  return v;
+}
+
 int sim_topk_epw() {
   static const int forced = env_int("MCLST_SIM_EPW", 0);
   if (forced == 4 || forced == 8 || forced == 16) return forced;
@@ -659,7 +1052,7 @@ int sim_topk_splits(int64_t n_query, int64_t n_bank, int cluster) {
   double best_eff = 0.0;
   // at most 8 candidate streams per query (S * epw/4): the re-rank merges them in 16 KiB of
   // shared memory per query
-  const int smax = (int)std::min<int64_t>(std::max(1, 8 / (sim_topk_epw() / 4)), tiles);
+  const int smax = (int)std::min<int64_t>(sim_topk_use_ring() ? 8 : std::max(1, 8 / (sim_topk_epw() / 4)), tiles);
   for (int S = 1; S <= smax; ++S) {
     const int64_t ctas = qblocks * S;
     const double eff = (double)ctas / (double)(ceil_div(ctas, sms) * sms);
@@ -679,7 +1072,8 @@ void tc_workspace(Arena& a, int64_t n_bank, int64_t n_query, int dim, int top_k,
   w.q_pad = (int64_t)align_up((size_t)n_query, 128 * w.cluster);
   w.n_pad = (int64_t)align_up((size_t)n_bank, ST_BN);
   w.S = sim_topk_splits(n_query, n_bank, w.cluster);
-  w.SS = w.S * (w.epw / 4);
+  w.ring = sim_topk_use_ring() && w.cluster == 1 && tc_cap_for_k(top_k) <= 512;
+  w.SS = w.ring ? w.S : w.S * (w.epw / 4);
   w.cap = tc_cap_for_k(top_k);
   w.stats = a.take<uint32_t>(16);
   w.qpack = a.take<uint8_t>(tilepack_bytes(w.q_pad, nkb * 64));
@@ -692,13 +1086,21 @@ void tc_workspace(Arena& a, int64_t n_bank, int64_t n_query, int dim, int top_k,
   w.cand = a.take<uint2>((size_t)w.q_pad * w.SS * w.cap);
   w.cand_cnt = a.take<int>((size_t)w.q_pad * w.SS);
   w.fb_list = a.take<int>((size_t)n_query);
+  // seed pass: a strided 1/32 sample of the bank tiles, at most 64 tiles, at least 2k chunks
+  const int64_t tiles = w.n_pad / ST_BN;
+  static const int seed_max = env_int("MCLST_SIM_SEED_TILES", 128);
+  int n_seed = (int)std::min<int64_t>(seed_max, tiles / 8);
+  static const int seed_env = env_int("MCLST_SIM_SEED", 1);
+  if (!seed_env || n_seed * 8 < 2 * top_k) n_seed = 0;
+  w.n_seed = n_seed;
+  w.seed = n_seed ? a.take<float>((size_t)w.q_pad * n_seed * 8) : nullptr;
 }
 
 int launch_pack_rows(const float* x, int64_t rows, int64_t rows_pad, int64_t ld, int dim, int nkb,
                      uint8_t* packed, double* nrm, float* resid, uint32_t* stats, cudaStream_t st) {
   const int wpb = 8;
   const bool vec = (dim % 8 == 0) && (ld % 4 == 0) && ((uintptr_t)x % 16 == 0);
-  const unsigned grid = (unsigned)ceil_div(rows_pad, wpb);
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(rows_pad, wpb), (int64_t)sm_count() * 8 * 4);
   if (vec) pack_rows_kernel<true><<<grid, wpb * 32, 0, st>>>(x, rows, rows_pad, ld, dim, nkb, packed, nrm, resid, stats);
   else pack_rows_kernel<false><<<grid, wpb * 32, 0, st>>>(x, rows, rows_pad, ld, dim, nkb, packed, nrm, resid, stats);
   MCLST_LAUNCH_CHECK();
@@ -748,8 +1150,37 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
   p.q_resid = w.q_resid; p.bank_stats = w.stats; p.cand = w.cand; p.cand_cnt = w.cand_cnt;
   p.gthr = w.gthr; p.dump = dump; p.dump_ld = dump_ld;
   p.ablate = sim_topk_ablate();
-  MCLST_CUDA(cudaMemsetAsync(w.gthr, 0, (size_t)w.q_pad * sizeof(uint32_t), st));
+  p.seed_out = nullptr; p.tile_begin = 0; p.tile_stride = 1; p.n_tiles = 0;
+  static const int keep_gthr = env_int("MCLST_SIM_KEEP_GTHR", 0);   // experiment: warm thresholds
+  if (!keep_gthr) MCLST_CUDA(cudaMemsetAsync(w.gthr, 0, (size_t)w.q_pad * sizeof(uint32_t), st));
   dim3 grid((unsigned)(w.q_pad / 128), (unsigned)w.S);
+  if (w.n_seed > 0 && dump == nullptr && !keep_gthr && p.ablate == 0) {
+    // ---- seed pass (legacy drain, 8 epilogue warps, one CTA per query block)
+    SimParams sp = p;
+    sp.seed_out = w.seed; sp.n_tiles = w.n_seed; sp.tile_begin = 0;
+    sp.tile_stride = std::max(1, p.tiles_total / w.n_seed);
+    sp.S = 1;
+    dim3 sgrid((unsigned)(w.q_pad / 128), 1);
+    int rc = launch_sim_topk_t<256, 1, 8>(sp, sgrid, st);
+    if (rc) return rc;
+    seed_threshold_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, st>>>(
+        w.seed, w.n_seed * 8, n_query, top_k, w.q_resid, w.stats, w.gthr);
+    MCLST_LAUNCH_CHECK();
+  }
+  if (w.ring) {
+    auto launch_ring = [&](auto kern) -> int {
+      static bool attr_set = false;
+      if (!attr_set) {
+        MCLST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RG_SMEM));
+        attr_set = true;
+      }
+      kern<<<grid, RG_THREADS, RG_SMEM, st>>>(p);
+      MCLST_LAUNCH_CHECK();
+      return 0;
+    };
+    if (w.cap == 256) return launch_ring(sim_topk_ring_kernel<256>);
+    if (w.cap == 512) return launch_ring(sim_topk_ring_kernel<512>);
+  }
   if (w.cap == 256) {
     if (w.cluster == 1) return launch_sim_topk_e<256, 1>(w.epw, p, grid, st);
     if (w.cluster == 2) return launch_sim_topk_e<256, 2>(w.epw, p, grid, st);
@@ -776,7 +1207,7 @@ int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64
   // shared memory: per warp a power-of-two number of 8-byte entries (bitonic sort), at most 4096;
   // a query whose streams hold more than that goes to the exact path
   int per_warp = 1;
-  while (per_warp < w.SS * w.cap && per_warp < 2048) per_warp <<= 1;
+  while (per_warp < w.SS * w.cap && per_warp < 1024) per_warp <<= 1;
   if (per_warp < 2 * top_k) per_warp = 2048;
   int wpb = 4;
   while (wpb > 1 && (size_t)wpb * per_warp * 8 > 64 * 1024) wpb >>= 1;
