@@ -181,7 +181,8 @@ int mclst_neighbor_weights(const float* distances, const float* values, int64_t 
  *   MCLST_T_SOFT_MUL  baselines/Bleep/models.py:70-79: ... /2*T; targets stay in the graph.
  * spot_emb, image_emb: [batch, dim] float32.  loss_out: one float32 (device).  d_spot /
  * d_image (both or neither): gradients of the loss w.r.t. the two inputs.  No batch x batch
- * matrix is held beyond one row block (MCLST_LOSS_SCRATCH_MB, default 1024).  The workspace
+ * matrix is held beyond one row block (scratch budget MCLST_LOSS_SCRATCH_MB, default 32768:
+ * batches up to 32k rows then fit one block; smaller budgets stream row blocks).  The workspace
  * query takes the number of rows this call owns (= batch here). */
 int mclst_contrastive_loss_workspace_bytes(int batch, int dim, int target_mode, int64_t rows_local,
                                            size_t* bytes);

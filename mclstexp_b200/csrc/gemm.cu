@@ -135,25 +135,32 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// Persistent: grid = min(tiles, SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ... with the
+// same three roles as sim_topk (TMA producer / single-thread MMA issuer / 4 epilogue warps) and a
+// double-buffered 2 x 256-column TMEM accumulator, so the epilogue of tile i (TMEM -> registers ->
+// 128 KiB of global stores) overlaps the MMAs of tile i+1.  Tile order keeps the B operand tile
+// fixed across consecutive CTAs (L2 reuse).
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_tn_kernel(const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + GM_STAGES * GM_STAGE_BYTES);
   uint64_t* bar_empty = bar_full + GM_STAGES;
-  uint64_t* bar_done = bar_empty + GM_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
+  uint64_t* bar_tfull = bar_empty + GM_STAGES;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mb = blockIdx.x, nb = blockIdx.y, z = blockIdx.z;
   const int nkb = p.nkb;
   const int iters = p.nseg * nkb;
+  const int mt = (int)((p.M + GM_BM - 1) / GM_BM), nt = (int)((p.N + GM_BN - 1) / GM_BN);
+  const int64_t tiles = (int64_t)mt * nt * p.batch;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < GM_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-    mbar_init(bar_done, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -161,94 +168,113 @@ gemm_tn_kernel(const GemmParams p) {
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint8_t* a_hi = p.a_hi + (size_t)z * p.a_batch_bytes;
-      const uint8_t* a_lo = p.a_lo ? p.a_lo + (size_t)z * p.a_batch_bytes : nullptr;
-      const uint8_t* b_hi = p.b_hi + (size_t)z * p.b_batch_bytes;
-      const uint8_t* b_lo = p.b_lo ? p.b_lo + (size_t)z * p.b_batch_bytes : nullptr;
       uint32_t stage = 0, phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        const int seg = it / nkb, kb = it - seg * nkb;
-        // segment 0: hi*hi, 1: lo*hi, 2: hi*lo
-        const uint8_t* a = (seg == 1) ? a_lo : a_hi;
-        const uint8_t* b = (seg == 2) ? b_lo : b_hi;
-        mbar_wait(&bar_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&bar_full[stage], GM_STAGE_BYTES);
-        uint8_t* dst = smem + stage * GM_STAGE_BYTES;
-        bulk_g2s(dst, a + ((size_t)mb * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES, &bar_full[stage]);
-        bulk_g2s(dst + TP_SLICE_BYTES, b + ((size_t)(2 * nb) * nkb + kb) * TP_SLICE_BYTES,
-                 TP_SLICE_BYTES, &bar_full[stage]);
-        bulk_g2s(dst + 2 * TP_SLICE_BYTES, b + ((size_t)(2 * nb + 1) * nkb + kb) * TP_SLICE_BYTES,
-                 TP_SLICE_BYTES, &bar_full[stage]);
-        if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int mb = (int)(tile % mt), nb = (int)((tile / mt) % nt), z = (int)(tile / ((int64_t)mt * nt));
+        const uint8_t* a_hi = p.a_hi + (size_t)z * p.a_batch_bytes;
+        const uint8_t* a_lo = p.a_lo ? p.a_lo + (size_t)z * p.a_batch_bytes : nullptr;
+        const uint8_t* b_hi = p.b_hi + (size_t)z * p.b_batch_bytes;
+        const uint8_t* b_lo = p.b_lo ? p.b_lo + (size_t)z * p.b_batch_bytes : nullptr;
+        for (int it = 0; it < iters; ++it) {
+          const int seg = it / nkb, kb = it - seg * nkb;
+          // segment 0: hi*hi, 1: lo*hi, 2: hi*lo
+          const uint8_t* a = (seg == 1) ? a_lo : a_hi;
+          const uint8_t* b = (seg == 2) ? b_lo : b_hi;
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bar_full[stage], GM_STAGE_BYTES);
+          uint8_t* dst = smem + stage * GM_STAGE_BYTES;
+          bulk_g2s(dst, a + ((size_t)mb * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES, &bar_full[stage]);
+          bulk_g2s(dst + TP_SLICE_BYTES, b + ((size_t)(2 * nb) * nkb + kb) * TP_SLICE_BYTES,
+                   TP_SLICE_BYTES, &bar_full[stage]);
+          bulk_g2s(dst + 2 * TP_SLICE_BYTES, b + ((size_t)(2 * nb + 1) * nkb + kb) * TP_SLICE_BYTES,
+                   TP_SLICE_BYTES, &bar_full[stage]);
+          if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(GM_BM, GM_BN, false);
       uint32_t stage = 0, phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(&bar_full[stage], phase);
+      int n = 0;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n) {
+        const int buf = n & 1;
+        mbar_wait(&bar_tempty[buf], ((n >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * GM_STAGE_BYTES);
-        const uint32_t b_addr = a_addr + TP_SLICE_BYTES;
+        const uint32_t d_tmem = tmem_base + buf * GM_BN;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&bar_full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * GM_STAGE_BYTES);
+          const uint32_t b_addr = a_addr + TP_SLICE_BYTES;
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          mma_f16_ss(tmem_base, make_smem_desc_sw128(a_addr + k4 * 32),
-                     make_smem_desc_sw128(b_addr + k4 * 32), idesc, (it | k4) != 0 ? 1u : 0u);
-        mma_commit(&bar_empty[stage]);
-        if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
+          for (int k4 = 0; k4 < 4; ++k4)
+            mma_f16_ss(d_tmem, make_smem_desc_sw128(a_addr + k4 * 32),
+                       make_smem_desc_sw128(b_addr + k4 * 32), idesc, (it | k4) != 0 ? 1u : 0u);
+          mma_commit(&bar_empty[stage]);
+          if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(&bar_tfull[buf]);
       }
-      mma_commit(bar_done);
     }
   } else {
     // ------------------------------------------------------------ epilogue
     const int quad = warp & 3;
-    const int64_t m = (int64_t)mb * GM_BM + quad * 32 + lane;
-    const bool m_ok = m < p.M;
-    float* crow = p.c + (size_t)z * p.c_batch_elems + m * p.ldc;
-    const float* rrow = p.residual ? p.residual + (size_t)z * p.c_batch_elems + m * p.ldc : nullptr;
-    mbar_wait(bar_done, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int64_t n0 = (int64_t)nb * GM_BN;
-    const bool vec_ok = (p.ldc % 4 == 0) && ((uintptr_t)p.c % 16 == 0) &&
+    const bool vec_ok = (p.ldc % 4 == 0) && ((uintptr_t)p.c % 16 == 0) && (p.c_batch_elems % 4 == 0) &&
                         (!p.residual || (uintptr_t)p.residual % 16 == 0);
+    int n = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n) {
+      const int mb = (int)(tile % mt), nb = (int)((tile / mt) % nt), z = (int)(tile / ((int64_t)mt * nt));
+      const int buf = n & 1;
+      const int64_t m = (int64_t)mb * GM_BM + quad * 32 + lane;
+      const bool m_ok = m < p.M;
+      float* crow = p.c + (size_t)z * p.c_batch_elems + m * p.ldc;
+      const float* rrow = p.residual ? p.residual + (size_t)z * p.c_batch_elems + m * p.ldc : nullptr;
+      mbar_wait(&bar_tfull[buf], (n >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * GM_BN;
+      const int64_t n0 = (int64_t)nb * GM_BN;
 #pragma unroll 1
-    for (int c = 0; c < GM_BN / 32; ++c) {
-      if (n0 + c * 32 >= p.N) break;             // uniform
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + c * 32, v);
-      tmem_ld_wait();
-      if (!m_ok) continue;
-      const int64_t nbase = n0 + c * 32;
-      float o[32];
+      for (int c = 0; c < GM_BN / 32; ++c) {
+        if (n0 + c * 32 >= p.N) break;             // uniform
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        if (!m_ok) continue;
+        const int64_t nbase = n0 + c * 32;
+        float o[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]) * p.alpha;
-        if (p.bias && nbase + j < p.N) x += __ldg(p.bias + nbase + j);
-        if (p.act == 1) x = gelu_erf(x);
-        o[j] = x;
-      }
-      if (vec_ok && nbase + 32 <= p.N) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 w = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-          if (rrow) {
-            const float4 rr = *reinterpret_cast<const float4*>(rrow + nbase + j);
-            w.x += rr.x; w.y += rr.y; w.z += rr.z; w.w += rr.w;
-          }
-          *reinterpret_cast<float4*>(crow + nbase + j) = w;
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]) * p.alpha;
+          if (p.bias && nbase + j < p.N) x += __ldg(p.bias + nbase + j);
+          if (p.act == 1) x = gelu_erf(x);
+          o[j] = x;
         }
-      } else {
+        if (vec_ok && nbase + 32 <= p.N) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nbase + j < p.N) crow[nbase + j] = o[j] + (rrow ? rrow[nbase + j] : 0.f);
+          for (int j = 0; j < 32; j += 4) {
+            float4 w = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            if (rrow) {
+              const float4 rr = *reinterpret_cast<const float4*>(rrow + nbase + j);
+              w.x += rr.x; w.y += rr.y; w.z += rr.z; w.w += rr.w;
+            }
+            *reinterpret_cast<float4*>(crow + nbase + j) = w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nbase + j < p.N) crow[nbase + j] = o[j] + (rrow ? rrow[nbase + j] : 0.f);
+        }
       }
+      // accumulator drained: hand the buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[buf]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 int launch_gemm_tn(const GemmParams& p, cudaStream_t st) {
@@ -260,8 +286,11 @@ int launch_gemm_tn(const GemmParams& p, cudaStream_t st) {
     MCLST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
     attr_set = true;
   }
-  dim3 grid((unsigned)ceil_div(p.M, GM_BM), (unsigned)ceil_div(p.N, GM_BN), (unsigned)std::max(1, p.batch));
-  gemm_tn_kernel<<<grid, GM_THREADS, GM_SMEM, st>>>(p);
+  GemmParams q = p;
+  q.batch = std::max(1, p.batch);
+  const int64_t tiles = ceil_div(p.M, GM_BM) * ceil_div(p.N, GM_BN) * q.batch;
+  const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
+  gemm_tn_kernel<<<grid, GM_THREADS, GM_SMEM, st>>>(q);
   MCLST_LAUNCH_CHECK();
   return 0;
 }

@@ -228,9 +228,12 @@ static LossPlan plan_loss(void* ws, size_t cap, int B, int D, int soft, int want
   return L;
 }
 
+// Row-block scratch budget.  A B200 has 180 GB: by default up to 32 GiB may be spent so that
+// batches up to 32k rows need a single row block (no recomputation of the three products per
+// sweep); smaller budgets stream the batch in row blocks.
 static size_t loss_budget() {
   const char* e = getenv("MCLST_LOSS_SCRATCH_MB");
-  return (size_t)(e ? atoll(e) : 1024) << 20;
+  return (size_t)(e ? atoll(e) : 32768) << 20;
 }
 
 // rows [i0, i0+rows) of P1 = S I^T / T, P2 = I S^T / T, P3 = [I|S][I|S]^T * a
