@@ -241,6 +241,13 @@ def train_step_cfg2(dev):
             net(batch).backward()
         ms = _time_cuda(step, iters=5, warm=2)
         res[f"G{G}"] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms}
+        try:                                   # same step replayed from a CUDA graph
+            from mclstexp_b200.graphs import GraphedTrainStep
+            gstep = GraphedTrainStep(net, batch)
+            msg = _time_cuda(lambda: gstep(batch), iters=10, warm=2)
+            res[f"G{G}"].update({"graph_ms_per_step": msg, "graph_steps_per_s": 1e3 / msg})
+        except Exception as e:                 # report, do not hide
+            res[f"G{G}"]["graph_error"] = f"{type(e).__name__}: {e}"[:200]
     return res
 
 

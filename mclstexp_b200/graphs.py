@@ -1,0 +1,53 @@
+"""CUDA-graph capture of one training step of the hot path.
+
+At the reference's batch sizes (128-1024 spots) a forward+backward of the path is ~300 small
+kernel launches and is launch-latency bound ("tiny-problem regime").
+Capturing it once and replaying removes the per-launch host cost; the kernels are unchanged.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict
+
+import torch
+
+
+class GraphedTrainStep:
+    """``step(batch) -> loss`` with forward + backward replayed from a CUDA graph.
+
+    ``model`` is a ``mclstexp_b200.model.mclSTExp_Attention`` (or any module built from this
+    package's layers) whose ``forward(batch)`` returns the loss.  Gradients land in the
+    parameters' ``.grad`` exactly as with eager ``loss.backward()``; call ``optimizer.step()``
+    after ``step()`` as usual.  Batch shapes are fixed at capture time.  Drop references to any
+    loss tensor of an earlier eager step before constructing this (a live autograd graph
+    created on the default stream invalidates the capture)."""
+
+    def __init__(self, model: torch.nn.Module, example_batch: Dict[str, torch.Tensor], warmup: int = 3):
+        self.model = model
+        self.static = {k: v.clone() for k, v in example_batch.items()}
+        self.table_rows = getattr(getattr(model, "x_embed", None), "num_embeddings", None)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up off the default stream
+            for _ in range(warmup):
+                for p in model.parameters():
+                    p.grad = None
+                model(self.static).backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        for p in model.parameters():       # backward inside the capture then ASSIGNS fresh .grad
+            p.grad = None                  # buffers from the graph's pool: every replay overwrites them
+        with torch.cuda.graph(self.graph):
+            self.loss = model(self.static)
+            self.loss.backward()
+
+    def __call__(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        pos = batch.get("position")
+        if pos is not None and self.table_rows is not None:
+            lo, hi = pos.min(), pos.max()                  # nn.Embedding would raise here
+            if bool((lo < 0) | (hi >= self.table_rows)):
+                raise IndexError("position index out of range for x_embed / y_embed")
+        for k, v in self.static.items():
+            v.copy_(batch[k], non_blocking=True)
+        self.graph.replay()
+        return self.loss

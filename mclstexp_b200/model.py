@@ -210,7 +210,9 @@ class _EmbedAdd(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         (position,) = ctx.saved_tensors
-        if int(ctx.err.item()):
+        # (reading the flag synchronises; under CUDA-graph capture the check is the caller's job:
+        # mclstexp_b200.graphs.GraphedTrainStep validates positions before every replay)
+        if not torch.cuda.is_current_stream_capturing() and int(ctx.err.item()):
             raise IndexError("position index out of range for x_embed / y_embed (nn.Embedding(65536, dim))")
         d_out = _c2d(d_out)
         B, G = d_out.shape

@@ -127,3 +127,27 @@ def test_cpu_tensors_are_rejected():
     head = mm.ProjectionHead(8, 256)
     with pytest.raises(MclstError):
         head(torch.zeros(2, 8))
+
+
+def test_graphed_train_step_matches_eager():
+    from mclstexp_b200.graphs import GraphedTrainStep
+    m = dict(G=171, E=256, heads=8, dim_head=64, layers=2, B=128, T=1.0, kind="st", seed=31)
+    net, _ = _build(m, "soft")
+    feats, expr, pos = (t.cuda() for t in _inputs(m))
+    batch = {"image": feats, "expression": expr, "position": pos}
+    net.zero_grad(set_to_none=True)
+    loss = net(batch)
+    loss.backward()
+    eager = {k: p.grad.clone() for k, p in net.named_parameters()}
+    l_eager = loss.item()
+    del loss                       # a live autograd graph from the default stream would break capture
+    step = GraphedTrainStep(net, batch)
+    for _ in range(2):
+        l = step(batch)
+    assert abs(l.item() - l_eager) <= 1e-6 * abs(l_eager)
+    for k, p in net.named_parameters():
+        assert torch.allclose(p.grad, eager[k], rtol=1e-5, atol=1e-6 * float(eager[k].abs().max()) + 1e-12), k
+    bad = dict(batch, position=pos.clone())
+    bad["position"][0, 0] = 1e6
+    with pytest.raises(IndexError):
+        step(bad)
