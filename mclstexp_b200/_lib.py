@@ -12,7 +12,7 @@ import re
 from typing import List
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmclst_b200.so")
+LIB_PATH = os.path.join(HERE, os.environ.get("MCLST_LIB_NAME", "libmclst_b200.so"))
 HEADER = os.path.join(os.path.dirname(HERE), "include", "mclst_b200.h")
 
 # weight modes / flags (mirrors of the header enums)

@@ -16,13 +16,13 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "csrc", "build")
-LIB = os.path.join(HERE, "libmclst_b200.so")
+OBJ = os.path.join(HERE, "csrc", os.environ.get("MCLST_OBJ_DIR", "build"))
+LIB = os.path.join(HERE, os.environ.get("MCLST_LIB_NAME", "libmclst_b200.so"))
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false",
-          "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+          "-Xptxas", "-v", "--expt-relaxed-constexpr"] + os.environ.get("MCLST_EXTRA_NVCC_FLAGS", "").split()
 
 
 def sources():

@@ -224,30 +224,47 @@ __device__ __noinline__ PruneState warp_prune(uint2* my_buf, uint32_t* my_gthr, 
 }
 
 // One 32-column chunk of one query row: append every similarity above the running threshold.
-// Two-level test (chunk max, then 8-wide group max) keeps the common "one survivor in the
-// warp" case at ~25 instructions.
+// Two-level test (chunk max, then FILTER_GS-wide group max) keeps the common "one survivor in
+// the warp" case short; the bank-tail bound check lives in a separate (cold) instantiation.
+#ifndef FILTER_GS
+#define FILTER_GS 8
+#endif
+template <int CAP, bool TAIL>
+__device__ __forceinline__ void filter_groups(const uint32_t (&v)[32], const float (&g)[32 / FILTER_GS],
+                                              uint2* my_buf, int& cnt, float thr, uint32_t nb,
+                                              int n_left) {
+#pragma unroll
+  for (int h = 0; h < 32 / FILTER_GS; ++h) {
+    if (g[h] > thr) {
+#pragma unroll
+      for (int j = 0; j < FILTER_GS; ++j) {
+        const int e = FILTER_GS * h + j;
+        if (__uint_as_float(v[e]) > thr && (!TAIL || e < n_left))
+          my_buf[cnt++] = make_uint2(v[e], nb + e);
+      }
+    }
+  }
+}
+
 template <int CAP>
 __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint2* my_buf,
                                              uint32_t* my_gthr, int& cnt, float& thr, int& flagged,
                                              uint32_t nb, int n_left, int k, float e2) {
-  float g[4];
+  constexpr int NG = 32 / FILTER_GS;
+  float g[NG];
 #pragma unroll
-  for (int h = 0; h < 4; ++h) {
-    float m = __uint_as_float(v[8 * h]);
+  for (int h = 0; h < NG; ++h) {
+    float m = __uint_as_float(v[FILTER_GS * h]);
 #pragma unroll
-    for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(v[8 * h + j]));
+    for (int j = 1; j < FILTER_GS; ++j) m = fmaxf(m, __uint_as_float(v[FILTER_GS * h + j]));
     g[h] = m;
   }
-  if (fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])) > thr) {
+  float mall = g[0];
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      if (g[h] > thr) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (__uint_as_float(v[8 * h + j]) > thr && 8 * h + j < n_left)
-            my_buf[cnt++] = make_uint2(v[8 * h + j], nb + 8 * h + j);
-      }
-    }
+  for (int h = 1; h < NG; ++h) mall = fmaxf(mall, g[h]);
+  if (mall > thr) {
+    if (n_left >= 32) filter_groups<CAP, false>(v, g, my_buf, cnt, thr, nb, n_left);
+    else filter_groups<CAP, true>(v, g, my_buf, cnt, thr, nb, n_left);
   }
   const bool need = cnt > CAP - 32;
   if (__any_sync(0xffffffffu, need)) {
