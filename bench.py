@@ -383,8 +383,14 @@ def main():
             ach, peak, unit = work / t / 1e12, peaks["tf_sust"], "TFLOP/s"
         else:
             ach, peak, unit = work / t / 1e9, peaks["hbm"], "GB/s"
+        traffic = None          # DRAM bytes per launch from the committed ncu capture of this workload
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("workload") == args.workload and tj.get("n_gpus") == world:
+                traffic = tj["bytes_per_launch"].get(top)
         roofline = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
-                    "frac": ach / peak, "traffic": None, "peak_source": peaks["source"],
+                    "frac": ach / peak, "traffic": traffic, "peak_source": peaks["source"],
                     "kernel_ms": kern[top], "share_of_step": share[top] / ms,
                     "kernels_ms_per_step": share}
     # whole-job roofline over all GPUs: max(FLOPs / tensor peak, bytes / HBM peak)

@@ -172,6 +172,19 @@ int mclst_merge_topk(const float* values, const int64_t* indices, const float* d
 int mclst_neighbor_weights(const float* distances, const float* values, int64_t n_query, int top_k,
                            int weight_mode, float* out_weights, mclst_stream_t stream);
 
+/* ---------------------------------------------------------------- evaluation metrics ---- */
+
+/* Per-gene statistics of the predicted vs true expression matrices ([n_spots, genes], float32
+ * or float64): mean of the truth (top-50 HEG selection, evel_her2st.py:201-205), Pearson r
+ * (utils.py:52-65 get_R / scipy pearsonr; NaN for a constant column), and the per-gene sums of
+ * squared and absolute errors (sklearn MSE / MAE at evel_her2st.py:214-221 are their totals over
+ * n_spots * genes).  All outputs float64 [genes]; scratch from mclst_gene_metrics_scratch_doubles. */
+int mclst_gene_metrics_scratch_doubles(int genes, size_t* n);
+int mclst_gene_metrics(const void* truth, int64_t ld_true, int true_is_f64, const void* pred,
+                       int64_t ld_pred, int pred_is_f64, int64_t n_spots, int genes,
+                       double* mean_true, double* pcc, double* sq_err, double* abs_err,
+                       double* scratch, mclst_stream_t stream);
+
 /* ---------------------------------------------------------------- contrastive loss ------ */
 
 /* Symmetric image<->spot contrastive loss, forward and backward in one call.

@@ -55,6 +55,8 @@ def load() -> C.CDLL:
     lib.mclst_find_matches_workspace_bytes.argtypes = [i64, i64, i32, i32, i32, C.POINTER(sz)]
     lib.mclst_find_matches.argtypes = [p, i64, i64, p, i64, i64, i32, i32, i64, p, p, p, sz, i32, p]
     lib.mclst_debug_similarity.argtypes = [p, i64, i64, p, i64, i64, i32, p, i64, p, sz, p]
+    lib.mclst_gene_metrics_scratch_doubles.argtypes = [i32, C.POINTER(sz)]
+    lib.mclst_gene_metrics.argtypes = [p, i64, i32, p, i64, i32, i64, i32, p, p, p, p, p, p]
     lib.mclst_merge_topk.argtypes = [p, p, p, i32, i64, i32, p, p, p, p]
     lib.mclst_neighbor_weights.argtypes = [p, p, i64, i32, i32, p, p]
     lib.mclst_contrastive_loss_workspace_bytes.argtypes = [i32, i32, i32, i64, C.POINTER(sz)]

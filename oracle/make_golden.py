@@ -308,7 +308,55 @@ def lift_as_function(path, lo, hi):
     return compile(mod, "<%s %d-%d>" % (path, lo, hi), "exec")
 
 
+def golden_metrics():
+    """utils.get_R (utils.py:52-65) imported from the reference and the metric lines of the fold
+    loop (evel_her2st.py:201-221) lifted verbatim; AnnData is replaced by a minimal stand-in with
+    the three members those lines use (.X, .shape, column selection by name)."""
+    sys.path.insert(0, REF)
+    import utils as ref_utils
+    sys.path.pop(0)
+
+    class Ann:                                        # what anndata.AnnData offers to those lines
+        def __init__(self, X, names=None):
+            self.X = np.asarray(X)
+            self.shape = self.X.shape
+            self.var_names = np.array(names if names is not None else [str(i) for i in range(self.X.shape[1])])
+
+        def __getitem__(self, key):
+            _, names = key
+            pos = {n: i for i, n in enumerate(self.var_names)}
+            cols = [pos[n] for n in names]
+            return Ann(self.X[:, cols], list(names))
+
+    out, meta = {}, {}
+    for name, Q, G, seed in (("a", 300, 60, 71), ("b", 57, 130, 72)):
+        true = synth.expression(Q, G, seed).astype(np.float64)
+        rng = np.random.default_rng(seed)
+        pred = 0.6 * true + 0.4 * rng.random((Q, G)) + 0.05 * rng.standard_normal((Q, G))
+        pred[:, 3] = 0.25                                  # constant column -> pearsonr is NaN
+        pred = pred.astype(np.float32).astype(np.float64)    # stored as float32 in the fixture
+        meta[name] = dict(Q=Q, G=G, seed=seed, checksum=checksum(true, pred))
+        code = lift_statements("evel_her2st.py", 201, 221)
+        ns = {"np": np, "get_R": ref_utils.get_R, "adata_ture": Ann(true), "adata_pred": Ann(pred),
+              "true": true, "pred": pred, "heg_pcc_list": [], "hvg_pcc_list": [], "mse_list": [],
+              "mae_list": []}
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            quiet_exec(code, ns)
+        out[f"{name}/heg_pcc"] = np.array(ns["heg_pcc_list"][0])
+        out[f"{name}/hvg_pcc"] = np.array(ns["hvg_pcc_list"][0])
+        out[f"{name}/mse"] = np.array(ns["mse_list"][0])
+        out[f"{name}/mae"] = np.array(ns["mae_list"][0])
+        out[f"{name}/pred"] = pred.astype(np.float32)        # noise is not regenerable from synth alone
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
+    print("metrics.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    golden_retrieval()
-    golden_model()
+    if "--metrics-only" not in sys.argv:
+        golden_retrieval()
+        golden_model()
+    golden_metrics()

@@ -241,6 +241,29 @@ def retrieve_ref(spot_key, expression_key, image_query, top_k, mode="inv_sq_l2")
 
 
 # --------------------------------------------------------------------------
+# downstream metrics
+# --------------------------------------------------------------------------
+
+
+def metrics_ref(true: np.ndarray, pred: np.ndarray, top_genes: int = 50) -> Dict[str, float]:
+    """evel_her2st.py:201-221 with utils.py:52-65 (get_R): per-gene scipy pearsonr, the top-50
+    genes by mean true expression, NaN columns dropped from the HVG mean, sklearn MSE / MAE
+    (plain means over all entries)."""
+    from scipy.stats import pearsonr
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = np.array([pearsonr(pred[:, g], true[:, g])[0] for g in range(true.shape[1])])   # utils.py:56-59
+    gene_mean_expression = np.mean(true, axis=0)                                  # evel_her2st.py:201
+    top = np.argsort(gene_mean_expression)[::-1][:top_genes]                       # :202
+    heg = r[top]                                                                   # :207
+    hvg = r[~np.isnan(r)]                                                          # :209
+    return {"heg_pcc": float(np.mean(heg)), "hvg_pcc": float(np.mean(hvg)),       # :211-212
+            "mse": float(np.mean((true - pred) ** 2)),                             # :216
+            "mae": float(np.mean(np.abs(true - pred))), "pcc": r}                  # :219
+
+
+# --------------------------------------------------------------------------
 # a7 / a8  contrastive losses
 # --------------------------------------------------------------------------
 

@@ -179,3 +179,23 @@ def test_path_forward_backward_is_the_reference(golden_model, case):
         else:
             mine = p.grad.numpy()
         np.testing.assert_allclose(mine, g, rtol=0, atol=1e-4 * np.abs(g).max() + 1e-9, err_msg=k)
+
+
+# ------------------------------------------------------------------ downstream metrics
+@pytest.fixture(scope="session")
+def golden_metrics():
+    from conftest import _load
+    return _load("metrics.npz")
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_metrics_ref_is_the_reference(golden_metrics, name):
+    z, meta = golden_metrics
+    m = meta[name]
+    true = synth.expression(m["Q"], m["G"], m["seed"]).astype(np.float64)
+    pred = z[f"{name}/pred"].astype(np.float64)
+    assert golden_checksum(true, pred) == m["checksum"]
+    got = oracle.metrics_ref(true, pred)
+    for key in ("heg_pcc", "hvg_pcc", "mse", "mae"):
+        np.testing.assert_allclose(got[key], z[f"{name}/{key}"], rtol=1e-12, err_msg=key)
+    assert np.isnan(got["pcc"][3])
