@@ -370,7 +370,7 @@ def main():
     alg = {   # algorithmic work per launch: FLOPs for the similarity kernels, bytes otherwise
         "sim_topk": ("tensor", 2.0 * Q * n_local * D),
         "exact_topk": ("tensor", 2.0 * Q * n_local * D),
-        "weighted_average": ("hbm", Q * k * G * 4.0 + Q * k * D * 4.0 + Q * G * 4.0),
+        "weighted_average": ("hbm", Q * k * G * 4.0 + Q * G * 4.0),   # distances come from the re-rank
         "weighted_gather": ("hbm", Q * k * G * 4.0 / (grid.bank_shards if world > 1 else 1) + Q * G * 4.0),
         "row_norms": ("hbm", (n_local + Q) * D * 4.0),
         "pack_rows": ("hbm", (n_local + Q) * D * 6.0),
