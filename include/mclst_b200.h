@@ -239,6 +239,13 @@ int mclst_softmax_forward(float* scores, int64_t ld, int64_t rows, int cols, mcl
 int mclst_softmax_backward(const float* probs, float* d_probs_to_d_scores, int64_t ld, int64_t rows,
                            int cols, mclst_stream_t stream);
 
+/* Block-diagonal softmax for the eval bank build (evel_her2st.py:24, 47-69: spots are embedded in
+ * consecutive batches of `group`; attention never crosses a batch).  scores [rows, cols] holds
+ * tiles of `cols` consecutive tokens (cols % group == 0); inside a token's own group the softmax
+ * runs over the valid tokens (< n_valid), every other column becomes 0.  In place. */
+int mclst_softmax_blockdiag(float* scores, int64_t ld, int64_t rows, int cols, int group,
+                            int64_t n_valid, mclst_stream_t stream);
+
 /* out[c] = sum_r x[r,c] (bias gradients), deterministic order. */
 int mclst_col_sum(const float* x, int64_t ld, int64_t rows, int cols, float* out, mclst_stream_t stream);
 

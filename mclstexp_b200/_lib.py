@@ -73,6 +73,7 @@ def load() -> C.CDLL:
     lib.mclst_gelu_backward.argtypes = [p, p, p, i64, p]
     lib.mclst_softmax_forward.argtypes = [p, i64, i64, i32, p]
     lib.mclst_softmax_backward.argtypes = [p, p, i64, i64, i32, p]
+    lib.mclst_softmax_blockdiag.argtypes = [p, i64, i64, i32, i32, i64, p]
     lib.mclst_col_sum.argtypes = [p, i64, i64, i32, p, p]
     lib.mclst_matmul_workspace_bytes.argtypes = [i64, i64, i64, i32, C.POINTER(sz)]
     lib.mclst_matmul.argtypes = [p, i64, i32, i64, p, i64, i32, i64, p, i64, i64, i64, i64, i64, i32,

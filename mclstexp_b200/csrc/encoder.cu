@@ -193,6 +193,31 @@ softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dp, int64_t 
   for (int c = threadIdx.x; c < C; c += EN_THREADS) pd[c] = pp[c] * (pd[c] - t);
 }
 
+// Block-diagonal softmax for grouped attention (eval bank build, evel_her2st.py:24,47-69: the bank
+// is embedded in consecutive batches of `group` spots and tokens only attend inside their batch).
+// scores: [rows, cols] tiles of `cols` consecutive tokens (cols % group == 0); row r is token
+// (r / cols) * cols + r % cols.  Inside the token's own group the softmax is taken over the valid
+// tokens (< n_valid); every other column is set to 0 so that P V only mixes the group.
+__global__ void __launch_bounds__(128)
+softmax_blockdiag_kernel(float* __restrict__ s, int64_t ld, int cols, int group, int64_t n_valid) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  float* p = s + r * ld;
+  const int64_t tile0 = (r / cols) * cols;            // first token of this tile
+  const int i = (int)(r - tile0);
+  const int g0 = (i / group) * group;
+  const int g1 = (int)min((int64_t)(g0 + group), n_valid - tile0);   // valid columns of the group
+  float m = -INFINITY;
+  for (int c = g0 + lane; c < g1; c += 32) m = fmaxf(m, p[c]);
+  m = warp_max(m);
+  float t = 0.f;
+  for (int c = g0 + lane; c < g1; c += 32) t += expf(p[c] - m);
+  t = warp_sum(t);
+  const float inv = t > 0.f ? 1.f / t : 0.f;
+  for (int c = lane; c < cols; c += 32)
+    p[c] = (c >= g0 && c < g1) ? expf(p[c] - m) * inv : 0.f;
+}
+
 // ---------------------------------------------------------------- column sums (bias grads)
 __global__ void __launch_bounds__(256)
 col_sum_kernel(const float* __restrict__ x, int64_t ld, int64_t R, int C, float* __restrict__ out) {
@@ -317,6 +342,18 @@ extern "C" int mclst_softmax_backward(const float* probs, float* d_probs_to_d_sc
   if (rows == 0) return 0;
   prof_mark((cudaStream_t)stream, "softmax_bwd");
   softmax_bwd_kernel<<<(unsigned)rows, EN_THREADS, 0, (cudaStream_t)stream>>>(probs, d_probs_to_d_scores, ld, cols);
+  MCLST_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mclst_softmax_blockdiag(float* scores, int64_t ld, int64_t rows, int cols, int group,
+                                       int64_t n_valid, mclst_stream_t stream) {
+  MCLST_REQUIRE(scores, MCLST_ERR_INVALID, "softmax_blockdiag: null");
+  MCLST_REQUIRE(cols >= 1 && group >= 1 && cols % group == 0 && rows % 4 == 0, MCLST_ERR_INVALID,
+                "softmax_blockdiag: cols %d must be a multiple of group %d, rows a multiple of 4", cols, group);
+  if (rows == 0) return 0;
+  prof_mark((cudaStream_t)stream, "softmax_blockdiag");
+  softmax_blockdiag_kernel<<<(unsigned)(rows / 4), 128, 0, (cudaStream_t)stream>>>(scores, ld, cols, group, n_valid);
   MCLST_LAUNCH_CHECK();
   return 0;
 }

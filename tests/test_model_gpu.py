@@ -151,3 +151,29 @@ def test_graphed_train_step_matches_eager():
     bad["position"][0, 0] = 1e6
     with pytest.raises(IndexError):
         step(bad)
+
+
+@pytest.mark.parametrize("N,group", [(200, 32), (128, 32), (31, 32), (1000, 64), (333, 16)])
+def test_embed_bank_equals_per_batch_loop(N, group):
+    """Fused block-diagonal bank build == the reference's loop over un-shuffled batches
+    (evel_her2st.py:24, 47-70), including the short last batch."""
+    from mclstexp_b200.embed import embed_bank
+    m = dict(G=171, E=64, heads=8, dim_head=64, layers=2, B=N, T=1.0, kind="visium", seed=41)
+    net, sd = _build(m)
+    net.eval()
+    feats, expr, pos = _inputs(m)
+    img, spot = embed_bank(net, expr.cuda(), pos.cuda(), feats.cuda(), group=group)
+    want = []
+    with torch.no_grad():
+        for b0 in range(0, N, group):
+            want.append(oracle.spot_embedding_ref(sd, expr[b0:b0 + group], pos[b0:b0 + group],
+                                                  m["heads"], m["layers"]))
+        want = torch.cat(want).numpy()
+        want_img = oracle.projection_head_ref(feats, sd, "image_projection.").numpy()
+    _close(spot, want, "spot_embeddings")
+    _close(img, want_img, "image_embeddings")
+    # and the module-attribute loop of the reference's get_embeddings gives the same
+    with torch.no_grad():
+        loop = torch.cat([net.embed_spots(expr[b0:b0 + group].cuda(), pos[b0:b0 + group].cuda())
+                          for b0 in range(0, N, group)])
+    _close(spot, loop.cpu().numpy(), "fused vs loop", rtol=1e-4)
