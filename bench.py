@@ -251,6 +251,28 @@ def train_step_cfg2(dev):
     return res
 
 
+def bank_build(dev):
+    """fused eval embedding forward (batches of 32 un-shuffled spots, as
+    evel_her2st.py:24,47-70) over 131 072 spots, G = 785 (her2st), vs the per-batch module loop."""
+    from torch import nn
+    from mclstexp_b200 import model as mm
+    from mclstexp_b200.embed import embed_bank
+    N, G = 131072, 785
+    net = mm.mclSTExp_Attention("none", 1.0, 1024, G, 256, 8, 64, 2)
+    net.image_encoder = nn.Identity()
+    net = net.to(dev).eval()
+    g = torch.Generator(device=dev)
+    g.manual_seed(11)
+    expr = torch.rand(N, G, generator=g, device=dev)
+    pos = torch.randint(0, 64, (N, 2), generator=g, device=dev).float()
+    ms = _time_cuda(lambda: embed_bank(net, expr, pos), iters=3, warm=1)
+    with torch.no_grad():
+        ms_loop = _time_cuda(lambda: [net.embed_spots(expr[b:b + 32], pos[b:b + 32]) for b in range(0, 4096, 32)],
+                             iters=2, warm=1) * (N / 4096)
+    return {"spots": N, "genes": G, "fused_ms": ms, "fused_spots_per_s": N / (ms * 1e-3),
+            "per_batch_loop_ms_extrapolated": ms_loop}
+
+
 # --------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -459,6 +481,7 @@ def main():
         extra = {"contrastive_loss_soft_fwd_bwd": loss_sweep(dev, peaks, world, rank, not args.full_loss_sweep)}
         if world == 1:
             extra["train_step_cfg2_B1024"] = train_step_cfg2(dev)
+            extra["bank_build_group32"] = bank_build(dev)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -141,6 +141,7 @@ struct SimParams {
   // every 32-score chunk into seed_out [q_pad][n_tiles * 8] (no candidates, no thresholds)
   float* seed_out;
   int tile_begin, tile_stride, n_tiles;     // used when seed_out != nullptr
+  int prune_gap;        // appended entries between two prunes of a row (<= CAP - 32 - survivors)
 };
 
 // eps: |tensor-core score - exact cosine| for a pair with fp16 residual norms rq, rs
@@ -249,7 +250,8 @@ __device__ __forceinline__ void filter_groups(const uint32_t (&v)[32], const flo
 template <int CAP>
 __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint2* my_buf,
                                              uint32_t* my_gthr, int& cnt, float& thr, int& flagged,
-                                             uint32_t nb, int n_left, int k, float e2) {
+                                             uint32_t nb, int n_left, int k, float e2, int& trigger,
+                                             int gap) {
   constexpr int NG = 32 / FILTER_GS;
   float g[NG];
 #pragma unroll
@@ -266,9 +268,12 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], uint2* my_
     if (n_left >= 32) filter_groups<CAP, false>(v, g, my_buf, cnt, thr, nb, n_left);
     else filter_groups<CAP, true>(v, g, my_buf, cnt, thr, nb, n_left);
   }
-  const bool need = cnt > CAP - 32;
+  // prune when the buffer is full OR `gap` entries arrived since the last prune: every prune
+  // tightens the threshold, and a tight threshold is what keeps the append path rare
+  const bool need = cnt > trigger;
   if (__any_sync(0xffffffffu, need)) {
     const PruneState ps = warp_prune<CAP>(my_buf, my_gthr, cnt, thr, flagged, need, k, e2);
+    if (need) trigger = min(CAP - 32, max(ps.cnt + gap, k + 16));
     cnt = ps.cnt; thr = ps.thr; flagged = ps.flagged;
   }
 }
@@ -401,6 +406,8 @@ sim_topk_kernel(const SimParams p) {
     int cnt = 0;
     int flagged = 0;
     const int k = p.k;
+    const int gap = p.prune_gap;
+    int trigger = min(CAP - 32, max(k + 16, gap + k));
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + part * PART_COLS;
     int it = 0;
 #pragma unroll 1
@@ -450,7 +457,7 @@ sim_topk_kernel(const SimParams p) {
         }
         if (p.ablate == 0)
           filter_chunk<CAP>(va, my_buf, my_gthr, cnt, thr, flagged, (uint32_t)(col_base + c * 32),
-                            n_valid - c * 32, k, e2);
+                            n_valid - c * 32, k, e2, trigger, gap);
         else if ((va[0] ^ va[13] ^ va[31]) == 0x12345678u) cnt++;
         tmem_ld_wait();
         if (c + 2 < NCH) {
@@ -468,7 +475,7 @@ sim_topk_kernel(const SimParams p) {
         }
         if (p.ablate == 0)
           filter_chunk<CAP>(vb, my_buf, my_gthr, cnt, thr, flagged,
-                            (uint32_t)(col_base + (c + 1) * 32), n_valid - (c + 1) * 32, k, e2);
+                            (uint32_t)(col_base + (c + 1) * 32), n_valid - (c + 1) * 32, k, e2, trigger, gap);
         else if ((vb[0] ^ vb[13] ^ vb[31]) == 0x12345678u) cnt++;
       }
     }
@@ -1168,6 +1175,8 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
   p.gthr = w.gthr; p.dump = dump; p.dump_ld = dump_ld;
   p.ablate = sim_topk_ablate();
   p.seed_out = nullptr; p.tile_begin = 0; p.tile_stride = 1; p.n_tiles = 0;
+  static const int gap_env = env_int("MCLST_SIM_PRUNE_GAP", 1 << 20);
+  p.prune_gap = gap_env;
   static const int keep_gthr = env_int("MCLST_SIM_KEEP_GTHR", 0);   // experiment: warm thresholds
   if (!keep_gthr) MCLST_CUDA(cudaMemsetAsync(w.gthr, 0, (size_t)w.q_pad * sizeof(uint32_t), st));
   dim3 grid((unsigned)(w.q_pad / 128), (unsigned)w.S);
