@@ -18,6 +18,7 @@
 // embeddings, probabilities and gradients thereof (|x| << 1e4); pack_split saturates and
 // flags anything larger so the caller can fail loudly instead of returning inf.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "gemm.cuh"
 #include "umma.cuh"
@@ -125,21 +126,28 @@ int launch_pack_split(const float* x, int64_t rows, int64_t cols, int64_t ld, bo
 }
 
 // ============================================================================ gemm_tn
-constexpr int GM_THREADS = 192;
+constexpr int GM_EPI_WARPS = 8;                              // two per TMEM lane quadrant, 4 column chunks each
+constexpr int GM_THREADS = 64 + 32 * GM_EPI_WARPS;
 constexpr int GM_BM = 128, GM_BN = 256;
 constexpr int GM_STAGES = 4;
 constexpr int GM_STAGE_BYTES = 3 * TP_SLICE_BYTES;     // A slice (128 rows) + B slice (256 rows)
-constexpr int GM_SMEM = GM_STAGES * GM_STAGE_BYTES + 1024 + 1024;
+constexpr int GM_EPI_BYTES = GM_EPI_WARPS * 32 * 32 * 4;                // one 32x32 fp32 transpose tile per epilogue warp
+constexpr int GM_SMEM = GM_STAGES * GM_STAGE_BYTES + 1024 + GM_EPI_BYTES + 1024;
 
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-// Persistent: grid = min(tiles, SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ... with the
-// same three roles as sim_topk (TMA producer / single-thread MMA issuer / 4 epilogue warps) and a
-// double-buffered 2 x 256-column TMEM accumulator, so the epilogue of tile i (TMEM -> registers ->
-// 128 KiB of global stores) overlaps the MMAs of tile i+1.  Tile order keeps the B operand tile
-// fixed across consecutive CTAs (L2 reuse).
+// Persistent: every CTA walks output tiles with the same three roles as sim_topk (TMA producer /
+// single-thread MMA issuer / 8 epilogue warps) and a double-buffered 2 x 256-column TMEM
+// accumulator, so the epilogue of tile i (TMEM -> registers -> 128 KiB of global stores) overlaps
+// the MMAs of tile i+1.
+// CL = 2: the two CTAs of a cluster take vertically adjacent 128-row tiles of the same 256-column
+// strip; each fetches half of every B slice and multicasts it to both.  With both operands
+// streamed a 128x256 tile needs 87 FLOP per byte from L2 (16 TB/s at full tensor rate, more than
+// L2 delivers: the CL = 1 kernel measured ~500 TFLOP/s on the loss products); sharing B cuts the
+// traffic per CTA from 48 to 32 KiB per K block.
+template <int CL>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_tn_kernel(const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -153,24 +161,31 @@ gemm_tn_kernel(const GemmParams p) {
   const int nkb = p.nkb;
   const int iters = p.nseg * nkb;
   const int mt = (int)((p.M + GM_BM - 1) / GM_BM), nt = (int)((p.N + GM_BN - 1) / GM_BN);
-  const int64_t tiles = (int64_t)mt * nt * p.batch;
+  const int mg = (mt + CL - 1) / CL;                     // groups of CL vertically adjacent tiles
+  const int64_t groups = (int64_t)mg * nt * p.batch;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  const int64_t g0 = blockIdx.x / CL, gstep = gridDim.x / CL;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < GM_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
+    for (int i = 0; i < GM_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], CL); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], GM_EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
+      const uint64_t pol = policy_evict_last();
       uint32_t stage = 0, phase = 0;
-      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int mb = (int)(tile % mt), nb = (int)((tile / mt) % nt), z = (int)(tile / ((int64_t)mt * nt));
+      for (int64_t g = g0; g < groups; g += gstep) {
+        const int mb = min((int)(g % mg) * CL + (int)crank, mt - 1);     // ghost tiles re-read the last block
+        const int nb = (int)((g / mg) % nt), z = (int)(g / ((int64_t)mg * nt));
         const uint8_t* a_hi = p.a_hi + (size_t)z * p.a_batch_bytes;
         const uint8_t* a_lo = p.a_lo ? p.a_lo + (size_t)z * p.a_batch_bytes : nullptr;
         const uint8_t* b_hi = p.b_hi + (size_t)z * p.b_batch_bytes;
@@ -184,10 +199,17 @@ gemm_tn_kernel(const GemmParams p) {
           mbar_arrive_expect_tx(&bar_full[stage], GM_STAGE_BYTES);
           uint8_t* dst = smem + stage * GM_STAGE_BYTES;
           bulk_g2s(dst, a + ((size_t)mb * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES, &bar_full[stage]);
-          bulk_g2s(dst + TP_SLICE_BYTES, b + ((size_t)(2 * nb) * nkb + kb) * TP_SLICE_BYTES,
-                   TP_SLICE_BYTES, &bar_full[stage]);
-          bulk_g2s(dst + 2 * TP_SLICE_BYTES, b + ((size_t)(2 * nb + 1) * nkb + kb) * TP_SLICE_BYTES,
-                   TP_SLICE_BYTES, &bar_full[stage]);
+          if (CL == 1) {
+            bulk_g2s(dst + TP_SLICE_BYTES, b + ((size_t)(2 * nb) * nkb + kb) * TP_SLICE_BYTES,
+                     TP_SLICE_BYTES, &bar_full[stage]);
+            bulk_g2s(dst + 2 * TP_SLICE_BYTES, b + ((size_t)(2 * nb + 1) * nkb + kb) * TP_SLICE_BYTES,
+                     TP_SLICE_BYTES, &bar_full[stage]);
+          } else {
+            // this CTA fetches row block 2 nb + crank of B and multicasts it to the pair
+            bulk_g2s_mcast(dst + (1 + crank) * TP_SLICE_BYTES,
+                           b + ((size_t)(2 * nb + crank) * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES,
+                           &bar_full[stage], kMask, pol);
+          }
           if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -197,7 +219,7 @@ gemm_tn_kernel(const GemmParams p) {
       constexpr uint32_t idesc = make_idesc_f16(GM_BM, GM_BN, false);
       uint32_t stage = 0, phase = 0;
       int n = 0;
-      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n) {
+      for (int64_t g = g0; g < groups; g += gstep, ++n) {
         const int buf = n & 1;
         mbar_wait(&bar_tempty[buf], ((n >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -211,7 +233,8 @@ gemm_tn_kernel(const GemmParams p) {
           for (int k4 = 0; k4 < 4; ++k4)
             mma_f16_ss(d_tmem, make_smem_desc_sw128(a_addr + k4 * 32),
                        make_smem_desc_sw128(b_addr + k4 * 32), idesc, (it | k4) != 0 ? 1u : 0u);
-          mma_commit(&bar_empty[stage]);
+          if (CL == 1) mma_commit(&bar_empty[stage]);
+          else mma_commit_mcast(&bar_empty[stage], kMask);
           if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
         }
         mma_commit(&bar_tfull[buf]);
@@ -219,52 +242,74 @@ gemm_tn_kernel(const GemmParams p) {
     }
   } else {
     // ------------------------------------------------------------ epilogue
+    // tcgen05.ld hands every thread one ROW of the chunk; storing that directly makes each warp
+    // store touch 32 different 128-byte lines (measured: 1.3 TB/s on the 4 GiB loss products).
+    // Each warp therefore transposes its 32x32 chunk through an XOR-swizzled shared tile and
+    // stores 4 full 128-byte row segments per instruction.
     const int quad = warp & 3;
+    const int chalf = (warp - 2) >> 2;                     // which half of the 8 column chunks
+    float4* tile = reinterpret_cast<float4*>(smem + GM_STAGES * GM_STAGE_BYTES + 1024) + (warp - 2) * 256;
     const bool vec_ok = (p.ldc % 4 == 0) && ((uintptr_t)p.c % 16 == 0) && (p.c_batch_elems % 4 == 0) &&
                         (!p.residual || (uintptr_t)p.residual % 16 == 0);
+    const int sub = lane >> 3, c4 = lane & 7;              // store phase: row it*4+sub, columns c4*4..+3
     int n = 0;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n) {
-      const int mb = (int)(tile % mt), nb = (int)((tile / mt) % nt), z = (int)(tile / ((int64_t)mt * nt));
+    for (int64_t g = g0; g < groups; g += gstep, ++n) {
+      const int mb = (int)(g % mg) * CL + (int)crank;
+      const int nb = (int)((g / mg) % nt), z = (int)(g / ((int64_t)mg * nt));
       const int buf = n & 1;
-      const int64_t m = (int64_t)mb * GM_BM + quad * 32 + lane;
-      const bool m_ok = m < p.M;
-      float* crow = p.c + (size_t)z * p.c_batch_elems + m * p.ldc;
-      const float* rrow = p.residual ? p.residual + (size_t)z * p.c_batch_elems + m * p.ldc : nullptr;
+      const int64_t m0 = (int64_t)mb * GM_BM + quad * 32;
+      float* cbase = p.c + (size_t)z * p.c_batch_elems;
+      const float* rbase = p.residual ? p.residual + (size_t)z * p.c_batch_elems : nullptr;
       mbar_wait(&bar_tfull[buf], (n >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * GM_BN;
       const int64_t n0 = (int64_t)nb * GM_BN;
 #pragma unroll 1
-      for (int c = 0; c < GM_BN / 32; ++c) {
-        if (n0 + c * 32 >= p.N) break;             // uniform
+      for (int c = chalf * 4; c < chalf * 4 + 4; ++c) {
+        if (n0 + c * 32 >= p.N || mb >= mt || m0 >= p.M) break;             // uniform
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
-        if (!m_ok) continue;
-        const int64_t nbase = n0 + c * 32;
-        float o[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]) * p.alpha;
-          if (p.bias && nbase + j < p.N) x += __ldg(p.bias + nbase + j);
-          if (p.act == 1) x = gelu_erf(x);
-          o[j] = x;
+        for (int j = 0; j < 8; ++j)
+          tile[lane * 8 + (j ^ (lane & 7))] =
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        const int64_t col = n0 + c * 32 + c4 * 4;
+        const bool full4 = vec_ok && col + 4 <= p.N;
+        float bias[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (col + i < p.N) bias[i] = __ldg(p.bias + col + i);
         }
-        if (vec_ok && nbase + 32 <= p.N) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 w = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-            if (rrow) {
-              const float4 rr = *reinterpret_cast<const float4*>(rrow + nbase + j);
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + sub;
+          const float4 t = tile[row * 8 + (c4 ^ (row & 7))];
+          const int64_t m = m0 + row;
+          if (m >= p.M) continue;
+          float o[4] = {t.x * p.alpha + bias[0], t.y * p.alpha + bias[1], t.z * p.alpha + bias[2],
+                        t.w * p.alpha + bias[3]};
+          if (p.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = gelu_erf(o[i]);
+          }
+          float* crow = cbase + m * p.ldc + col;
+          if (full4) {
+            float4 w = make_float4(o[0], o[1], o[2], o[3]);
+            if (rbase) {
+              const float4 rr = *reinterpret_cast<const float4*>(rbase + m * p.ldc + col);
               w.x += rr.x; w.y += rr.y; w.z += rr.z; w.w += rr.w;
             }
-            *reinterpret_cast<float4*>(crow + nbase + j) = w;
-          }
-        } else {
+            *reinterpret_cast<float4*>(crow) = w;
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nbase + j < p.N) crow[nbase + j] = o[j] + (rrow ? rrow[nbase + j] : 0.f);
+            for (int i = 0; i < 4; ++i)
+              if (col + i < p.N) crow[i] = o[i] + (rbase ? rbase[m * p.ldc + col + i] : 0.f);
+          }
         }
+        __syncwarp();
       }
       // accumulator drained: hand the buffer back to the MMA warp
       tc_fence_before();
@@ -274,25 +319,48 @@ gemm_tn_kernel(const GemmParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int CL>
+static int launch_gemm_cl(const GemmParams& q, cudaStream_t st) {
+  auto kern = gemm_tn_kernel<CL>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MCLST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
+    attr_set = true;
+  }
+  const int64_t mt = ceil_div(q.M, GM_BM), nt = ceil_div(q.N, GM_BN);
+  const int64_t groups = ceil_div(mt, CL) * nt * q.batch;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(CL * std::min<int64_t>(groups, sm_count() / CL)));
+  cfg.blockDim = dim3(GM_THREADS);
+  cfg.dynamicSmemBytes = GM_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MCLST_CUDA(cudaLaunchKernelEx(&cfg, kern, q));
+  MCLST_LAUNCH_CHECK();
+  return 0;
 }
 
 int launch_gemm_tn(const GemmParams& p, cudaStream_t st) {
   MCLST_REQUIRE(p.M > 0 && p.N > 0 && p.nkb > 0 && (p.nseg == 1 || p.nseg == 3), MCLST_ERR_INVALID,
                 "gemm: bad shape M=%lld N=%lld nkb=%d nseg=%d", (long long)p.M, (long long)p.N, p.nkb, p.nseg);
   MCLST_REQUIRE(p.nseg == 1 || (p.a_lo && p.b_lo), MCLST_ERR_INVALID, "gemm: split needs lo parts");
-  static bool attr_set = false;
-  if (!attr_set) {
-    MCLST_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
-    attr_set = true;
-  }
   GemmParams q = p;
   q.batch = std::max(1, p.batch);
+  static const int force = [] { const char* e = getenv("MCLST_GEMM_CLUSTER"); return e ? atoi(e) : 0; }();
   const int64_t tiles = ceil_div(p.M, GM_BM) * ceil_div(p.N, GM_BN) * q.batch;
-  const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
-  gemm_tn_kernel<<<grid, GM_THREADS, GM_SMEM, st>>>(q);
-  MCLST_LAUNCH_CHECK();
-  return 0;
+  // pairs pay off once the grid is saturated and there are at least two row tiles to pair
+  const bool pair = force == 2 || (force == 0 && p.M > GM_BM && tiles >= 2 * (int64_t)sm_count());
+  return pair ? launch_gemm_cl<2>(q, st) : launch_gemm_cl<1>(q, st);
 }
 
 // ---- operand bookkeeping --------------------------------------------------------------

@@ -53,12 +53,21 @@ row_lse_kernel(const float* __restrict__ P, int64_t ld, int ncols, int64_t row0,
   __shared__ float sh[LS_THREADS / 32];
   const int64_t r = blockIdx.x;
   const float* p = P + r * ld;
-  float m = -INFINITY;
-  for (int j = threadIdx.x; j < ncols; j += LS_THREADS) m = fmaxf(m, p[j]);
-  m = block_max(m, sh);
-  float s = 0.f;
-  for (int j = threadIdx.x; j < ncols; j += LS_THREADS) s += expf(p[j] - m);
-  s = block_sum(s, sh);
+  // one pass: running (max, sum) pairs per thread, 16-byte loads over the 4-aligned body
+  float m = -INFINITY, s = 0.f;
+  auto push = [&](float x) {
+    if (x > m) { s = s * expf(m - x) + 1.f; m = x; }
+    else s += expf(x - m);
+  };
+  const int n4 = ((ld & 3) == 0) ? (ncols >> 2) : 0;
+  for (int j = threadIdx.x; j < n4; j += LS_THREADS) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p) + j);
+    push(v.x); push(v.y); push(v.z); push(v.w);
+  }
+  for (int j = n4 * 4 + threadIdx.x; j < ncols; j += LS_THREADS) push(p[j]);
+  const float mb = block_max(m, sh);
+  s = block_sum(m == -INFINITY ? 0.f : s * expf(m - mb), sh);
+  m = mb;
   if (threadIdx.x == 0) {
     lse[row0 + r] = m + logf(s);
     if (diag) diag[row0 + r] = p[row0 + r];
@@ -76,11 +85,17 @@ soft_pass2_kernel(const float* __restrict__ P1, const float* __restrict__ P3, in
   const float* p3 = P3 + r * ld;
   const float rl_r = rl[rg], za_r = za[rg];
   float w = 0.f, c = 0.f;
-  for (int j = threadIdx.x; j < ncols; j += LS_THREADS) {
-    const float a = p3[j];
-    w += expf(a - za_r) * (rl_r + cl[j] - 2.f * p1[j]);
-    c += expf(a - za[j]);
+  auto push = [&](float a, float p1j, int j) {
+    w += expf(a - za_r) * (rl_r + __ldg(cl + j) - 2.f * p1j);
+    c += expf(a - __ldg(za + j));
+  };
+  const int n4 = ((ld & 3) == 0) ? (ncols >> 2) : 0;
+  for (int j = threadIdx.x; j < n4; j += LS_THREADS) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p3) + j);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p1) + j);
+    push(a.x, b.x, 4 * j); push(a.y, b.y, 4 * j + 1); push(a.z, b.z, 4 * j + 2); push(a.w, b.w, 4 * j + 3);
   }
+  for (int j = n4 * 4 + threadIdx.x; j < ncols; j += LS_THREADS) push(p3[j], p1[j], j);
   w = block_sum(w, sh);
   c = block_sum(c, sh);
   if (threadIdx.x == 0) { wbar[rg] = w; cs[rg] = c; }
@@ -131,54 +146,80 @@ __device__ __forceinline__ void store_split(uint8_t* hi, uint8_t* lo, size_t off
 }
 
 // Gradient factors of one row block, written as split TilePack operands.  One thread per
-// (row, 8-column chunk).  Gradients of magnitude ~1/B are scaled by 2B before the fp16 split
-// (keeps them in fp16's normal range); the GEMM alpha undoes it.
+// (group of GF_ROWS rows, 8-column chunk): the five per-column statistics of its chunk stay in
+// registers while it walks the rows (loading them per element made the kernel LSU-bound: 40 scalar
+// loads per 8 elements next to 6 vector loads of data).  Gradients of magnitude ~1/B are scaled
+// by 2B before the fp16 split (keeps them in fp16's normal range); the GEMM alpha undoes it.
+constexpr int GF_ROWS = 8;
 __global__ void __launch_bounds__(256)
 grad_factor_kernel(const GradParams p, int64_t rows_pad) {
   const int chunks = p.nkb_half * 8;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t r = t / chunks;
-  const int c = (int)(t - r * chunks);
-  if (r >= rows_pad) return;
-  float g1[8], g2[8], gs[8];
+  const int64_t rgp = t / chunks;
+  const int c = (int)(t - rgp * chunks);
+  if (rgp * GF_ROWS >= rows_pad) return;
+  float rl_j[8], cl_j[8], za_j[8], wb_j[8], cs_j[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { g1[i] = 0.f; g2[i] = 0.f; gs[i] = 0.f; }
-  if (r < p.rows) {
-    const int64_t rg = p.row0 + r;
-    const float rl_r = p.rl[rg], cl_r = p.cl[rg];
-    const float za_r = p.soft ? p.za[rg] : 0.f, wb_r = p.soft ? p.wbar[rg] : 0.f;
-    const float cs_r = p.soft ? p.cs[rg] : 1.f;
+  for (int i = 0; i < 8; ++i) {
+    const int j = c * 8 + i;
+    const bool ok = j < p.B;
+    rl_j[i] = ok ? __ldg(p.rl + j) : 0.f;
+    cl_j[i] = ok ? __ldg(p.cl + j) : 0.f;
+    za_j[i] = (ok && p.soft) ? __ldg(p.za + j) : 0.f;
+    wb_j[i] = (ok && p.soft) ? __ldg(p.wbar + j) : 0.f;
+    cs_j[i] = (ok && p.soft) ? __ldg(p.cs + j) : 1.f;
+  }
+#pragma unroll 1
+  for (int rr = 0; rr < GF_ROWS; ++rr) {
+    const int64_t r = rgp * GF_ROWS + rr;
+    float g1[8], g2[8], gs[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int j = c * 8 + i;
-      if (j < p.B) {
-        const float p1 = p.P1[r * p.ld + j], p2 = p.P2[r * p.ld + j];
-        const float rl_j = p.rl[j], cl_j = p.cl[j];
-        float pt_rj, pt_jr, cs_j;
-        if (p.soft) {
-          const float a = p.P3[r * p.ld + j];
-          pt_rj = expf(a - za_r);
-          pt_jr = expf(a - p.za[j]);
-          cs_j = p.cs[j];
-          const float da_rj = pt_rj * (rl_r + cl_j - 2.f * p1 - wb_r);
-          const float da_jr = pt_jr * (rl_j + cl_r - 2.f * p2 - p.wbar[j]);
-          gs[i] = (da_rj + da_jr) * p.a_scale;
-        } else {
-          pt_rj = pt_jr = (rg == j) ? 1.f : 0.f;
-          cs_j = 1.f;
+    for (int i = 0; i < 8; ++i) { g1[i] = 0.f; g2[i] = 0.f; gs[i] = 0.f; }
+    if (r < p.rows) {
+      const int64_t rg = p.row0 + r;
+      const float rl_r = __ldg(p.rl + rg), cl_r = __ldg(p.cl + rg);
+      const float za_r = p.soft ? __ldg(p.za + rg) : 0.f, wb_r = p.soft ? __ldg(p.wbar + rg) : 0.f;
+      const float cs_r = p.soft ? __ldg(p.cs + rg) : 1.f;
+      // the product rows are B64 wide: two 16-byte loads per array are always in bounds
+      float p1v[8], p2v[8], p3v[8];
+      const size_t o = (size_t)r * p.ld + (size_t)c * 8;
+      *reinterpret_cast<float4*>(p1v) = __ldg(reinterpret_cast<const float4*>(p.P1 + o));
+      *reinterpret_cast<float4*>(p1v + 4) = __ldg(reinterpret_cast<const float4*>(p.P1 + o) + 1);
+      *reinterpret_cast<float4*>(p2v) = __ldg(reinterpret_cast<const float4*>(p.P2 + o));
+      *reinterpret_cast<float4*>(p2v + 4) = __ldg(reinterpret_cast<const float4*>(p.P2 + o) + 1);
+      if (p.soft) {
+        *reinterpret_cast<float4*>(p3v) = __ldg(reinterpret_cast<const float4*>(p.P3 + o));
+        *reinterpret_cast<float4*>(p3v + 4) = __ldg(reinterpret_cast<const float4*>(p.P3 + o) + 1);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = c * 8 + i;
+        if (j < p.B) {
+          const float p1 = p1v[i], p2 = p2v[i];
+          float pt_rj, pt_jr;
+          if (p.soft) {
+            const float a = p3v[i];
+            pt_rj = expf(a - za_r);
+            pt_jr = expf(a - za_j[i]);
+            const float da_rj = pt_rj * (rl_r + cl_j[i] - 2.f * p1 - wb_r);
+            const float da_jr = pt_jr * (rl_j[i] + cl_r - 2.f * p2 - wb_j[i]);
+            gs[i] = (da_rj + da_jr) * p.a_scale;
+          } else {
+            pt_rj = pt_jr = (rg == j) ? 1.f : 0.f;
+          }
+          g1[i] = (expf(p1 - rl_r) + cs_j[i] * expf(p1 - cl_j[i]) - 2.f * pt_rj) * p.inv_t;   // 2B * dLg_rj / T
+          g2[i] = (expf(p2 - rl_j[i]) + cs_r * expf(p2 - cl_r) - 2.f * pt_jr) * p.inv_t;      // 2B * dLg_jr / T
         }
-        g1[i] = (expf(p1 - rl_r) + cs_j * expf(p1 - cl_j) - 2.f * pt_rj) * p.inv_t;   // 2B * dLg_rj / T
-        g2[i] = (expf(p2 - rl_j) + cs_r * expf(p2 - cl_r) - 2.f * pt_jr) * p.inv_t;   // 2B * dLg_jr / T
       }
     }
-  }
-  const size_t off = tilepack_chunk_offset(r, c, p.nkb_total);
-  store_split(p.ga_hi, p.ga_lo, off, g1);
-  store_split(p.gb_hi, p.gb_lo, off, g2);
-  if (p.soft) {
-    const size_t off2 = tilepack_chunk_offset(r, p.nkb_half * 8 + c, p.nkb_total);
-    store_split(p.ga_hi, p.ga_lo, off2, gs);
-    store_split(p.gb_hi, p.gb_lo, off2, gs);
+    const size_t off = tilepack_chunk_offset(r, c, p.nkb_total);
+    store_split(p.ga_hi, p.ga_lo, off, g1);
+    store_split(p.gb_hi, p.gb_lo, off, g2);
+    if (p.soft) {
+      const size_t off2 = tilepack_chunk_offset(r, p.nkb_half * 8 + c, p.nkb_total);
+      store_split(p.ga_hi, p.ga_lo, off2, gs);
+      store_split(p.gb_hi, p.gb_lo, off2, gs);
+    }
   }
 }
 
@@ -349,7 +390,7 @@ static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_em
         gp.ga_hi = L.GA.hi; gp.ga_lo = L.GA.lo; gp.gb_hi = L.GB.hi; gp.gb_lo = L.GB.lo;
         gp.nkb_total = L.GA.nkb; gp.nkb_half = (int)(L.B64 / 64);
         const int64_t rows_pad = (int64_t)align_up((size_t)nr, 128);
-        const int64_t threads = rows_pad * gp.nkb_half * 8;
+        const int64_t threads = rows_pad / GF_ROWS * gp.nkb_half * 8;
         grad_factor_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, st>>>(gp, rows_pad);
         MCLST_LAUNCH_CHECK();
         GemmParams g{};
