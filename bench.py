@@ -441,15 +441,16 @@ def main():
                 idx, emb, ex = retrieval.retrieve(hb, he, hq, top_k=k, mode=args.mode, want_emb=False,
                                                   out_dtype=torch.float32)
                 return idx, ex
-            sh = mdist.BankShard(hb.to(dev, non_blocking=True), he.to(dev, non_blocking=True), off, ntot)
+            sh = mdist.BankShard.from_host(hb, he, off, ntot, dev)
             idx, val, _, ex = mdist.retrieve_sharded(sh, hq.to(dev, non_blocking=True), k, args.mode,
                                                      group=grid.group)
             if grid.b_index == 0:            # one rank of every query group reads its slice back
-                return idx.cpu().numpy(), ex.cpu().numpy()
+                return retrieval.to_host(idx, ex)
             torch.cuda.synchronize()
             return None
 
-        e2e_step()
+        r = e2e_step()
+        r = e2e_step()                       # twice: both alternating pinned result buffers exist
         n_e2e = max(1, min(args.steps, 3))
         barrier()
         t0 = time.perf_counter()
@@ -461,7 +462,21 @@ def main():
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": Q / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+        resident = None
+        if world == 1:
+            # serving form: the bank stays on the device, only the queries travel per call
+            bank_obj = retrieval.Bank(hb, he)
+            r = bank_obj.retrieve(hq, top_k=k, mode=args.mode, want_emb=False, out_dtype=torch.float32)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                r = bank_obj.retrieve(hq, top_k=k, mode=args.mode, want_emb=False, out_dtype=torch.float32)
+            dtr = (time.perf_counter() - t0) / n_e2e
+            resident = {"value": Q / dtr, "unit": UNIT, "ms_per_step": dtr * 1e3,
+                        "h2d_bytes_per_step": int(Q * D * 4), "d2h_bytes_per_step": int(Q * k * 8 + Q * G * 4),
+                        "api": "mclstexp_b200.retrieval.Bank(...).retrieve(host queries) -> host arrays"}
+            del bank_obj
+        e2e = {"value": Q / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "resident_bank": resident,
                "h2d_bytes_per_step": int((N * (D + G) * (grid.query_groups if world > 1 else 1) + Q * D *
                                           (grid.bank_shards if world > 1 else 1)) * 4),
                "d2h_bytes_per_step": int(Q * k * 8 + Q * G * 4),

@@ -46,12 +46,29 @@ class BankShard:
     expression_key: torch.Tensor    # [n_local, G] float32 / float64
     index_offset: int               # global index of local row 0
     n_total: int
+    expr_ready: Optional["torch.cuda.Event"] = None   # set when expression_key is still uploading
 
     @classmethod
     def from_full(cls, spot_key, expression_key, rank: int, world: int) -> "BankShard":
         lo, hi = shard_bounds(spot_key.shape[0], world)[rank]
         return cls(spot_key[lo:hi].contiguous(), expression_key[lo:hi].contiguous(), lo,
                    spot_key.shape[0])
+
+    @classmethod
+    def from_host(cls, spot_key: torch.Tensor, expression_key: torch.Tensor, index_offset: int,
+                  n_total: int, device) -> "BankShard":
+        """Upload one shard from (pinned) host tensors.  The expression rows -- most of the bytes,
+        not needed before the average -- go on a side stream so that the copy runs underneath the
+        shard's top-k kernels; ``retrieve_sharded`` waits for ``expr_ready``."""
+        from .retrieval import _side_stream
+        device = torch.device(device)
+        sk = spot_key.to(device, non_blocking=True)
+        side = _side_stream(device)
+        with torch.cuda.stream(side):
+            ek = expression_key.to(device, non_blocking=True)
+            ready = side.record_event()
+        ek.record_stream(torch.cuda.current_stream(device))
+        return cls(sk, ek, index_offset, n_total, ready)
 
 
 class CudaBackend:
@@ -130,6 +147,8 @@ def retrieve_sharded(shard: BankShard, query: torch.Tensor, top_k: int = 50, mod
         dsts = _all_gather_stack(dst, group) if need_dist else None
         val, idx, dst = backend.merge(vals, idxs, dsts, top_k)
     w = backend.weights(dst, val, mode)
+    if shard.expr_ready is not None:
+        torch.cuda.current_stream(shard.expression_key.device).wait_event(shard.expr_ready)
     expr = backend.partial_average(shard.expression_key, shard.index_offset, idx, w)
     emb = backend.partial_average(shard.spot_key, shard.index_offset, idx, w) if want_emb else None
     if world > 1:

@@ -24,9 +24,35 @@ from ._lib import WEIGHT_MODES, check, load, ptr, require_cuda, stream_ptr
 ArrayLike = Union[np.ndarray, torch.Tensor]
 
 __all__ = ["find_matches", "find_matches_cscc", "find_matches_device", "weighted_topk_average",
-           "weighted_topk_average_device", "retrieve", "retrieve_device", "last_counters"]
+           "weighted_topk_average_device", "retrieve", "retrieve_device", "last_counters", "to_host", "Bank"]
 
 _last_ws: Optional[torch.Tensor] = None
+_side_streams: dict = {}
+_PIN_MIN_BYTES = 1 << 20
+
+
+def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """One extra stream per device for the uploads that can run under the top-k kernels."""
+    key = (dev.type, dev.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
+
+
+def to_host(*tensors: Optional[torch.Tensor]):
+    """Results to NumPy with ONE synchronisation; anything of a megabyte or more lands in a pinned
+    buffer from torch's caching host allocator (PCIe rate instead of the pageable staging rate).
+    The returned arrays own those buffers."""
+    outs = []
+    for t in tensors:
+        if t is None:
+            outs.append(None)
+            continue
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=t.numel() * t.element_size() >= _PIN_MIN_BYTES)
+        h.copy_(t, non_blocking=True)
+        outs.append(h)
+    torch.cuda.current_stream().synchronize()
+    return [None if h is None else h.numpy() for h in outs]
 
 
 def _dev_f32(x: ArrayLike, device=None) -> torch.Tensor:
@@ -101,11 +127,11 @@ def find_matches(spot_embeddings: ArrayLike, query_embeddings: ArrayLike, top_k:
     bank = _dev_f32(spot_embeddings)
     qry = _dev_f32(query_embeddings, bank.device)
     val, idx = find_matches_device(bank, qry, top_k, exact_only=exact_only, need_values=return_values)
-    idx_np = idx.cpu().numpy()
+    with torch.cuda.device(idx.device):
+        idx_np, val_np = to_host(idx, val if return_values else None)
     if idx_np.shape[0] == 1:
         idx_np = idx_np[0]
     if return_values:
-        val_np = val.cpu().numpy()
         if val_np.shape[0] == 1:
             val_np = val_np[0]
         return val_np, idx_np
@@ -173,7 +199,9 @@ def weighted_topk_average(spot_key: ArrayLike, expression_key: ArrayLike, image_
     if values is not None:
         val = _dev_f32(values, sk.device)
     emb, expr = weighted_topk_average_device(sk, ek, iq, idx, mode, val)
-    return emb.cpu().numpy(), expr.cpu().numpy()
+    with torch.cuda.device(sk.device):
+        emb_np, expr_np = to_host(emb, expr)
+    return emb_np, expr_np
 
 
 def retrieve_device(spot_key: torch.Tensor, expression_key: torch.Tensor, image_query: torch.Tensor,
@@ -212,13 +240,49 @@ def retrieve(spot_key: ArrayLike, expression_key: ArrayLike, image_query: ArrayL
     if not torch.cuda.is_available():
         raise _lib.MclstError("no CUDA device: retrieve has no CPU fallback")
     dev = torch.device("cuda", torch.cuda.current_device())
+    cur = torch.cuda.current_stream(dev)
     sk = _to_dev(spot_key, dev)
     iq = _to_dev(image_query, dev)
-    ek = _to_dev(expression_key, dev, (torch.float32, torch.float64))
     if iq.dim() == 1:
         iq = iq[None]
-    idx, val, emb, expr = retrieve_device(sk, ek, iq, top_k, mode, want_emb=want_emb, out_dtype=out_dtype)
-    return idx.cpu().numpy(), (emb.cpu().numpy() if emb is not None else None), expr.cpu().numpy()
+    need_dist = mode in ("inv_sq_l1", "inv_sq_l2", "bleep_exp")
+    r = find_matches_device(sk, iq, top_k, dist_p=(1 if mode == "inv_sq_l1" else 2) if need_dist else None)
+    val, idx, dst = (r[0], r[1], r[2]) if need_dist else (r[0], r[1], None)
+    # the expression rows (the bulk of the bytes) are not needed until the average: they are
+    # uploaded on a side stream, underneath the top-k kernels launched above (also when the source
+    # is pageable and the copy call blocks the host)
+    side = _side_stream(dev)
+    with torch.cuda.stream(side):
+        ek = _to_dev(expression_key, dev, (torch.float32, torch.float64))
+        uploaded = side.record_event()
+    ek.record_stream(cur)
+    cur.wait_event(uploaded)
+    emb, expr = weighted_topk_average_device(sk, ek, iq, idx, mode, val if mode == "similarity" else None,
+                                             want_emb, out_dtype, distances=dst)
+    idx_np, emb_np, expr_np = to_host(idx, emb, expr)
+    return idx_np, emb_np, expr_np
+
+
+class Bank:
+    """A bank (spot_key, expression_key) kept resident on the device across many ``retrieve`` calls:
+    the serving form of the fold loop, where only the queries travel per call."""
+
+    def __init__(self, spot_key: ArrayLike, expression_key: ArrayLike, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.MclstError("no CUDA device: Bank has no CPU fallback")
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.spot_key = _to_dev(spot_key, dev).contiguous()
+        self.expression_key = _to_dev(expression_key, dev, (torch.float32, torch.float64)).contiguous()
+        if self.spot_key.shape[0] != self.expression_key.shape[0]:
+            raise ValueError("spot_key and expression_key must have the same number of rows")
+
+    def __len__(self) -> int:
+        return self.spot_key.shape[0]
+
+    def retrieve(self, image_query: ArrayLike, top_k: int = 50, p: int = 2, mode: Optional[str] = None,
+                 want_emb: bool = True, out_dtype=torch.float64):
+        with torch.cuda.device(self.spot_key.device):
+            return retrieve(self.spot_key, self.expression_key, image_query, top_k, p, mode, want_emb, out_dtype)
 
 
 def debug_similarity(spot_embeddings: ArrayLike, query_embeddings: ArrayLike) -> torch.Tensor:

@@ -175,3 +175,27 @@ def test_cfg3_shape_properties():
     # the exact path and the default path agree everywhere
     val_e, idx_e = retrieval.find_matches_device(tb, tq, c["k"], exact_only=True)
     assert torch.equal(idx_e, idx) and torch.equal(val_e, val)
+
+
+def test_resident_bank_and_pinned_io_equal_one_shot():
+    """retrieve() with pageable NumPy inputs, with pinned tensors, and Bank.retrieve() with the
+    bank resident give byte-identical results (the upload overlap and the pinned result buffers
+    of the host layer change nothing numerically); results large enough to take the pinned path."""
+    N, Q, D, G, k = 6000, 1500, 256, 300, 50
+    bank = synth.embeddings(N, D, 4101, "clustered")
+    qry = synth.embeddings(Q, D, 4102, "clustered")
+    expr = synth.expression(N, G, 4103)
+    a = retrieval.retrieve(bank, expr, qry, top_k=k, p=2)
+    pb, pe, pq = (torch.from_numpy(x).pin_memory() for x in (bank, expr, qry))
+    b = retrieval.retrieve(pb, pe, pq, top_k=k, p=2)
+    resident = retrieval.Bank(bank, expr)
+    assert len(resident) == N
+    c = resident.retrieve(qry, top_k=k, p=2)
+    c2 = resident.retrieve(pq, top_k=k, p=2)                     # second call reuses the pinned pool
+    for other in (b, c, c2):
+        for x, y in zip(a, other):
+            assert x.dtype == y.dtype and x.shape == y.shape
+            np.testing.assert_array_equal(x, y)
+    assert a[0].dtype == np.int64 and a[1].dtype == np.float64 and a[2].dtype == np.float64
+    sval, sidx = oracle.find_matches_spec(bank, qry[::50], k)
+    np.testing.assert_array_equal(a[0][::50], sidx)
