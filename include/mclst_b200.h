@@ -111,6 +111,14 @@ int mclst_debug_similarity(const float* bank, int64_t n_bank, int64_t ld_bank,
                            float* out, int64_t ld_out, void* workspace, size_t workspace_bytes,
                            mclst_stream_t stream);
 
+/* Testing aid (host only, no device needed): the work decomposition of the persistent top-k
+ * kernel for query_blocks x bank_tiles on `lanes` SMs with at most max_slots candidate streams
+ * per query block.  Writes up to max_units records {lane, query_block, tile_begin, tile_end,
+ * slot} (5 ints each) to units and their number to *n_units; *slots = streams per query block.
+ * Not part of the reference surface. */
+int mclst_debug_lane_plan(int64_t query_blocks, int64_t bank_tiles, int lanes, int max_slots,
+                          int* units, int64_t max_units, int64_t* n_units, int* slots);
+
 /* The per-query loop evel_her2st.py:175-187 / evel_visium.py:194-205 /
  * evel_cscc.py:198-215 / BLEEP_inference.ipynb cell 5: weights from the UN-normalised
  * spot_key rows selected by `indices` and the query, then the weighted average of those

@@ -18,7 +18,7 @@ int launch_exact_topk(const float* bank, int64_t N, int64_t ldb, const double* b
 
 // ---- tensor-core candidate path (sim_topk.cu)
 struct TcWorkspace {
-  int nkb, S, SS, cap, cluster, epw, ring;   // SS = S * (epw / 4) candidate streams per query
+  int nkb, S, SS, cap, cluster, epw, ring, lanes;   // SS = S * (epw / 4) candidate streams per query
   int64_t q_pad, n_pad;
   uint32_t* stats;          // [0..7] bank: max residual bits, non-finite flag; [8..15] queries
   uint8_t *qpack, *bpack;

@@ -488,6 +488,291 @@ sim_topk_kernel(const SimParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ============================================================================ sim_topk (lanes)
+// Persistent form of the kernel above: one CTA ("lane") per SM walks a short list of units
+// (query block, bank-tile range, stream slot), so that every SM gets the same number of tiles
+// whatever the number of query blocks.  The (query block x stream) grid above idles SMs whenever
+// blocks * S is not close to a multiple of 148 (128 blocks on 148 SMs: 14 % lost, which is what
+// the 4x2 eight-GPU decomposition ran into) and pays for balance with extra streams per query
+// (S = 4 at 256 blocks: twice the candidates for the re-rank).  Unit lists, QT blocks, T tiles, W lanes:
+//   * rounds = QT / W full rounds: lane c takes block j*W + c over the whole bank (slot 0);
+//   * the rest = QT % W blocks share one last round of rest*T/W tiles per lane: each block gets
+//     w = W / rest dedicated lanes that split the MAIN region [0, M) of the bank w ways
+//     (slots 0..w-1), and the R = W - w*rest left-over lanes cut the TAIL region [M, T) of all
+//     rest blocks into equal linear runs (slots w, w+1), M = T*w*rest/W.
+// Lanes of a round start together and advance at the same rate, so all of them read the same
+// bank tiles at about the same time (one HBM read, the rest L2 hits) exactly like the waves of
+// the grid kernel; tail lanes take their boundary-aligned pieces first and the partial head
+// piece last for the same reason (two aligned groups instead of R unrelated streams).
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+struct LanePlan {
+  int W, rounds, rest, w, R, M, Lt, slots;
+  int h, hm;      // sub-units (= fresh candidate buffers) per full-round unit / per main-lane unit
+};
+struct LaneUnit { int qb, t0, t1, slot; };
+
+__host__ __device__ inline bool lane_unit(const LanePlan& L, int T, int c, int j, LaneUnit& u) {
+  if (j < L.rounds * L.h) {
+    const int r = j / L.h, sub = j - r * L.h;
+    u.qb = r * L.W + c;
+    u.t0 = (int)((int64_t)T * sub / L.h);
+    u.t1 = (int)((int64_t)T * (sub + 1) / L.h);
+    u.slot = sub;
+    return true;
+  }
+  j -= L.rounds * L.h;
+  if (L.rest == 0) return false;
+  const int main_lanes = L.w * L.rest;
+  if (c < main_lanes) {
+    if (j >= L.hm) return false;
+    const int ql = c / L.w, part = (c - ql * L.w) * L.hm + j, parts = L.w * L.hm;
+    u.qb = L.rounds * L.W + ql;
+    u.t0 = (int)((int64_t)L.M * part / parts);
+    u.t1 = (int)((int64_t)L.M * (part + 1) / parts);
+    u.slot = part;
+    return true;
+  }
+  if (c >= main_lanes + L.R) return false;
+  const int64_t Tt = T - L.M;
+  const int jt = c - main_lanes;
+  const int64_t lo = (int64_t)jt * L.Lt;
+  const int64_t end = (int64_t)L.rest * Tt;
+  const int64_t hi = lo + L.Lt < end ? lo + L.Lt : end;
+  if (lo >= hi) return false;
+  const int64_t first_b = (lo + Tt - 1) / Tt * Tt;                    // first block boundary >= lo
+  const int64_t head_end = first_b < hi ? first_b : hi;              // head piece = [lo, head_end)
+  const int64_t nb = hi > first_b ? (hi - first_b + Tt - 1) / Tt : 0;  // boundary-aligned pieces
+  int64_t a, b;
+  if (j < nb) { a = first_b + (int64_t)j * Tt; b = a + Tt < hi ? a + Tt : hi; }
+  else if (j == nb && head_end > lo) { a = lo; b = head_end; }
+  else return false;
+  const int64_t ql = a / Tt;
+  u.qb = L.rounds * L.W + (int)ql;
+  u.t0 = L.M + (int)(a - ql * Tt);
+  u.t1 = L.M + (int)(b - ql * Tt);
+  u.slot = L.w * L.hm + jt - (int)((ql * Tt) / L.Lt);
+  return true;
+}
+
+static LanePlan plan_lanes(int64_t qt, int64_t T, int W, int max_slots) {
+  LanePlan L{};
+  L.W = (int)std::min<int64_t>(W, std::max<int64_t>(qt, 1) * max_slots);
+  L.W = std::max(1, std::min(L.W, W));
+  L.rounds = (int)(qt / L.W);
+  L.rest = (int)(qt % L.W);
+  L.w = 0; L.R = 0; L.M = (int)T; L.Lt = 0; L.slots = 1;
+  if (L.rest > 0) {
+    int w = L.W / L.rest;
+    w = (int)std::min<int64_t>(std::min(w, max_slots), std::max<int64_t>(T, 1));
+    L.w = std::max(1, w);
+    const int left = L.W - L.w * L.rest;
+    if (left > 0 && left < L.rest && L.w + 2 <= max_slots) {
+      // main region length: whichever rounding of T*w*rest/W gives the smaller makespan
+      const int64_t m_lo = T * L.w * L.rest / L.W;
+      int64_t best_m = T, best_span = ceil_div(T, (int64_t)L.w);
+      for (int64_t M = m_lo; M <= std::min(T - 1, m_lo + 1); ++M) {
+        if (M < L.w) continue;
+        const int64_t span = std::max(ceil_div(M, (int64_t)L.w), ceil_div((int64_t)L.rest * (T - M), (int64_t)left));
+        if (span < best_span) { best_span = span; best_m = M; }
+      }
+      if (best_m < T) {
+        L.R = left; L.M = (int)best_m;
+        L.Lt = (int)ceil_div((int64_t)L.rest * (T - best_m), (int64_t)left);
+      }
+    }
+    L.slots = L.w + (L.R > 0 ? 2 : 0);
+  }
+  // Fresh candidate buffers instead of prunes: a unit cut into h back-to-back sub-units gives each
+  // its own slot, so the later ones start from the threshold the earlier ones published and rarely
+  // fill up (the grid kernel got this for free from S = 2; one long stream per query block cost
+  // 2 ms of extra prune stalls at cfg4).
+  static const int split = env_int("MCLST_SIM_ROUND_SPLIT", 2);
+  L.h = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(split, max_slots), T));
+  L.hm = 1;
+  if (L.rest > 0) {
+    const int room = (max_slots - (L.R > 0 ? 2 : 0)) / L.w;
+    L.hm = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(split, room), std::max<int64_t>(1, L.M / L.w)));
+    L.slots = L.w * L.hm + (L.R > 0 ? 2 : 0);
+  }
+  if (L.rounds > 0) L.slots = std::max(L.slots, L.h);
+  return L;
+}
+
+template <int CAP, int EPW>
+__global__ void __launch_bounds__(64 + 32 * EPW, 1)
+sim_topk_lanes_kernel(const SimParams p, const LanePlan L) {
+  constexpr int CP = EPW / 4;
+  constexpr int PART_COLS = ST_BN / CP;
+  constexpr int NCH = PART_COLS / 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + ST_A_BYTES;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + ST_STAGES * ST_STAGE_BYTES);
+  uint64_t* bar_empty = bar_full + ST_STAGES;
+  uint64_t* bar_a = bar_empty + ST_STAGES;
+  uint64_t* bar_afree = bar_a + 1;
+  uint64_t* bar_tfull = bar_afree + 1;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x;
+  const int nkb = p.nkb;
+  const int T = p.tiles_total;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ST_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    mbar_init(bar_a, 1);
+    mbar_init(bar_afree, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], EPW); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint64_t pol_keep = policy_evict_last();
+      uint32_t stage = 0, phase = 0;
+      LaneUnit u;
+      for (int j = 0; lane_unit(L, T, c, j, u); ++j) {
+        if (j > 0) mbar_wait(bar_afree, (uint32_t)(j - 1) & 1u);   // previous unit's MMAs have read sA
+        mbar_arrive_expect_tx(bar_a, (uint32_t)(nkb * TP_SLICE_BYTES));
+        for (int kb = 0; kb < nkb; ++kb)
+          bulk_g2s(sA + kb * TP_SLICE_BYTES,
+                   p.qpack + ((size_t)u.qb * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES, bar_a);
+        for (int t = u.t0; t < u.t1; ++t) {
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&bar_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&bar_full[stage], ST_STAGE_BYTES);
+            uint8_t* dst = sB + stage * ST_STAGE_BYTES;
+            bulk_g2s_hint(dst, p.bpack + ((size_t)(2 * t) * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES,
+                          &bar_full[stage], pol_keep);
+            bulk_g2s_hint(dst + TP_SLICE_BYTES, p.bpack + ((size_t)(2 * t + 1) * nkb + kb) * TP_SLICE_BYTES,
+                          TP_SLICE_BYTES, &bar_full[stage], pol_keep);
+            if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, ST_BN, false);
+      const uint32_t a_base = smem_u32(sA);
+      const uint32_t b_base = smem_u32(sB);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      LaneUnit u;
+      for (int j = 0; lane_unit(L, T, c, j, u); ++j) {
+        mbar_wait(bar_a, (uint32_t)j & 1u);
+        tc_fence_after();
+        for (int t = u.t0; t < u.t1; ++t, ++it) {
+          const int buf = it & 1;
+          mbar_wait(&bar_tempty[buf], ((it >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * ST_BN;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&bar_full[stage], phase);
+            tc_fence_after();
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t ad = make_smem_desc_sw128(a_base + kb * TP_SLICE_BYTES + k4 * 32);
+              const uint64_t bd = make_smem_desc_sw128(b_base + stage * ST_STAGE_BYTES + k4 * 32);
+              mma_f16_ss(d_tmem, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+            }
+            mma_commit(&bar_empty[stage]);
+            if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+          }
+          mma_commit(&bar_tfull[buf]);
+        }
+        mma_commit(bar_afree);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: threshold filter
+    const int quad = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int SS = L.slots * CP;
+    const float rs_max = __uint_as_float(p.bank_stats[0]);
+    const int k = p.k;
+    const int gap = p.prune_gap;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + part * PART_COLS;
+    int it = 0;
+    LaneUnit u;
+#pragma unroll 1
+    for (int j = 0; lane_unit(L, T, c, j, u); ++j) {
+      const int64_t q = (int64_t)u.qb * 128 + row;
+      const bool q_valid = q < p.Q;
+      const int stream = u.slot * CP + part;
+      uint2* my_buf = p.cand + ((size_t)q * SS + stream) * CAP;
+      uint32_t* my_gthr = p.gthr + q;
+      const float rq = q_valid ? p.q_resid[q] : 0.f;
+      const float e2 = 2.02f * pair_eps(rq, rs_max);
+      float thr = q_valid ? __int_as_float(0xff800000) : __int_as_float(0x7f800000);
+      int cnt = 0;
+      int flagged = 0;
+      int trigger = min(CAP - 32, max(k + 16, gap + k));
+#pragma unroll 1
+      for (int t = u.t0; t < u.t1; ++t, ++it) {
+        const int buf = it & 1;
+        // adopt the best threshold any other stream of this query has published so far
+        const uint32_t gk = q_valid ? *reinterpret_cast<volatile uint32_t*>(my_gthr) : 0u;
+        mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
+        tc_fence_after();
+        if (gk != 0u) thr = fmaxf(thr, ord2f(gk));
+        const uint32_t taddr = t_lane + buf * ST_BN;
+        const int64_t col_base = (int64_t)t * ST_BN + part * PART_COLS;
+        const int n_valid = (int)min((int64_t)PART_COLS, p.N - col_base);
+        uint32_t va[32], vb[32];
+        if (p.ablate == 2) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_tempty[buf]);
+          continue;
+        }
+        tmem_ld_32x32(taddr, va);
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ch += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x32(taddr + (ch + 1) * 32, vb);
+          if (p.ablate == 0)
+            filter_chunk<CAP>(va, my_buf, my_gthr, cnt, thr, flagged, (uint32_t)(col_base + ch * 32),
+                              n_valid - ch * 32, k, e2, trigger, gap);
+          else if ((va[0] ^ va[13] ^ va[31]) == 0x12345678u) cnt++;
+          tmem_ld_wait();
+          if (ch + 2 < NCH) {
+            tmem_ld_32x32(taddr + (ch + 2) * 32, va);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[buf]);
+          }
+          if (p.ablate == 0)
+            filter_chunk<CAP>(vb, my_buf, my_gthr, cnt, thr, flagged,
+                              (uint32_t)(col_base + (ch + 1) * 32), n_valid - (ch + 1) * 32, k, e2, trigger, gap);
+          else if ((vb[0] ^ vb[13] ^ vb[31]) == 0x12345678u) cnt++;
+        }
+      }
+      if (q_valid) p.cand_cnt[(size_t)q * SS + stream] = flagged ? -1 : cnt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // ============================================================================ sim_topk (event ring)
 // Same TMA -> tcgen05.mma -> TMEM pipeline, different drain.  ncu on the kernel above showed the
 // TMEM-critical warps spending half their time in single-lane append chains and L2 round trips
@@ -1034,12 +1319,8 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
 }
 
 // ============================================================================ host side
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
 int sim_topk_epw();
+int sim_topk_use_lanes();
 int sim_topk_cluster(int64_t n_query) {
   static const int forced = env_int("MCLST_SIM_CLUSTER", 0);
   if (forced == 1 || forced == 2 || forced == 4) return forced;
@@ -1057,6 +1338,12 @@ int sim_topk_use_ring() {
   // once thresholds are warm (26.1 vs 26.7 ms at cfg4), but its 4 worker warps fall behind while
   // thresholds are still converging (38 vs 32 ms end to end) -- off until the seed pass is tighter.
   static const int v = env_int("MCLST_SIM_RING", 0);
+  return v;
+}
+
+int sim_topk_use_lanes() {
+  // persistent lane kernel (balanced unit lists) instead of the (query block x stream) grid
+  static const int v = env_int("MCLST_SIM_LANES", 1);
   return v;
 }
 
@@ -1097,6 +1384,9 @@ void tc_workspace(Arena& a, int64_t n_bank, int64_t n_query, int dim, int top_k,
   w.n_pad = (int64_t)align_up((size_t)n_bank, ST_BN);
   w.S = sim_topk_splits(n_query, n_bank, w.cluster);
   w.ring = sim_topk_use_ring() && w.cluster == 1 && tc_cap_for_k(top_k) <= 512;
+  w.lanes = sim_topk_use_lanes() && !w.ring && w.cluster == 1;
+  if (w.lanes)
+    w.S = plan_lanes(w.q_pad / 128, w.n_pad / ST_BN, sm_count(), std::max(1, 8 / (w.epw / 4))).slots;
   w.SS = w.ring ? w.S : w.S * (w.epw / 4);
   w.cap = tc_cap_for_k(top_k);
   w.stats = a.take<uint32_t>(16);
@@ -1195,17 +1485,31 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
   }
   if (w.ring) {
     auto launch_ring = [&](auto kern) -> int {
-      static bool attr_set = false;
-      if (!attr_set) {
-        MCLST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RG_SMEM));
-        attr_set = true;
-      }
+      MCLST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RG_SMEM));
       kern<<<grid, RG_THREADS, RG_SMEM, st>>>(p);
       MCLST_LAUNCH_CHECK();
       return 0;
     };
     if (w.cap == 256) return launch_ring(sim_topk_ring_kernel<256>);
     if (w.cap == 512) return launch_ring(sim_topk_ring_kernel<512>);
+  }
+  if (w.lanes && dump == nullptr) {
+    const LanePlan L = plan_lanes(w.q_pad / 128, p.tiles_total, sm_count(), std::max(1, 8 / (w.epw / 4)));
+    MCLST_REQUIRE(L.slots == w.S, MCLST_ERR_UNSUPPORTED, "sim_topk: lane plan changed (%d vs %d slots)", L.slots, w.S);
+    // slots a query block does not use must read as empty
+    MCLST_CUDA(cudaMemsetAsync(w.cand_cnt, 0, (size_t)w.q_pad * w.SS * sizeof(int), st));
+    auto launch_lanes = [&](auto kern, int threads) -> int {
+      // (all instantiations share one function-pointer type, hence one lambda body: no static flag)
+      MCLST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+      kern<<<(unsigned)L.W, threads, ST_SMEM, st>>>(p, L);
+      MCLST_LAUNCH_CHECK();
+      return 0;
+    };
+    if (w.cap == 256 && w.epw == 8) return launch_lanes(sim_topk_lanes_kernel<256, 8>, 64 + 32 * 8);
+    if (w.cap == 256 && w.epw == 4) return launch_lanes(sim_topk_lanes_kernel<256, 4>, 64 + 32 * 4);
+    if (w.cap == 256 && w.epw == 16) return launch_lanes(sim_topk_lanes_kernel<256, 16>, 64 + 32 * 16);
+    if (w.cap == 1024 && w.epw == 8) return launch_lanes(sim_topk_lanes_kernel<1024, 8>, 64 + 32 * 8);
+    if (w.cap == 1024 && w.epw == 4) return launch_lanes(sim_topk_lanes_kernel<1024, 4>, 64 + 32 * 4);
   }
   if (w.cap == 256) {
     if (w.cluster == 1) return launch_sim_topk_e<256, 1>(w.epw, p, grid, st);
@@ -1254,3 +1558,24 @@ int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64
 }
 
 }  // namespace mclst
+
+extern "C" int mclst_debug_lane_plan(int64_t query_blocks, int64_t bank_tiles, int lanes, int max_slots,
+                                     int* units, int64_t max_units, int64_t* n_units, int* slots) {
+  using namespace mclst;
+  MCLST_REQUIRE(query_blocks >= 1 && bank_tiles >= 1 && lanes >= 1 && max_slots >= 1 && n_units && slots,
+                MCLST_ERR_INVALID, "debug_lane_plan: bad args");
+  const LanePlan L = plan_lanes(query_blocks, bank_tiles, lanes, max_slots);
+  *slots = L.slots;
+  int64_t n = 0;
+  for (int c = 0; c < L.W; ++c) {
+    LaneUnit u;
+    for (int j = 0; lane_unit(L, (int)bank_tiles, c, j, u); ++j, ++n) {
+      if (units && n < max_units) {
+        int* o = units + 5 * n;
+        o[0] = c; o[1] = u.qb; o[2] = u.t0; o[3] = u.t1; o[4] = u.slot;
+      }
+    }
+  }
+  *n_units = n;
+  return 0;
+}

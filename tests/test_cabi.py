@@ -1,5 +1,6 @@
 """CPU checks of the C-ABI boundary: the library builds for sm_100a, loads, and exports
 every symbol include/mclst_b200.h declares.  No compute calls (no GPU here)."""
+import numpy as np
 import ctypes
 import os
 import subprocess
@@ -57,3 +58,43 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def _lane_plan(lib, qt, tiles, lanes, max_slots):
+    import ctypes as C
+    cap = qt * max_slots + 4 * lanes + 16
+    units = np.zeros((cap, 5), dtype=np.int32)
+    n, slots = C.c_int64(), C.c_int()
+    rc = lib.mclst_debug_lane_plan(C.c_int64(qt), C.c_int64(tiles), lanes, max_slots,
+                                   units.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(n), C.byref(slots))
+    assert rc == 0 and n.value <= cap
+    return units[:n.value], slots.value
+
+
+def test_lane_plan_covers_every_tile_once():
+    """Host-only property of the persistent top-k kernel's work decomposition: every
+    (query block, bank tile) belongs to exactly one unit, no two units share a candidate
+    stream (query block, slot), slots stay below the advertised count, and the headline shapes
+    are balanced to within 0.1 % of the ideal tiles-per-SM."""
+    import random
+    lib = _lib.load()
+    rng = random.Random(7)
+    cases = [(512, 7813, 148, 4), (256, 3907, 148, 4), (128, 3907, 148, 4), (64, 7813, 148, 4),
+             (1, 1, 148, 4), (147, 10, 148, 4), (149, 100, 148, 4), (75, 1000, 148, 4), (5, 36, 148, 2)]
+    cases += [(rng.randint(1, 500), rng.randint(1, 300), rng.choice([148, 132, 8, 3, 1]),
+               rng.choice([1, 2, 4, 8])) for _ in range(120)]
+    for qt, tiles, lanes, max_slots in cases:
+        units, slots = _lane_plan(lib, qt, tiles, lanes, max_slots)
+        assert 1 <= slots <= max_slots
+        cover = np.zeros((qt, tiles), dtype=np.int32)
+        load = np.zeros(lanes, dtype=np.int64)
+        streams = set()
+        for c, qb, t0, t1, slot in units:
+            assert 0 <= c < lanes and 0 <= qb < qt and 0 <= t0 < t1 <= tiles and 0 <= slot < slots
+            assert (qb, slot) not in streams
+            streams.add((qb, slot))
+            cover[qb, t0:t1] += 1
+            load[c] += t1 - t0
+        assert (cover == 1).all(), (qt, tiles, lanes, max_slots)
+        if tiles > 1000 and lanes == 148:
+            assert load.max() <= 1.001 * qt * tiles / lanes + 1
