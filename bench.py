@@ -286,6 +286,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-bank-shards", type=int, default=0,
+                    help="bank shards of the end-to-end (host array) job at N > 1; default: all ranks")
     ap.add_argument("--exact-only", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the loss / train-step metrics")
     ap.add_argument("--bank-shards", type=int, default=int(os.environ.get("MCLST_BANK_SHARDS", 0)),
@@ -339,6 +341,16 @@ def main():
         config["parallelism"] = (f"{grid.query_groups} query groups x {grid.bank_shards} bank shards "
                                  "(candidate all-gather + merge inside a group)")
         shard = mdist.BankShard.from_full(bank, expr, grid.b_index, grid.bank_shards)
+        e2e_host = None
+        if not args.no_e2e:
+            # the one-shot host-array job is upload-bound, so its decomposition shards the bank
+            # over ALL ranks (every byte crosses PCIe once) and replicates the queries
+            eshards = args.e2e_bank_shards if args.e2e_bank_shards > 0 else world
+            egrid = grid if eshards == grid.bank_shards else mdist.make_retrieval_grid(eshards, world, rank)
+            lo, hi = mdist.shard_bounds(N, egrid.bank_shards)[egrid.b_index]
+            eq0, eq1 = egrid.query_slice(Q)
+            e2e_host = (egrid, bank[lo:hi].cpu().pin_memory(), expr[lo:hi].cpu().pin_memory(),
+                        qry[eq0:eq1].cpu().pin_memory(), lo)
         q0, q1 = grid.query_slice(Q)
         qry = qry[q0:q1].contiguous()
         del bank, expr
@@ -429,11 +441,11 @@ def main():
         if world == 1:
             hb, he = bank.cpu().pin_memory(), expr.cpu().pin_memory()
             del bank, expr
+            hq = qry.cpu().pin_memory()
         else:
-            hb, he = shard.spot_key.cpu().pin_memory(), shard.expression_key.cpu().pin_memory()
-            off, ntot = shard.index_offset, shard.n_total
+            egrid, hb, he, hq, off = e2e_host
+            ntot = N
             del shard
-        hq = qry.cpu().pin_memory()
         torch.cuda.empty_cache()
 
         def e2e_step():
@@ -443,8 +455,8 @@ def main():
                 return idx, ex
             sh = mdist.BankShard.from_host(hb, he, off, ntot, dev)
             idx, val, _, ex = mdist.retrieve_sharded(sh, hq.to(dev, non_blocking=True), k, args.mode,
-                                                     group=grid.group)
-            if grid.b_index == 0:            # one rank of every query group reads its slice back
+                                                     group=egrid.group)
+            if egrid.b_index == 0:           # one rank of every query group reads its slice back
                 return retrieval.to_host(idx, ex)
             torch.cuda.synchronize()
             return None
@@ -477,12 +489,13 @@ def main():
                         "api": "mclstexp_b200.retrieval.Bank(...).retrieve(host queries) -> host arrays"}
             del bank_obj
         e2e = {"value": Q / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "resident_bank": resident,
-               "h2d_bytes_per_step": int((N * (D + G) * (grid.query_groups if world > 1 else 1) + Q * D *
-                                          (grid.bank_shards if world > 1 else 1)) * 4),
+               "h2d_bytes_per_step": int((N * (D + G) * (egrid.query_groups if world > 1 else 1) + Q * D *
+                                          (egrid.bank_shards if world > 1 else 1)) * 4),
                "d2h_bytes_per_step": int(Q * k * 8 + Q * G * 4),
                "api": "mclstexp_b200.retrieval.retrieve(host arrays) -> host arrays" if world == 1 else
-                      "mclstexp_b200.distributed.retrieve_sharded from pinned host shards; one rank per "
-                      "query group reads its slice back"}
+                      f"mclstexp_b200.distributed.BankShard.from_host + retrieve_sharded from pinned host "
+                      f"shards, {egrid.query_groups} query groups x {egrid.bank_shards} bank shards; one rank "
+                      "per query group reads its slice back"}
         del hb, he, hq
 
     extra = None

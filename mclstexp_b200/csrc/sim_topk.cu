@@ -602,7 +602,9 @@ static LanePlan plan_lanes(int64_t qt, int64_t T, int W, int max_slots) {
   return L;
 }
 
-template <int CAP, int EPW>
+// SEED = true: the seed pass on the same balanced unit lists -- "tile" t of a unit is bank tile
+// tile_begin + t * tile_stride of the sample and the epilogue only records chunk maxima.
+template <int CAP, int EPW, bool SEED>
 __global__ void __launch_bounds__(64 + 32 * EPW, 1)
 sim_topk_lanes_kernel(const SimParams p, const LanePlan L) {
   constexpr int CP = EPW / 4;
@@ -623,7 +625,7 @@ sim_topk_lanes_kernel(const SimParams p, const LanePlan L) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x;
   const int nkb = p.nkb;
-  const int T = p.tiles_total;
+  const int T = SEED ? p.n_tiles : p.tiles_total;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < ST_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
@@ -651,13 +653,14 @@ sim_topk_lanes_kernel(const SimParams p, const LanePlan L) {
           bulk_g2s(sA + kb * TP_SLICE_BYTES,
                    p.qpack + ((size_t)u.qb * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES, bar_a);
         for (int t = u.t0; t < u.t1; ++t) {
+          const int bt = SEED ? p.tile_begin + t * p.tile_stride : t;       // bank tile
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&bar_empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&bar_full[stage], ST_STAGE_BYTES);
             uint8_t* dst = sB + stage * ST_STAGE_BYTES;
-            bulk_g2s_hint(dst, p.bpack + ((size_t)(2 * t) * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES,
+            bulk_g2s_hint(dst, p.bpack + ((size_t)(2 * bt) * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES,
                           &bar_full[stage], pol_keep);
-            bulk_g2s_hint(dst + TP_SLICE_BYTES, p.bpack + ((size_t)(2 * t + 1) * nkb + kb) * TP_SLICE_BYTES,
+            bulk_g2s_hint(dst + TP_SLICE_BYTES, p.bpack + ((size_t)(2 * bt + 1) * nkb + kb) * TP_SLICE_BYTES,
                           TP_SLICE_BYTES, &bar_full[stage], pol_keep);
             if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
           }
@@ -732,9 +735,27 @@ sim_topk_lanes_kernel(const SimParams p, const LanePlan L) {
         tc_fence_after();
         if (gk != 0u) thr = fmaxf(thr, ord2f(gk));
         const uint32_t taddr = t_lane + buf * ST_BN;
-        const int64_t col_base = (int64_t)t * ST_BN + part * PART_COLS;
+        const int64_t col_base = (int64_t)(SEED ? p.tile_begin + t * p.tile_stride : t) * ST_BN + part * PART_COLS;
         const int n_valid = (int)min((int64_t)PART_COLS, p.N - col_base);
         uint32_t va[32], vb[32];
+        if (SEED) {
+          // record the maximum of every 32-score chunk of this thread's columns
+          float* so = p.seed_out + (size_t)q * (p.n_tiles * 8) + (size_t)t * 8 + part * NCH;
+#pragma unroll 1
+          for (int ch = 0; ch < NCH; ++ch) {
+            tmem_ld_32x32(taddr + ch * 32, va);
+            tmem_ld_wait();
+            float m = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              m = fmaxf(m, (ch * 32 + e < n_valid) ? __uint_as_float(va[e]) : -INFINITY);
+            if (q_valid) so[ch] = m;
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_tempty[buf]);
+          continue;
+        }
         if (p.ablate == 2) {
           tc_fence_before();
           __syncwarp();
@@ -764,7 +785,7 @@ sim_topk_lanes_kernel(const SimParams p, const LanePlan L) {
           else if ((vb[0] ^ vb[13] ^ vb[31]) == 0x12345678u) cnt++;
         }
       }
-      if (q_valid) p.cand_cnt[(size_t)q * SS + stream] = flagged ? -1 : cnt;
+      if (!SEED && q_valid) p.cand_cnt[(size_t)q * SS + stream] = flagged ? -1 : cnt;
     }
   }
 
@@ -1092,12 +1113,27 @@ seed_threshold_kernel(const float* __restrict__ seed, int n_vals, int64_t Q, int
   if (q >= Q) return;
   const float* v = seed + (size_t)q * n_vals;
   uint32_t T = 0;
-  for (int bit = 31; bit >= 8; --bit) {
-    const uint32_t cand = T | (1u << bit);
-    int c = 0;
-    for (int i = lane; i < n_vals; i += 32) c += (f2ord(v[i]) >= cand) ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= k) T = cand;
+  if (n_vals <= 1024) {
+    // the usual case: the whole sample as ordered keys in registers, 24 compare sweeps
+    uint32_t key[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) key[i] = (lane + 32 * i < n_vals) ? f2ord(v[lane + 32 * i]) : 0u;
+    for (int bit = 31; bit >= 8; --bit) {
+      const uint32_t cand = T | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) c += (key[i] >= cand) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= k) T = cand;
+    }
+  } else {
+    for (int bit = 31; bit >= 8; --bit) {
+      const uint32_t cand = T | (1u << bit);
+      int c = 0;
+      for (int i = lane; i < n_vals; i += 32) c += (f2ord(v[i]) >= cand) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= k) T = cand;
+    }
   }
   if (lane == 0 && T != 0u) {
     const float e2 = 2.02f * pair_eps(q_resid[q], __uint_as_float(bank_stats[0]));
@@ -1476,9 +1512,18 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
     sp.seed_out = w.seed; sp.n_tiles = w.n_seed; sp.tile_begin = 0;
     sp.tile_stride = std::max(1, p.tiles_total / w.n_seed);
     sp.S = 1;
-    dim3 sgrid((unsigned)(w.q_pad / 128), 1);
-    int rc = launch_sim_topk_t<256, 1, 8>(sp, sgrid, st);
-    if (rc) return rc;
+    if (w.lanes) {
+      // balanced persistent form; one sub-unit per unit (no candidate slots involved)
+      LanePlan SL = plan_lanes(w.q_pad / 128, w.n_seed, sm_count(), 4);
+      auto kern = sim_topk_lanes_kernel<256, 8, true>;
+      MCLST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+      kern<<<(unsigned)SL.W, 64 + 32 * 8, ST_SMEM, st>>>(sp, SL);
+      MCLST_LAUNCH_CHECK();
+    } else {
+      dim3 sgrid((unsigned)(w.q_pad / 128), 1);
+      int rc = launch_sim_topk_t<256, 1, 8>(sp, sgrid, st);
+      if (rc) return rc;
+    }
     seed_threshold_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, st>>>(
         w.seed, w.n_seed * 8, n_query, top_k, w.q_resid, w.stats, w.gthr);
     MCLST_LAUNCH_CHECK();
@@ -1505,11 +1550,11 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
       MCLST_LAUNCH_CHECK();
       return 0;
     };
-    if (w.cap == 256 && w.epw == 8) return launch_lanes(sim_topk_lanes_kernel<256, 8>, 64 + 32 * 8);
-    if (w.cap == 256 && w.epw == 4) return launch_lanes(sim_topk_lanes_kernel<256, 4>, 64 + 32 * 4);
-    if (w.cap == 256 && w.epw == 16) return launch_lanes(sim_topk_lanes_kernel<256, 16>, 64 + 32 * 16);
-    if (w.cap == 1024 && w.epw == 8) return launch_lanes(sim_topk_lanes_kernel<1024, 8>, 64 + 32 * 8);
-    if (w.cap == 1024 && w.epw == 4) return launch_lanes(sim_topk_lanes_kernel<1024, 4>, 64 + 32 * 4);
+    if (w.cap == 256 && w.epw == 8) return launch_lanes(sim_topk_lanes_kernel<256, 8, false>, 64 + 32 * 8);
+    if (w.cap == 256 && w.epw == 4) return launch_lanes(sim_topk_lanes_kernel<256, 4, false>, 64 + 32 * 4);
+    if (w.cap == 256 && w.epw == 16) return launch_lanes(sim_topk_lanes_kernel<256, 16, false>, 64 + 32 * 16);
+    if (w.cap == 1024 && w.epw == 8) return launch_lanes(sim_topk_lanes_kernel<1024, 8, false>, 64 + 32 * 8);
+    if (w.cap == 1024 && w.epw == 4) return launch_lanes(sim_topk_lanes_kernel<1024, 4, false>, 64 + 32 * 4);
   }
   if (w.cap == 256) {
     if (w.cluster == 1) return launch_sim_topk_e<256, 1>(w.epw, p, grid, st);
