@@ -168,7 +168,7 @@ def cpu_reference_time(cfg, mode, budget_s=20.0, seed=7, threads=None):
 
 
 # --------------------------------------------------------------------------- second metric
-def _time_cuda(fn, iters=3, warm=1):
+def _time_cuda(fn, iters=5, warm=2):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -186,7 +186,7 @@ def loss_sweep(dev, peaks, world, rank, quick):
     at world > 1 the batch is the GLOBAL batch, sharded by rows with embedding all-gather."""
     from mclstexp_b200 import loss as mloss
     out = {}
-    sizes = [256, 1024, 4096] if quick else synth.CONFIGS["cfg5"]["B_sweep"]
+    sizes = [256, 1024, 4096, 32768] if quick else synth.CONFIGS["cfg5"]["B_sweep"]
     g = torch.Generator(device=dev)
     g.manual_seed(99)
     for B in sizes:

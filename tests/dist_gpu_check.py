@@ -53,6 +53,22 @@ def main():
         ok &= same and e1 < 1e-3
         if rank == 0:
             print(f"grid {grid.query_groups}x{grid.bank_shards}: identical={same}, expr rel err {e1:.2e}")
+    # shards uploaded from pinned host memory (expression rows on a side stream) and a larger
+    # query count so that every rank runs several rounds of the persistent top-k kernel
+    N, Q, D, G, k = 60000, 24000, 256, 300, 50
+    bank = torch.tensor(synth.embeddings(N, D, 41, "clustered"), device=dev)
+    expr = torch.tensor(synth.expression(N, G, 42), device=dev)
+    qry = torch.tensor(synth.embeddings(Q, D, 43, "clustered"), device=dev)
+    lo, hi = N * rank // world, N * (rank + 1) // world
+    hb, he = bank[lo:hi].cpu().pin_memory(), expr[lo:hi].cpu().pin_memory()
+    shard = BankShard.from_host(hb, he, lo, N, dev)
+    idx, val, _, ex = retrieve_sharded(shard, qry, k, "inv_sq_l2")
+    idx1, val1, _, ex1 = retrieval.retrieve_device(bank, expr, qry, k, "inv_sq_l2")
+    same = torch.equal(idx, idx1) and torch.equal(val, val1)
+    e1 = float((ex - ex1).abs().max() / ex1.abs().max())
+    ok &= same and e1 < 1e-3
+    if rank == 0:
+        print(f"from_host shards, Q={Q}: identical={same}, expr rel err {e1:.2e}")
     for targets in ("eye", "soft"):
         B, D = 128 * world * 2, 256
         S = torch.tensor(synth.embeddings(B, D, 21, "clustered", centres=9) * 0.5, device=dev)

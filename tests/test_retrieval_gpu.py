@@ -199,3 +199,39 @@ def test_resident_bank_and_pinned_io_equal_one_shot():
     assert a[0].dtype == np.int64 and a[1].dtype == np.float64 and a[2].dtype == np.float64
     sval, sidx = oracle.find_matches_spec(bank, qry[::50], k)
     np.testing.assert_array_equal(a[0][::50], sidx)
+
+
+def test_bank_shard_from_host_single_rank():
+    """BankShard.from_host (expression rows uploaded on a side stream) + retrieve_sharded without a
+    process group equals retrieve_device on the same data."""
+    from mclstexp_b200.distributed import BankShard, retrieve_sharded
+    N, Q, D, G, k = 9000, 700, 256, 200, 50
+    bank = synth.embeddings(N, D, 5101, "clustered")
+    qry = synth.embeddings(Q, D, 5102, "clustered")
+    expr = synth.expression(N, G, 5103)
+    dev = torch.device("cuda", 0)
+    hb, he = torch.from_numpy(bank).pin_memory(), torch.from_numpy(expr).pin_memory()
+    tq = torch.from_numpy(qry).to(dev)
+    shard = BankShard.from_host(hb, he, 0, N, dev)
+    idx, val, emb, ex = retrieve_sharded(shard, tq, k, "inv_sq_l2", want_emb=True)
+    idx1, val1, emb1, ex1 = retrieval.retrieve_device(hb.to(dev), he.to(dev), tq, k, "inv_sq_l2", want_emb=True)
+    assert torch.equal(idx, idx1) and torch.equal(val, val1)
+    torch.testing.assert_close(ex, ex1, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(emb, emb1, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("N,Q", [(70000, 19000), (70000, 16384), (5000, 40000), (300, 19100)])
+def test_lane_rounds_bit_exact(N, Q):
+    """Shapes whose query-block count exercises every branch of the persistent kernel's unit lists
+    (full rounds + main/tail last round; many rounds over a short bank; tiny bank): default path
+    == exact path == spec on sampled rows."""
+    k = 50
+    bank = synth.embeddings(N, 256, 6001 + N, "clustered")
+    qry = synth.embeddings(Q, 256, 6002 + Q, "clustered")
+    tb, tq = torch.from_numpy(bank).cuda(), torch.from_numpy(qry).cuda()
+    val, idx = retrieval.find_matches_device(tb, tq, k)
+    val_e, idx_e = retrieval.find_matches_device(tb, tq, k, exact_only=True)
+    assert torch.equal(idx, idx_e) and torch.equal(val, val_e)
+    rows = np.arange(0, Q, 997)
+    sval, sidx = oracle.find_matches_spec(bank, qry[rows], k)
+    np.testing.assert_array_equal(idx.cpu().numpy()[rows], sidx)
