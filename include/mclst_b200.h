@@ -274,6 +274,36 @@ int mclst_matmul(const float* A, int64_t lda, int a_trans, int64_t a_batch_strid
                  const float* bias, int act, const float* residual, int precise,
                  void* workspace, size_t workspace_bytes, mclst_stream_t stream);
 
+/* ---------------------------------------------------------------- embedding-table Adam --- */
+
+/* torch.optim.Adam(lr, betas, eps, weight_decay) as train.py:118-120 applies it to the position
+ * tables x_embed / y_embed (model.py:204-205), without streaming 2 x 65536 x G parameters and
+ * their moments through HBM on every step: rows a step does not touch are deferred and replayed
+ * in registers (same arithmetic, step by step) when they are next read.  Lazy == dense bit for
+ * bit; dense == torch up to fp32 rounding.
+ *   coef_table   device buffer of mclst_adam_coef_bytes(max_steps) bytes: per-step scalars
+ *   set_step     records the scalars of step `step` (1-based) -- call once per optimiser step
+ *   dense        one step on n contiguous elements (grad nullable = zero data gradient)
+ *   lazy_rows    for the distinct rows long(position[:, column]) of a batch: replay steps
+ *                last_step[row]+1 .. steps_done; with d_out ([batch, genes], the gradient of the
+ *                embed-add output) also apply step steps_done + 1 with the row's summed gradient.
+ *                first_scratch: table_rows ints.  error_flag (device) is OR-ed with 1 when a
+ *                position is outside [0, table_rows).
+ *   lazy_flush   every row to steps_done (before state_dict / evaluation reads the table) */
+size_t mclst_adam_coef_bytes(int max_steps);
+int mclst_adam_set_step(void* coef_table, int max_steps, int step, double lr, double beta1,
+                        double beta2, double eps, double weight_decay, mclst_stream_t stream);
+int mclst_adam_dense(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     const void* coef_table, int step, mclst_stream_t stream);
+int mclst_adam_lazy_rows(float* table, float* exp_avg, float* exp_avg_sq, int* last_step,
+                         int* first_scratch, int table_rows, int genes, const float* position,
+                         int64_t ld_p, int column, int batch, const float* d_out, int64_t ld_d,
+                         const void* coef_table, int steps_done, uint32_t* error_flag,
+                         mclst_stream_t stream);
+int mclst_adam_lazy_flush(float* table, float* exp_avg, float* exp_avg_sq, int* last_step,
+                          int table_rows, int genes, const void* coef_table, int steps_done,
+                          mclst_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

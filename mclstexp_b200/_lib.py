@@ -84,6 +84,14 @@ def load() -> C.CDLL:
                                            i32, i64, i32, p, p, i32, p]
     lib.mclst_neighbor_distances.argtypes = [p, i64, i64, p, i64, i64, i32, p, i32, i64, i32, p, p]
     lib.mclst_weighted_gather.argtypes = [p, i64, i64, i32, i32, p, p, i64, i32, i64, p, p]
+    f64 = C.c_double
+    lib.mclst_debug_lane_plan.argtypes = [i64, i64, i32, i32, p, i64, C.POINTER(i64), C.POINTER(i32)]
+    lib.mclst_adam_coef_bytes.argtypes = [i32]
+    lib.mclst_adam_coef_bytes.restype = sz
+    lib.mclst_adam_set_step.argtypes = [p, i32, i32, f64, f64, f64, f64, f64, p]
+    lib.mclst_adam_dense.argtypes = [p, p, p, p, i64, p, i32, p]
+    lib.mclst_adam_lazy_rows.argtypes = [p, p, p, p, p, i32, i32, p, i64, i32, i32, p, i64, p, i32, p, p]
+    lib.mclst_adam_lazy_flush.argtypes = [p, p, p, p, i32, i32, p, i32, p]
     for name in header_symbols():
         fn = getattr(lib, name)          # AttributeError if the .so does not export it
         if fn.restype is C.c_int and name not in ("mclst_version",):

@@ -227,7 +227,33 @@ class _EmbedAdd(torch.autograd.Function):
         return (d_out if ctx.needs_input_grad[0] else None), None, dwx, dwy
 
 
+class _EmbedAddLazy(torch.autograd.Function):
+    """Same forward; the backward hands (position, d_out) to the tables' ``optim.LazyEmbeddingAdam``
+    instead of materialising two dense [65536, G] gradients."""
+
+    @staticmethod
+    def forward(ctx, expression, position, x_table, y_table, lazy):
+        out = _EmbedAdd.forward(ctx, expression, position, x_table, y_table)
+        ctx.lazy = lazy
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (position,) = ctx.saved_tensors
+        if int(ctx.err.item()):
+            raise IndexError("position index out of range for x_embed / y_embed (nn.Embedding(65536, dim))")
+        d_out = _c2d(d_out)
+        ctx.lazy.record(position, d_out)
+        return (d_out if ctx.needs_input_grad[0] else None), None, None, None, None
+
+
 def embed_add(expression, position, x_table, y_table, check_range: bool = True):
+    lazy = getattr(x_table, "_mclst_lazy", None)
+    if lazy is not None and lazy is getattr(y_table, "_mclst_lazy", None):
+        # tables owned by optim.LazyEmbeddingAdam: rows about to be read are brought up to date
+        lazy.catch_up(_c2d(position.float()))
+        if torch.is_grad_enabled() and (x_table.requires_grad or y_table.requires_grad):
+            return _EmbedAddLazy.apply(expression, position, x_table, y_table, lazy)
     out = _EmbedAdd.apply(expression, position, x_table, y_table)
     return out
 

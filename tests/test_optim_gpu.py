@@ -1,0 +1,118 @@
+"""Embedding-table Adam (csrc/optim.cu): the dense kernel against
+torch.optim.Adam (train.py:118-120), and the lazy row replay against the dense kernel, bit for bit."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+pytestmark = pytest.mark.gpu
+
+from mclstexp_b200 import model as mm, optim as mo            # noqa: E402
+
+HYPER = dict(lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-3)   # train.py:118-120
+
+
+def test_dense_kernel_matches_torch_adam():
+    torch.manual_seed(0)
+    dev = torch.device("cuda", 0)
+    p0 = torch.randn(777, 33, device=dev) * 0.3
+    ref = nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], **HYPER)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    coef = mo._CoefTable(dev, 64)
+    for step in range(1, 41):
+        g = torch.randn_like(p0) * (0.1 if step % 3 else 0.0)      # some all-zero data gradients
+        ref.grad = g.clone()
+        opt.step()
+        coef.set_step(step, HYPER["lr"], HYPER["betas"], HYPER["eps"], HYPER["weight_decay"])
+        mo.adam_dense_step(p, g, m, v, coef, step)
+    st = opt.state[ref]
+    torch.testing.assert_close(p, ref.data, rtol=2e-6, atol=1e-8)
+    torch.testing.assert_close(m, st["exp_avg"], rtol=1e-5, atol=1e-10)
+    torch.testing.assert_close(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.parametrize("G", [70, 300])
+def test_lazy_rows_equal_dense_bit_for_bit(G):
+    """Rows touched every step, intermittently, or never; duplicate positions inside a batch;
+    every observation point (the rows a batch reads, and everything after flush) must equal the
+    dense run exactly."""
+    torch.manual_seed(1)
+    dev = torch.device("cuda", 0)
+    R, B, steps = 500, 96, 25
+    tabs0 = [torch.randn(R, G, device=dev) * 0.2 for _ in range(2)]
+    lazy_tabs = [nn.Parameter(t.clone()) for t in tabs0]
+    lazy = mo.LazyEmbeddingAdam(lazy_tabs, **HYPER, max_steps=64)
+    dense = [t.clone() for t in tabs0]
+    dm = [torch.zeros_like(t) for t in tabs0]
+    dv = [torch.zeros_like(t) for t in tabs0]
+    coef = mo._CoefTable(dev, 64)
+    rng = np.random.default_rng(3)
+    for step in range(1, steps + 1):
+        hi = 40 if step % 5 else R                      # mostly a small range -> many duplicates
+        pos_np = rng.integers(0, hi, size=(B, 2)).astype(np.float32) + 0.4    # .long() truncates
+        pos = torch.from_numpy(pos_np).to(dev)
+        d_out = torch.randn(B, G, device=dev) * 0.05
+        # observation point 1: the rows this batch reads
+        lazy.catch_up(pos)
+        for i in range(2):
+            rows = pos[:, i].long()
+            assert torch.equal(lazy_tabs[i].data[rows], dense[i][rows]), (step, i)
+        lazy.record(pos, d_out)
+        lazy.step()
+        coef.set_step(step, HYPER["lr"], HYPER["betas"], HYPER["eps"], HYPER["weight_decay"])
+        for i in range(2):
+            g = torch.zeros(R, G, device=dev)
+            rows = pos[:, i].long().tolist()
+            for b, r in enumerate(rows):                # token order, like the kernel
+                g[r] += d_out[b]
+            mo.adam_dense_step(dense[i], g, dm[i], dv[i], coef, step)
+    assert lazy.steps_done == steps
+    # untouched rows are still stale before the flush ...
+    never = sorted(set(range(R)) - set(torch.cat([l.nonzero().flatten() for l in lazy.last]).tolist()))
+    if never:
+        assert not torch.equal(lazy_tabs[0].data[never], dense[0][never])
+    lazy.flush()
+    lazy.check_positions()
+    for i in range(2):
+        assert torch.equal(lazy_tabs[i].data, dense[i])
+        assert torch.equal(lazy.exp_avg[i], dm[i]) and torch.equal(lazy.exp_avg_sq[i], dv[i])
+        assert int(lazy.last[i].min()) == steps
+
+
+def test_training_steps_with_lazy_tables_match_stock_adam():
+    """train.py:36-38 on a small mclSTExp_Attention: TrainOptimizer (stock Adam + lazy tables) against
+    torch.optim.Adam over every parameter with dense table gradients."""
+    dev = torch.device("cuda", 0)
+    G, B = 96, 64
+
+    def build():
+        torch.manual_seed(5)
+        net = mm.mclSTExp_Attention("none", 1.0, 128, G, 64, 2, 16, 1)
+        net.image_encoder = nn.Identity()
+        return net.to(dev)
+
+    ref, new = build(), build()
+    new.load_state_dict(ref.state_dict())
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=1e-3)
+    opt_new = mo.TrainOptimizer(new, lr=1e-3, weight_decay=1e-3)
+    g = torch.Generator(device=dev)
+    g.manual_seed(11)
+    for step in range(6):
+        batch = {"image": torch.randn(B, 128, generator=g, device=dev),
+                 "expression": torch.rand(B, G, generator=g, device=dev),
+                 "position": torch.randint(0, 12 if step % 2 else 60, (B, 2), generator=g, device=dev).float()}
+        losses = []
+        for net, opt in ((ref, opt_ref), (new, opt_new)):
+            opt.zero_grad()
+            loss = net(batch)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        assert abs(losses[0] - losses[1]) <= 1e-4 * abs(losses[0]), (step, losses)
+    assert new.x_embed.weight.grad is None                      # no dense table gradient was built
+    sd_ref, sd_new = ref.state_dict(), new.state_dict()         # state_dict() flushes the tables
+    for k in sd_ref:
+        torch.testing.assert_close(sd_new[k], sd_ref[k], rtol=1e-3, atol=5e-5, msg=k)
+    with pytest.raises(Exception):
+        opt_new.lazy.step()                                      # no gradient recorded
