@@ -241,6 +241,22 @@ def train_step_cfg2(dev):
             net(batch).backward()
         ms = _time_cuda(step, iters=5, warm=2)
         res[f"G{G}"] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms}
+        try:                                   # whole step of train.py:36-38, optimiser included
+            import copy
+            from mclstexp_b200.optim import TrainOptimizer
+            for name in ("stock_adam", "lazy_tables"):
+                net2 = copy.deepcopy(net)
+                opt = (torch.optim.Adam(net2.parameters(), lr=1e-4, weight_decay=1e-3) if name == "stock_adam"
+                       else TrainOptimizer(net2, lr=1e-4, weight_decay=1e-3))
+
+                def full_step():
+                    opt.zero_grad()
+                    net2(batch).backward()
+                    opt.step()
+                res[f"G{G}"][f"with_optimizer_{name}_ms"] = _time_cuda(full_step, iters=5, warm=2)
+                del net2, opt
+        except Exception as e:                 # report, do not hide
+            res[f"G{G}"]["optimizer_error"] = f"{type(e).__name__}: {e}"[:200]
         try:                                   # same step replayed from a CUDA graph
             from mclstexp_b200.graphs import GraphedTrainStep
             gstep = GraphedTrainStep(net, batch)
