@@ -55,12 +55,19 @@ def to_host(*tensors: Optional[torch.Tensor]):
     return [None if h is None else h.numpy() for h in outs]
 
 
+def _from_numpy(x) -> torch.Tensor:
+    a = np.ascontiguousarray(x)
+    if not a.flags.writeable:            # read-only memory maps (io.load_fold): torch wants writable
+        a = a.copy()
+    return torch.from_numpy(a)
+
+
 def _dev_f32(x: ArrayLike, device=None) -> torch.Tensor:
     """What ``torch.tensor(x)`` does at evel_her2st.py:76-77, but onto the GPU."""
     if isinstance(x, torch.Tensor):
         t = x
     else:
-        t = torch.from_numpy(np.ascontiguousarray(x))
+        t = _from_numpy(x)
     if t.dtype != torch.float32:
         t = t.float()
     if not t.is_cuda:
@@ -223,7 +230,7 @@ def retrieve_device(spot_key: torch.Tensor, expression_key: torch.Tensor, image_
 
 
 def _to_dev(x: ArrayLike, device, dtypes=(torch.float32,)) -> torch.Tensor:
-    t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+    t = x if isinstance(x, torch.Tensor) else _from_numpy(x)
     if t.dtype not in dtypes:
         t = t.float()
     return t.to(device, non_blocking=True)
