@@ -227,9 +227,10 @@ class _ShardedLoss(torch.autograd.Function):
 
         def gather_rows(sel):
             loc = stats[sel, row0:row0 + rows].contiguous()
-            full = torch.empty((world, len(sel), rows), dtype=torch.float32, device=S.device)
+            # (output as the dim-0 concatenation of the inputs: the one shape both NCCL and gloo accept)
+            full = torch.empty((world * len(sel), rows), dtype=torch.float32, device=S.device)
             dist.all_gather_into_tensor(full, loc, group=group)
-            stats[sel] = full.permute(1, 0, 2).reshape(len(sel), B)
+            stats[sel] = full.view(world, len(sel), rows).permute(1, 0, 2).reshape(len(sel), B)
 
         phase(1)
         gather_rows([0, 1, 2, 5])

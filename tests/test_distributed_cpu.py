@@ -114,3 +114,118 @@ def test_shard_bounds_cover_everything():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             assert max(e - s for s, e in b) - min(e - s for s, e in b) <= 1
+
+
+# --------------------------------------------------------------------------------------------
+# Row-sharded contrastive loss: the exchange pattern of distributed._ShardedLoss (embedding
+# all-gather, three phases separated by all-gathers of the per-row statistics, loss all-reduce)
+# with the three CUDA phases replaced by a NumPy restatement working on the same raw buffers.
+class _PhaseOracleLib:
+    """Stands in for libmclst_b200.so: mclst_contrastive_loss_phase on host pointers, float64 inside.
+    stats rows: 0 rl, 1 cl, 2 za, 3 wbar, 4 cs, 5 diag (csrc/loss.cu)."""
+
+    @staticmethod
+    def _view(p, n):
+        import ctypes as C
+        addr = p.value if hasattr(p, "value") else int(p)
+        return np.ctypeslib.as_array((C.c_float * n).from_address(addr))
+
+    def mclst_contrastive_loss_workspace_bytes(self, B, D, mode, rows, out):
+        out._obj.value = 256
+        return 0
+
+    def mclst_contrastive_loss_phase(self, s, ld_s, i, ld_i, B, D, T, mode, row0, rows, phase, stats, loss,
+                                     d_s, ld_ds, d_i, ld_di, ws, ws_bytes, stream):
+        S = self._view(s, B * ld_s).reshape(B, ld_s)[:, :D].astype(np.float64)
+        I = self._view(i, B * ld_i).reshape(B, ld_i)[:, :D].astype(np.float64)
+        st = self._view(stats, 6 * B).reshape(6, B)
+        soft = mode != 0
+        a_scale = 0.0 if not soft else (1.0 / (2 * T) if mode == 1 else T / 2.0)
+        loc = slice(row0, row0 + rows)
+
+        def lse(x):
+            m = x.max(1, keepdims=True)
+            return (m + np.log(np.exp(x - m).sum(1, keepdims=True)))[:, 0]
+
+        Lg_loc = S[loc] @ I.T / T                      # Lg[r, j], r local
+        LgT_loc = I[loc] @ S.T / T                     # Lg[j, r] as [r, j]
+        A_loc = (I[loc] @ I.T + S[loc] @ S.T) * a_scale if soft else None
+        if phase == 1:
+            st[0, loc] = lse(Lg_loc)
+            st[1, loc] = lse(LgT_loc)
+            st[5, loc] = Lg_loc[np.arange(rows), np.arange(row0, row0 + rows)]
+            if soft:
+                st[2, loc] = lse(A_loc)
+            return 0
+        rl, cl, za, wbar, cs = (st[k].astype(np.float64) for k in range(5))
+        if phase == 2:
+            Pt = np.exp(A_loc - za[loc, None])
+            st[3, loc] = (Pt * (rl[loc, None] + cl[None, :] - 2 * Lg_loc)).sum(1)
+            st[4, loc] = np.exp(A_loc - za[None, :]).sum(1)
+            return 0
+        term = wbar[loc] if soft else rl[loc] + cl[loc] - 2 * st[5, loc].astype(np.float64)
+        self._view(loss, 1)[0] = term.sum() / (2 * B)
+        if d_s is None or (hasattr(d_s, "value") and not d_s.value):
+            return 0
+        if soft:
+            Pt_rj = np.exp(A_loc - za[loc, None])
+            Pt_jr = np.exp(A_loc - za[None, :])
+            cs_j, cs_r = cs[None, :], cs[loc, None]
+        else:
+            Pt_rj = Pt_jr = (np.arange(row0, row0 + rows)[:, None] == np.arange(B)[None, :]).astype(np.float64)
+            cs_j, cs_r = 1.0, 1.0
+        dLg_rj = (np.exp(Lg_loc - rl[loc, None]) + cs_j * np.exp(Lg_loc - cl[None, :]) - 2 * Pt_rj) / (2 * B)
+        dLg_jr = (np.exp(LgT_loc - rl[None, :]) + cs_r * np.exp(LgT_loc - cl[loc, None]) - 2 * Pt_jr) / (2 * B)
+        dS = dLg_rj @ I / T
+        dI = dLg_jr @ S / T
+        if soft:
+            W_rj = rl[loc, None] + cl[None, :] - 2 * Lg_loc
+            W_jr = rl[None, :] + cl[loc, None] - 2 * LgT_loc
+            sym = (Pt_rj * (W_rj - wbar[loc, None]) + Pt_jr * (W_jr - wbar[None, :])) / (2 * B)
+            dS += sym @ S * a_scale
+            dI += sym @ I * a_scale
+        self._view(d_s, rows * ld_ds).reshape(rows, ld_ds)[:, :D] = dS
+        self._view(d_i, rows * ld_di).reshape(rows, ld_di)[:, :D] = dI
+        return 0
+
+
+def _loss_worker(rank, world, port, targets, out_dir):
+    import contextlib
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mclstexp_b200.distributed as md
+    from mclstexp_b200 import synth
+    md.load = lambda: _PhaseOracleLib()                     # no CUDA in this process
+    md.stream_ptr = lambda: None
+    torch.cuda.device = lambda dev: contextlib.nullcontext()
+    B, D = 128 * world, 32
+    S = torch.from_numpy(synth.embeddings(B, D, 21, "clustered", centres=5) * 0.3)
+    I = torch.from_numpy(synth.embeddings(B, D, 22, "clustered", centres=5) * 0.3)
+    rows = B // world
+    Sl = S[rank * rows:(rank + 1) * rows].clone().requires_grad_(True)
+    Il = I[rank * rows:(rank + 1) * rows].clone().requires_grad_(True)
+    loss = md.contrastive_loss_sharded(Sl, Il, 0.7, targets)
+    (2.0 * loss).backward()                                 # upstream gradient other than 1
+    np.savez(os.path.join(out_dir, f"l{rank}.npz"), loss=loss.detach().numpy(), dS=Sl.grad.numpy(),
+             dI=Il.grad.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("targets", ["eye", "soft"])
+def test_sharded_loss_exchange_pattern_world2(tmp_path, targets):
+    from mclstexp_b200 import synth
+    from oracle import oracle
+    world = 2
+    port = 31500 + (os.getpid() + len(targets)) % 2000
+    mp.spawn(_loss_worker, args=(world, port, targets, str(tmp_path)), nprocs=world, join=True)
+    B, D = 128 * world, 32
+    S = synth.embeddings(B, D, 21, "clustered", centres=5) * 0.3
+    I = synth.embeddings(B, D, 22, "clustered", centres=5) * 0.3
+    loss, dS, dI = oracle.contrastive_loss_closed_form(S, I, 0.7, targets)
+    rows = B // world
+    for r in range(world):
+        z = np.load(os.path.join(tmp_path, f"l{r}.npz"))
+        assert abs(float(z["loss"]) - loss) <= 1e-5 * abs(loss)           # same value on every rank
+        np.testing.assert_allclose(z["dS"], 2.0 * dS[r * rows:(r + 1) * rows], rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(z["dI"], 2.0 * dI[r * rows:(r + 1) * rows], rtol=2e-4, atol=1e-7)
