@@ -229,3 +229,56 @@ def test_sharded_loss_exchange_pattern_world2(tmp_path, targets):
         assert abs(float(z["loss"]) - loss) <= 1e-5 * abs(loss)           # same value on every rank
         np.testing.assert_allclose(z["dS"], 2.0 * dS[r * rows:(r + 1) * rows], rtol=2e-4, atol=1e-7)
         np.testing.assert_allclose(z["dI"], 2.0 * dI[r * rows:(r + 1) * rows], rtol=2e-4, atol=1e-7)
+
+
+# --------------------------------------------------------------------------------------------
+# 2-D decomposition (query groups x bank shards) with per-group process groups, world size 4.
+def _grid_worker(rank, world, port, bank_shards, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mclstexp_b200 import synth
+    from mclstexp_b200.distributed import BankShard, make_retrieval_grid, retrieve_sharded
+    N, Q, D, G, k = 403, 37, 48, 9, 11
+    bank = torch.from_numpy(synth.embeddings(N, D, 15, "clustered"))
+    expr = torch.from_numpy(synth.expression(N, G, 16))
+    qry = torch.from_numpy(synth.embeddings(Q, D, 17, "clustered"))
+    grid = make_retrieval_grid(bank_shards, world, rank)
+    assert grid.query_groups * grid.bank_shards == world
+    assert (grid.q_index, grid.b_index) == (rank // bank_shards, rank % bank_shards)
+    shard = BankShard.from_full(bank, expr, grid.b_index, grid.bank_shards)
+    q0, q1 = grid.query_slice(Q)
+    idx, val, _, ex = retrieve_sharded(shard, qry[q0:q1].contiguous(), k, "inv_sq_l2", group=grid.group,
+                                       backend=OracleBackend())
+    np.savez(os.path.join(out_dir, f"g{rank}.npz"), idx=idx.numpy(), val=val.numpy(), ex=ex.numpy(),
+             q0=q0, q1=q1)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bank_shards", [1, 2, 4])
+def test_retrieval_grid_world4(tmp_path, bank_shards):
+    from mclstexp_b200 import synth
+    from mclstexp_b200.distributed import make_retrieval_grid
+    from oracle import oracle
+    world = 4
+    port = 33500 + (os.getpid() + 7 * bank_shards) % 2000
+    mp.spawn(_grid_worker, args=(world, port, bank_shards, str(tmp_path)), nprocs=world, join=True)
+    N, Q, D, G, k = 403, 37, 48, 9, 11
+    bank = synth.embeddings(N, D, 15, "clustered")
+    expr = synth.expression(N, G, 16)
+    qry = synth.embeddings(Q, D, 17, "clustered")
+    sval, sidx = oracle.find_matches_spec(bank, qry, k)
+    _, ex64 = oracle.weighted_average_spec(bank, expr, qry, sidx, "inv_sq_l2", sval)
+    covered = np.zeros(Q, dtype=np.int32)
+    for r in range(world):
+        z = np.load(os.path.join(tmp_path, f"g{r}.npz"))
+        q0, q1 = int(z["q0"]), int(z["q1"])
+        np.testing.assert_array_equal(z["idx"], sidx[q0:q1])
+        np.testing.assert_array_equal(z["val"], sval[q0:q1])
+        np.testing.assert_allclose(z["ex"], ex64[q0:q1], rtol=1e-4, atol=1e-6)
+        if r % bank_shards == 0:
+            covered[q0:q1] += 1
+    assert (covered == 1).all()                    # the query groups tile the queries exactly once
+    with pytest.raises(ValueError):
+        make_retrieval_grid(3, 4, 0)
