@@ -1,8 +1,8 @@
 """The body of the reference's fold loop as one call: load the held-out slide and the bank from the
-reference's on-disk layout, retrieve, score (evel_her2st.py:147-221; evel_visium.py:165-239;
+reference's on-disk layout, retrieve, score (evel_her2st.py:145-221; evel_visium.py:165-239;
 evel_cscc.py:168-250 differ only in the dataset paths, top-k and the L1 / L2 distance).
 
-    for fold in range(32):                                       # evel_her2st.py:147
+    for fold in range(32):                                       # evel_her2st.py:143
         scores = evaluate_fold(f"./embedding_result/her2st_result/embeddings_{fold}/",
                                expression_paths, fold, top_k=200, p=1)
 
@@ -23,7 +23,7 @@ def evaluate_fold(embedding_dir: str, expression_paths: Sequence[str], fold: int
                   p: int = 2, mode: Optional[str] = None, dim: int = 256, top_genes: int = 50,
                   return_prediction: bool = False) -> Dict[str, object]:
     """{'heg_pcc', 'hvg_pcc', 'mse', 'mae'} of held-out slide ``fold`` (+ 'indices', 'expr_pred',
-    'emb_pred' with ``return_prediction``): evel_her2st.py:149-221."""
+    'emb_pred' with ``return_prediction``): evel_her2st.py:145-221."""
     fd = mio.load_fold(embedding_dir, expression_paths, fold, dim=dim)
     if fd.n_total < top_k:
         raise ValueError(f"bank of {fd.n_total} spots is smaller than top_k={top_k}")

@@ -6,8 +6,8 @@ Reference layout (paths relative to /root/reference):
     fold directory, ``img_embeddings_{i+1}.npy`` and ``spot_embeddings_{i+1}.npy`` for slide i,
     each TRANSPOSED: ``[256, n_i]`` float32;
   * ``preprocessed_matrix.npy`` per slide is ``[G, n_i]`` (hvg_her2st.py:123; read at
-    evel_her2st.py:126-137);
-  * the fold loop (evel_her2st.py:147-172) drops slide ``fold`` from the bank, concatenates the
+    evel_her2st.py:126-127, :136-137);
+  * the fold loop (evel_her2st.py:145-172) drops slide ``fold`` from the bank, concatenates the
     rest along axis 1, and transposes whatever does not already have 256 columns / matching rows.
 
 ``load_fold`` reproduces that result; with ``rank``/``world`` it materialises only this rank's
@@ -37,7 +37,7 @@ class FoldData:
 
 def save_fold_embeddings(save_path: str, img_embeddings_all: np.ndarray, spot_embeddings_all: np.ndarray,
                          datasize: Sequence[int]) -> None:
-    """The file layout of ``save_embeddings`` (evel_her2st.py:108-117): rows
+    """The file layout of ``save_embeddings`` (evel_her2st.py:109-117): rows
     ``sum(datasize[:i]) .. sum(datasize[:i+1])`` of both arrays go to slide i+1's files, transposed."""
     img = np.asarray(img_embeddings_all)
     spot = np.asarray(spot_embeddings_all)
@@ -74,7 +74,7 @@ def slide_sizes(expression_paths: Sequence[str]) -> List[int]:
 def load_fold(embedding_dir: str, expression_paths: Sequence[str], fold: int, dim: int = 256,
               rank: int = 0, world: int = 1, mmap: bool = True,
               expression_dtype: Optional[np.dtype] = None) -> FoldData:
-    """Everything the fold-loop body needs (evel_her2st.py:147-172) for held-out slide ``fold``
+    """Everything the fold-loop body needs (evel_her2st.py:145-172) for held-out slide ``fold``
     (0-based, like the reference's loop variable).
 
     embedding_dir     directory holding ``spot_embeddings_{i+1}.npy`` / ``img_embeddings_{i+1}.npy``

@@ -354,9 +354,63 @@ def golden_metrics():
     print("metrics.npz:", len(out), "arrays")
 
 
+IO_SIZES = [5 + (7 * i) % 13 for i in range(32)]          # spots per slide (32 her2st slides)
+IO_GENES = 24
+
+
+def io_inputs():
+    """Seeded stand-ins for what the fold loop reads from disk: all image / spot embeddings
+    (rows in slide order) and one [G, n_i] expression matrix per slide."""
+    n = sum(IO_SIZES)
+    img = synth.embeddings(n, 256, 301, "iid")
+    spot = synth.embeddings(n, 256, 302, "iid")
+    expr = synth.expression(n, IO_GENES, 303).astype(np.float64)
+    mats, start = [], 0
+    for s in IO_SIZES:
+        mats.append(np.ascontiguousarray(expr[start:start + s].T))
+        start += s
+    return img, spot, mats
+
+
+def golden_io():
+    """The reference's own writer loop (evel_her2st.py:109-117) and fold-loop loading code
+    (:145-172) executed verbatim in a scratch directory (their paths are relative); the fixture
+    keeps SHA-256 digests and shapes of the four arrays they produce."""
+    import hashlib
+    import tempfile
+    img, spot, mats = io_inputs()
+    names = [f"S{i:02d}" for i in range(32)]
+    writer = lift_statements("evel_her2st.py", 109, 117)
+    loader = lift_statements("evel_her2st.py", 145, 172)
+    out, cwd = {}, os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            for fold in (0, 17, 31):
+                save_path = f"./embedding_result/her2st_result/embeddings_{fold}/"
+                os.makedirs(save_path)
+                quiet_exec(writer, {"np": np, "datasize": IO_SIZES, "img_embeddings_all": img,
+                                    "spot_embeddings_all": spot, "save_path": save_path})
+                ns = {"np": np, "os": os, "fold": fold, "names": names, "spot_expressions": list(mats)}
+                quiet_exec(loader, ns)
+                for key in ("spot_key", "expression_key", "image_query", "expression_gt"):
+                    a = np.ascontiguousarray(ns[key])
+                    out[f"{fold}/{key}"] = dict(shape=list(a.shape), dtype=str(a.dtype),
+                                                sha256=hashlib.sha256(a.tobytes()).hexdigest())
+        finally:
+            os.chdir(cwd)
+    with open(os.path.join(OUT, "io.json"), "w") as f:
+        json.dump({"sizes": IO_SIZES, "genes": IO_GENES, "arrays": out}, f, indent=1)
+    print("io.json:", len(out), "digests")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--io-only" in sys.argv:
+        golden_io()
+        sys.exit(0)
     if "--metrics-only" not in sys.argv:
         golden_retrieval()
         golden_model()
     golden_metrics()
+    golden_io()

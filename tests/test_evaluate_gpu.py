@@ -1,5 +1,5 @@
 """The whole fold-loop body from files (io.load_fold -> retrieval.retrieve -> metrics.evaluate) against
-the oracle pipeline on the same temporary files (evel_her2st.py:147-221)."""
+the oracle pipeline on the same temporary files (evel_her2st.py:145-221)."""
 import os
 
 import numpy as np

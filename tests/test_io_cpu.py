@@ -27,7 +27,7 @@ def _make_files(tmp_path, sizes, genes, dim=256, seed=0, expr_dtype=np.float64):
 
 
 def _reference_fold(emb_dir, paths, fold):
-    """evel_her2st.py:137-172 restated (paths instead of the hard-coded directories)."""
+    """evel_her2st.py:136-172 restated (paths instead of the hard-coded directories)."""
     n_slides = len(paths)
     spot_expressions = [np.load(p) for p in paths]
     spot_embeddings = [np.load(os.path.join(emb_dir, f"spot_embeddings_{i + 1}.npy")) for i in range(n_slides)]
@@ -98,3 +98,32 @@ def test_row_major_files_and_errors(tmp_path):
         mio.load_fold(emb_dir, paths, 0)
     with pytest.raises(ValueError):
         mio.save_fold_embeddings(emb_dir, img_all, spot_all, [30, 41])
+
+
+def test_writer_and_loader_match_reference_executed_digests(tmp_path):
+    """tests/golden/io.json: SHA-256 digests of the four arrays the reference's OWN writer loop
+    (evel_her2st.py:109-117) and fold-loop loading code (:145-172) produce, executed verbatim by
+    oracle/make_golden.py on seeded inputs.  Our writer + loader must reproduce them byte for byte."""
+    import hashlib
+    import json
+    from oracle import make_golden                            # only io_inputs(): the seeded inputs
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "io.json")) as f:
+        gold = json.load(f)
+    img, spot, mats = make_golden.io_inputs()
+    assert gold["sizes"] == make_golden.IO_SIZES and gold["genes"] == make_golden.IO_GENES
+    paths = []
+    for i, m in enumerate(mats):
+        d = os.path.join(str(tmp_path), f"slide{i}")
+        os.makedirs(d)
+        np.save(os.path.join(d, "preprocessed_matrix.npy"), m)
+        paths.append(os.path.join(d, "preprocessed_matrix.npy"))
+    for fold in (0, 17, 31):
+        emb_dir = os.path.join(str(tmp_path), f"embeddings_{fold}")
+        mio.save_fold_embeddings(emb_dir, img, spot, gold["sizes"])
+        fd = mio.load_fold(emb_dir, paths, fold)
+        for key in ("spot_key", "expression_key", "image_query", "expression_gt"):
+            a = np.ascontiguousarray(getattr(fd, key))
+            ref = gold["arrays"][f"{fold}/{key}"]
+            assert list(a.shape) == ref["shape"] and str(a.dtype) == ref["dtype"], (fold, key)
+            assert hashlib.sha256(a.tobytes()).hexdigest() == ref["sha256"], (fold, key)
