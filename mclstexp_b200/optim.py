@@ -149,7 +149,8 @@ class LazyEmbeddingAdam:
 class TrainOptimizer:
     """``torch.optim.Adam`` (stock) for every parameter except the position tables, which go to
     ``LazyEmbeddingAdam`` with the same hyper-parameters; the calls of train.py:36-38 unchanged.
-    ``model.state_dict()`` flushes the tables first."""
+    ``model.state_dict()`` and direct calls of ``model.x_embed`` / ``model.y_embed`` flush the tables
+    first; the model's own forward only catches up the rows it reads."""
 
     def __init__(self, model: nn.Module, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-3):
@@ -159,6 +160,10 @@ class TrainOptimizer:
         self.dense = torch.optim.Adam(rest, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         self.lazy = LazyEmbeddingAdam(tables, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         model.register_state_dict_pre_hook(lambda module, prefix, keep_vars: self.lazy.flush())
+        # reference-style evaluation calls the embedding modules directly (evel_her2st.py:52-57:
+        # ``model.x_embed(x)``), bypassing embed_add's per-row catch-up: bring everything current first
+        for emb in (model.x_embed, model.y_embed):
+            emb.register_forward_pre_hook(lambda module, args: self.lazy.flush())
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         self.dense.zero_grad(set_to_none=set_to_none)
