@@ -111,6 +111,12 @@ def test_training_steps_with_lazy_tables_match_stock_adam():
             losses.append(float(loss.detach()))
         assert abs(losses[0] - losses[1]) <= 1e-4 * abs(losses[0]), (step, losses)
     assert new.x_embed.weight.grad is None                      # no dense table gradient was built
+    # reference-style eval calls the embedding modules directly (evel_her2st.py:52-57): the
+    # forward pre-hook flushes the deferred rows first, including rows no batch ever touched
+    rows = torch.arange(0, 200, device=dev)
+    assert int(opt_new.lazy.last[0][150:200].max()) < opt_new.lazy.steps_done      # still stale
+    torch.testing.assert_close(new.x_embed(rows), ref.x_embed(rows), rtol=1e-3, atol=5e-5)
+    assert int(opt_new.lazy.last[0].min()) == opt_new.lazy.steps_done
     sd_ref, sd_new = ref.state_dict(), new.state_dict()         # state_dict() flushes the tables
     for k in sd_ref:
         torch.testing.assert_close(sd_new[k], sd_ref[k], rtol=1e-3, atol=5e-5, msg=k)
