@@ -478,3 +478,46 @@ def make_state_dict(G: int, E: int = 1024, P: int = 256, heads: int = 8, dim_hea
         sd[name + "layer_norm.weight"] = vec(P, 0.1, 1.0)
         sd[name + "layer_norm.bias"] = vec(P, 0.1)
     return sd
+
+
+# --------------------------------------------------------------------------
+# Adam on the position tables (train.py:118-120)
+# --------------------------------------------------------------------------
+
+
+def adam_step_ref(p, g, m, v, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-3):
+    """One step of torch.optim.Adam (L2 weight decay, no amsgrad) on float32 arrays, in the
+    operation order of torch/optim/adam.py::_single_tensor_adam -- the order csrc/optim.cu follows.
+    Returns the new (p, m, v)."""
+    f32 = np.float32
+    p, g, m, v = (np.asarray(a, dtype=f32) for a in (p, g, m, v))
+    b1, b2 = betas
+    g = g + f32(weight_decay) * p                                  # grad.add(param, alpha=wd)
+    m = m + (g - m) * f32(1.0 - b1)                                # exp_avg.lerp_(grad, 1 - beta1)
+    v = v * f32(b2) + f32(1.0 - b2) * g * g                        # mul_(beta2).addcmul_(grad, grad, 1-beta2)
+    bc1 = 1.0 - b1 ** step
+    bc2 = 1.0 - b2 ** step
+    step_size = lr / bc1
+    denom = np.sqrt(v) / f32(bc2 ** 0.5) + f32(eps)
+    p = p + f32(-step_size) * (m / denom)                          # addcdiv_(exp_avg, denom, value=-step_size)
+    return p.astype(f32), m.astype(f32), v.astype(f32)
+
+
+def adam_lazy_rows_ref(table, m, v, last, rows, row_grads, step, **hyper):
+    """The deferral of optim.LazyEmbeddingAdam restated on the host: bring ``rows`` (distinct) from
+    ``last[row]`` to ``step - 1`` with a zero data gradient, then apply ``step`` with ``row_grads``.
+    Operates in place on float32 arrays; ``last`` is an int array of steps applied per row."""
+    for r, g in zip(rows, row_grads):
+        pr, mr, vr = table[r], m[r], v[r]
+        for s in range(int(last[r]) + 1, step):
+            pr, mr, vr = adam_step_ref(pr, np.zeros_like(pr), mr, vr, s, **hyper)
+        pr, mr, vr = adam_step_ref(pr, g, mr, vr, step, **hyper)
+        table[r], m[r], v[r], last[r] = pr, mr, vr, step
+
+
+def adam_lazy_flush_ref(table, m, v, last, step, **hyper):
+    for r in range(table.shape[0]):
+        pr, mr, vr = table[r], m[r], v[r]
+        for s in range(int(last[r]) + 1, step + 1):
+            pr, mr, vr = adam_step_ref(pr, np.zeros_like(pr), mr, vr, s, **hyper)
+        table[r], m[r], v[r], last[r] = pr, mr, vr, step
