@@ -14,9 +14,16 @@
 //                   cp.async.bulk into a 4-stage ring, warp 1 issues tcgen05.mma, warps 2-5
 //                   run the epilogue out of TMEM (alpha, bias, exact-erf GELU, residual).
 //
-// Operand scale: fp16 overflows at 65504.  Operands on this path are LayerNorm outputs,
-// embeddings, probabilities and gradients thereof (|x| << 1e4); pack_split saturates and
-// flags anything larger so the caller can fail loudly instead of returning inf.
+// Operand scale: fp16 has a 5-bit exponent (overflow at 65504, subnormal below 6.1e-5), so every
+// operand is brought to the top of that range with an EXACT power-of-two factor before the split
+// and the factor is undone in the epilogue:
+//   * generic matmul: one factor per operand row (its largest |x| lands in [1, 2)), found by the
+//     pack kernel itself; the epilogue multiplies element (m, n) by inv_a[m] * inv_b[n];
+//   * operands that are concatenated along K or shared between products (the loss): one factor for
+//     the whole tensor, derived by every consumer from a device-side max|x| word (amax_bits).
+// Anything smaller than 2^-25 of its row's largest entry is lost, i.e. the error stays relative to
+// the row scale at fp32 level whatever the magnitude of the data (1e-30 .. 1e+30).  Non-finite
+// inputs are not scaled and propagate as inf/NaN exactly as in an fp32 product.
 #include <algorithm>
 #include <cstdlib>
 #include "common.cuh"
@@ -28,20 +35,57 @@ namespace mclst {
 using namespace ptx;
 
 // ============================================================================ pack_split
+// power-of-two factor 2^(1-e) that maps amax = m * 2^e (m in [0.5, 1)) into [1, 2); 1 for zero or
+// non-finite amax.  *inv receives the exact inverse.
+__device__ __forceinline__ float pow2_scale(float amax, float* inv) {
+  if (!(amax > 0.f) || !(amax < INFINITY)) { *inv = 1.f; return 1.f; }
+  int e;
+  frexpf(amax, &e);
+  e = max(-125, min(126, e));
+  *inv = ldexpf(1.f, e - 1);
+  return ldexpf(1.f, 1 - e);
+}
+__device__ __forceinline__ void split8(const float (&v)[8], uint4* h, uint4* l) {
+  uint32_t hh[4], ll[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half a = __float2half_rn(v[2 * i]), b = __float2half_rn(v[2 * i + 1]);
+    const __half al = __float2half_rn(v[2 * i] - __half2float(a));
+    const __half bl = __float2half_rn(v[2 * i + 1] - __half2float(b));
+    hh[i] = (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+    ll[i] = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
+  }
+  *h = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+  *l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+}
+
 // Non-transposed: out row r = in row r, K index = in column.  One warp per row.
+// inv_scale != null: per-row factor (computed here, inverse stored); else amax_bits != null: the
+// tensor-wide factor; else none.
 __global__ void __launch_bounds__(256)
 pack_split_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
                   float scale, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
                   int64_t rows_pad, int nkb_total, int kb_offset, int nkb_mine,
-                  uint32_t* __restrict__ flags, int64_t x_batch, size_t out_batch) {
+                  const uint32_t* __restrict__ amax_bits, float* __restrict__ inv_scale,
+                  int64_t x_batch, size_t out_batch) {
   x += (int64_t)blockIdx.z * x_batch;
   hi += (size_t)blockIdx.z * out_batch;
   if (lo) lo += (size_t)blockIdx.z * out_batch;
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows_pad) return;
+  float inv = 1.f;
+  if (inv_scale) {
+    float amax = 0.f;
+    if (r < rows)
+      for (int64_t k = lane; k < cols; k += 32) amax = fmaxf(amax, fabsf(__ldg(x + r * ld + k)));
+    amax = warp_max(amax);
+    scale *= pow2_scale(amax, &inv);
+    if (lane == 0) inv_scale[(size_t)blockIdx.z * rows_pad + r] = inv;
+  } else if (amax_bits) {
+    scale *= pow2_scale(__uint_as_float(__ldg(amax_bits)), &inv);
+  }
   const int nchunks = nkb_mine * 8;
-  bool bad = false;
   for (int c = lane; c < nchunks; c += 32) {
     float v[8];
 #pragma unroll
@@ -49,38 +93,46 @@ pack_split_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64
       const int64_t k = (int64_t)c * 8 + i;
       v[i] = (r < rows && k < cols) ? __ldg(x + r * ld + k) * scale : 0.f;
     }
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const __half a = __float2half_rn(v[2 * i]), b = __float2half_rn(v[2 * i + 1]);
-      const __half al = __float2half_rn(v[2 * i] - __half2float(a));
-      const __half bl = __float2half_rn(v[2 * i + 1] - __half2float(b));
-      bad |= !(fabsf(v[2 * i]) <= 65000.f) || !(fabsf(v[2 * i + 1]) <= 65000.f);
-      h[i] = (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-      l[i] = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
-    }
+    uint4 h, l;
+    split8(v, &h, &l);
     const size_t off = tilepack_chunk_offset(r, kb_offset * 8 + c, nkb_total);
-    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    if (lo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    if (lo) *reinterpret_cast<uint4*>(lo + off) = l;
   }
-  if (bad) atomicOr(flags, 1u);
 }
 
 // Transposed: out row r = in column r, K index = in row.  Lane <-> out row (contiguous in
 // the input), each thread gathers 8 consecutive K (8 input rows) for one 16-byte chunk.
+// With inv_scale the block first scans its 32 columns for their max|x| (gridDim.y must be 1).
 __global__ void __launch_bounds__(256)
 pack_split_t_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
                     float scale, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
                     int64_t out_rows_pad, int nkb_total, int kb_offset, int nkb_mine,
-                    uint32_t* __restrict__ flags, int64_t x_batch, size_t out_batch) {
+                    const uint32_t* __restrict__ amax_bits, float* __restrict__ inv_scale,
+                    int64_t x_batch, size_t out_batch) {
+  __shared__ float s_amax[8][32];
   x += (int64_t)blockIdx.z * x_batch;
   hi += (size_t)blockIdx.z * out_batch;
   if (lo) lo += (size_t)blockIdx.z * out_batch;
-  const int64_t r = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);      // out row = in column
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 32 + lane;                    // out row = in column
   const int cgroup = threadIdx.x >> 5;                                  // 8 chunk lanes per block
+  float inv = 1.f;
+  if (inv_scale) {
+    float amax = 0.f;
+    if (r < cols)
+      for (int64_t k = cgroup; k < rows; k += 8) amax = fmaxf(amax, fabsf(__ldg(x + k * ld + r)));
+    s_amax[cgroup][lane] = amax;
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < 8; ++g) amax = fmaxf(amax, s_amax[g][lane]);
+    scale *= pow2_scale(amax, &inv);
+    if (cgroup == 0 && r < out_rows_pad) inv_scale[(size_t)blockIdx.z * out_rows_pad + r] = inv;
+  } else if (amax_bits) {
+    scale *= pow2_scale(__uint_as_float(__ldg(amax_bits)), &inv);
+  }
   if (r >= out_rows_pad) return;
   const int nchunks = nkb_mine * 8;
-  bool bad = false;
   for (int c = blockIdx.y * 8 + cgroup; c < nchunks; c += gridDim.y * 8) {
     float v[8];
 #pragma unroll
@@ -88,38 +140,53 @@ pack_split_t_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int
       const int64_t k = (int64_t)c * 8 + i;                             // in row
       v[i] = (r < cols && k < rows) ? __ldg(x + k * ld + r) * scale : 0.f;
     }
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const __half a = __float2half_rn(v[2 * i]), b = __float2half_rn(v[2 * i + 1]);
-      const __half al = __float2half_rn(v[2 * i] - __half2float(a));
-      const __half bl = __float2half_rn(v[2 * i + 1] - __half2float(b));
-      bad |= !(fabsf(v[2 * i]) <= 65000.f) || !(fabsf(v[2 * i + 1]) <= 65000.f);
-      h[i] = (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-      l[i] = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
-    }
+    uint4 h, l;
+    split8(v, &h, &l);
     const size_t off = tilepack_chunk_offset(r, kb_offset * 8 + c, nkb_total);
-    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    if (lo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    if (lo) *reinterpret_cast<uint4*>(lo + off) = l;
   }
-  if (bad) atomicOr(flags, 1u);
+}
+
+// max|x| of a tensor as the bit pattern of a non-negative float (orders like an unsigned integer);
+// *out must be zeroed by the caller.  NaNs are ignored (fmaxf), +-inf is kept.
+__global__ void __launch_bounds__(256)
+amax_bits_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                 uint32_t* __restrict__ out) {
+  float amax = 0.f;
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    amax = fmaxf(amax, fabsf(__ldg(x + r * ld + c)));
+  }
+  amax = warp_max(amax);
+  if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(out, __float_as_uint(amax));
+}
+
+int launch_amax_bits(const float* x, int64_t rows, int64_t cols, int64_t ld, uint32_t* out, cudaStream_t st) {
+  const int64_t total = rows * cols;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 256 * 8), (int64_t)sm_count() * 8));
+  amax_bits_kernel<<<grid, 256, 0, st>>>(x, rows, cols, ld, out);
+  MCLST_LAUNCH_CHECK();
+  return 0;
 }
 
 int launch_pack_split(const float* x, int64_t rows, int64_t cols, int64_t ld, bool transpose,
                       float scale, const PackedOperand& dst, int kb_offset, int nkb_mine,
-                      uint32_t* flags, cudaStream_t st, int batch, int64_t x_batch_elems) {
+                      const uint32_t* amax_bits, float* inv_scale, cudaStream_t st, int batch,
+                      int64_t x_batch_elems) {
   if (!transpose) {
     const int wpb = 8;
     dim3 grid((unsigned)ceil_div(dst.rows_pad, wpb), 1, (unsigned)batch);
     pack_split_kernel<<<grid, wpb * 32, 0, st>>>(x, rows, cols, ld, scale, dst.hi, dst.lo,
-                                                 dst.rows_pad, dst.nkb, kb_offset, nkb_mine, flags,
-                                                 x_batch_elems, dst.bytes);
+                                                 dst.rows_pad, dst.nkb, kb_offset, nkb_mine, amax_bits,
+                                                 inv_scale, x_batch_elems, dst.bytes);
   } else {
-    dim3 grid((unsigned)ceil_div(dst.rows_pad, 32), (unsigned)std::min<int64_t>(64, nkb_mine),
+    dim3 grid((unsigned)ceil_div(dst.rows_pad, 32), inv_scale ? 1u : (unsigned)std::min<int64_t>(64, nkb_mine),
               (unsigned)batch);
     pack_split_t_kernel<<<grid, 256, 0, st>>>(x, rows, cols, ld, scale, dst.hi, dst.lo,
-                                              dst.rows_pad, dst.nkb, kb_offset, nkb_mine, flags,
-                                              x_batch_elems, dst.bytes);
+                                              dst.rows_pad, dst.nkb, kb_offset, nkb_mine, amax_bits,
+                                              inv_scale, x_batch_elems, dst.bytes);
   }
   MCLST_LAUNCH_CHECK();
   return 0;
@@ -252,6 +319,12 @@ gemm_tn_kernel(const GemmParams p) {
     const bool vec_ok = (p.ldc % 4 == 0) && ((uintptr_t)p.c % 16 == 0) && (p.c_batch_elems % 4 == 0) &&
                         (!p.residual || (uintptr_t)p.residual % 16 == 0);
     const int sub = lane >> 3, c4 = lane & 7;              // store phase: row it*4+sub, columns c4*4..+3
+    float alpha = p.alpha;
+    if (p.amax_bits) {                                     // undo the tensor-wide operand factor(s)
+      float inv;
+      pow2_scale(__uint_as_float(__ldg(p.amax_bits)), &inv);
+      alpha *= (p.amax_pow == 2) ? inv * inv : inv;
+    }
     int n = 0;
     for (int64_t g = g0; g < groups; g += gstep, ++n) {
       const int mb = (int)(g % mg) * CL + (int)crank;
@@ -260,6 +333,10 @@ gemm_tn_kernel(const GemmParams p) {
       const int64_t m0 = (int64_t)mb * GM_BM + quad * 32;
       float* cbase = p.c + (size_t)z * p.c_batch_elems;
       const float* rbase = p.residual ? p.residual + (size_t)z * p.c_batch_elems : nullptr;
+      float rs[8];                                         // alpha * per-row operand factor of my 8 store rows
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        rs[it] = alpha * ((p.a_scale && mb < mt) ? __ldg(p.a_scale + (size_t)z * p.a_scale_batch + m0 + it * 4 + sub) : 1.f);
       mbar_wait(&bar_tfull[buf], (n >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * GM_BN;
@@ -278,10 +355,14 @@ gemm_tn_kernel(const GemmParams p) {
         __syncwarp();
         const int64_t col = n0 + c * 32 + c4 * 4;
         const bool full4 = vec_ok && col + 4 <= p.N;
-        float bias[4] = {0.f, 0.f, 0.f, 0.f};
+        float bias[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {1.f, 1.f, 1.f, 1.f};
         if (p.bias) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) if (col + i < p.N) bias[i] = __ldg(p.bias + col + i);
+        }
+        if (p.b_scale) {                                   // (padded to 256 rows: always in bounds)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cs[i] = __ldg(p.b_scale + (size_t)z * p.b_scale_batch + col + i);
         }
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
@@ -289,8 +370,9 @@ gemm_tn_kernel(const GemmParams p) {
           const float4 t = tile[row * 8 + (c4 ^ (row & 7))];
           const int64_t m = m0 + row;
           if (m >= p.M) continue;
-          float o[4] = {t.x * p.alpha + bias[0], t.y * p.alpha + bias[1], t.z * p.alpha + bias[2],
-                        t.w * p.alpha + bias[3]};
+          const float ra = rs[it];
+          float o[4] = {t.x * (ra * cs[0]) + bias[0], t.y * (ra * cs[1]) + bias[1],
+                        t.z * (ra * cs[2]) + bias[2], t.w * (ra * cs[3]) + bias[3]};
           if (p.act == 1) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] = gelu_erf(o[i]);
@@ -356,6 +438,7 @@ int launch_gemm_tn(const GemmParams& p, cudaStream_t st) {
   MCLST_REQUIRE(p.nseg == 1 || (p.a_lo && p.b_lo), MCLST_ERR_INVALID, "gemm: split needs lo parts");
   GemmParams q = p;
   q.batch = std::max(1, p.batch);
+  prof_mark(st, "gemm_tn");
   static const int force = [] { const char* e = getenv("MCLST_GEMM_CLUSTER"); return e ? atoi(e) : 0; }();
   const int64_t tiles = ceil_div(p.M, GM_BM) * ceil_div(p.N, GM_BN) * q.batch;
   // pairs pay off once the grid is saturated and there are at least two row tiles to pair
@@ -372,11 +455,13 @@ size_t packed_operand_bytes(int64_t rows, int64_t k, bool is_b, int64_t* rows_pa
   return (size_t)rp * kb * TP_K * 2;
 }
 
-PackedOperand take_operand(Arena& a, int64_t rows, int64_t k, bool is_b, bool split, int batch) {
+PackedOperand take_operand(Arena& a, int64_t rows, int64_t k, bool is_b, bool split, int batch,
+                           bool row_scaled) {
   PackedOperand o{};
   o.bytes = packed_operand_bytes(rows, k, is_b, &o.rows_pad, &o.nkb);
   o.hi = a.take<uint8_t>(o.bytes * batch);
   o.lo = split ? a.take<uint8_t>(o.bytes * batch) : nullptr;
+  o.inv_scale = row_scaled ? a.take<float>((size_t)o.rows_pad * batch) : nullptr;
   return o;
 }
 
@@ -390,9 +475,8 @@ extern "C" int mclst_matmul_workspace_bytes(int64_t M, int64_t N, int64_t K, int
   MCLST_REQUIRE(bytes && M > 0 && N > 0 && K > 0 && batch >= 1, MCLST_ERR_INVALID,
                 "matmul_workspace: bad args");
   Arena a(nullptr, 0);
-  a.take<uint32_t>(16);
-  take_operand(a, M, K, false, true, batch);
-  take_operand(a, N, K, true, true, batch);
+  take_operand(a, M, K, false, true, batch, true);
+  take_operand(a, N, K, true, true, batch, true);
   *bytes = align_up(a.off, 256);
   return 0;
 }
@@ -407,24 +491,24 @@ extern "C" int mclst_matmul(const float* A, int64_t lda, int a_trans, int64_t a_
   MCLST_REQUIRE(M > 0 && N > 0 && K > 0 && batch >= 1, MCLST_ERR_INVALID, "matmul: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   Arena a(workspace, workspace_bytes);
-  uint32_t* flags = a.take<uint32_t>(16);
-  PackedOperand pa = take_operand(a, M, K, false, true, batch);
-  PackedOperand pb = take_operand(a, N, K, true, true, batch);
+  PackedOperand pa = take_operand(a, M, K, false, true, batch, true);
+  PackedOperand pb = take_operand(a, N, K, true, true, batch, true);
   MCLST_REQUIRE(a.ok(), MCLST_ERR_WORKSPACE, "matmul: workspace too small");
   int rc;
   prof_mark(st, "pack_split");
   // a_trans: A is stored [K, M] (operand rows are its columns); likewise b_trans: B stored [K, N]
   if ((rc = launch_pack_split(A, a_trans ? K : M, a_trans ? M : K, lda, a_trans != 0, 1.f, pa, 0,
-                              pa.nkb, flags, st, batch, a_batch_stride))) return rc;
+                              pa.nkb, nullptr, pa.inv_scale, st, batch, a_batch_stride))) return rc;
   if ((rc = launch_pack_split(B, b_trans ? K : N, b_trans ? N : K, ldb, b_trans != 0, 1.f, pb, 0,
-                              pb.nkb, flags, st, batch, b_batch_stride))) return rc;
+                              pb.nkb, nullptr, pb.inv_scale, st, batch, b_batch_stride))) return rc;
   GemmParams g{};
   g.a_hi = pa.hi; g.a_lo = pa.lo; g.b_hi = pb.hi; g.b_lo = pb.lo;
   g.a_batch_bytes = pa.bytes; g.b_batch_bytes = pb.bytes;
+  g.a_scale = pa.inv_scale; g.b_scale = pb.inv_scale;
+  g.a_scale_batch = (size_t)pa.rows_pad; g.b_scale_batch = (size_t)pb.rows_pad;
   g.nkb = pa.nkb; g.nseg = precise ? 3 : 1; g.M = M; g.N = N; g.c = C; g.ldc = ldc;
   g.c_batch_elems = (size_t)c_batch_stride;
   g.alpha = alpha; g.bias = bias; g.act = act; g.residual = residual; g.batch = batch;
-  prof_mark(st, "gemm_tn");
   rc = launch_gemm_tn(g, st);
   prof_mark(st, "end");
   return rc;

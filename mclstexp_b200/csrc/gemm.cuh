@@ -11,6 +11,7 @@ struct PackedOperand {
   int64_t rows_pad;   // multiple of 128 (A operand) or 256 (B operand)
   int nkb;            // K / 64 (padded)
   size_t bytes;       // bytes of one image (per batch entry)
+  float* inv_scale;   // [batch][rows_pad] inverse of the per-row power-of-two factor, or null
 };
 
 struct GemmParams {
@@ -25,16 +26,29 @@ struct GemmParams {
   const float* bias;        // [N] or null
   int act;                  // 0 none, 1 exact-erf GELU (applied after bias)
   const float* residual;    // same layout as c, added after the activation, or null
+  // operand factors undone by the epilogue (gemm.cu header): per-row vectors and / or a tensor-wide
+  // factor derived from a device max|x| word, applied amax_pow (1 or 2) times
+  const float *a_scale, *b_scale;
+  size_t a_scale_batch, b_scale_batch;
+  const uint32_t* amax_bits;
+  int amax_pow;
 };
 
 size_t packed_operand_bytes(int64_t rows, int64_t k, bool is_b, int64_t* rows_pad, int* nkb);
-PackedOperand take_operand(Arena& a, int64_t rows, int64_t k, bool is_b, bool split, int batch);
+PackedOperand take_operand(Arena& a, int64_t rows, int64_t k, bool is_b, bool split, int batch,
+                           bool row_scaled = false);
 // x [rows, cols] fp32 (ld) scaled by `scale`; transpose = false: operand rows = x rows, K = x
 // cols; transpose = true: operand rows = x cols, K = x rows.  Written at K-block kb_offset of
 // dst (dst.nkb blocks in total), nkb_mine blocks wide, zero padded.
+// Scaling: inv_scale != null -> per-row power-of-two factors found by the kernel (their inverses
+// are stored there; a transposed pack then scans whole columns, one block per 32 of them);
+// else amax_bits != null -> the tensor-wide factor of that max|x| word; else none.
 int launch_pack_split(const float* x, int64_t rows, int64_t cols, int64_t ld, bool transpose,
                       float scale, const PackedOperand& dst, int kb_offset, int nkb_mine,
-                      uint32_t* flags, cudaStream_t st, int batch = 1, int64_t x_batch_elems = 0);
+                      const uint32_t* amax_bits, float* inv_scale, cudaStream_t st, int batch = 1,
+                      int64_t x_batch_elems = 0);
+// atomicMax of max|x| (as float bits) into *out (zeroed by the caller)
+int launch_amax_bits(const float* x, int64_t rows, int64_t cols, int64_t ld, uint32_t* out, cudaStream_t st);
 int launch_gemm_tn(const GemmParams& p, cudaStream_t st);
 
 }  // namespace mclst

@@ -283,6 +283,7 @@ static int compute_blocks(const LossPlan& L, int64_t i0, int64_t rows, float inv
   const int nkbD = L.Sp.nkb;
   GemmParams g{};
   g.nseg = 3; g.batch = 1; g.M = rows; g.N = L.B; g.ldc = L.B64;
+  g.amax_bits = L.flags; g.amax_pow = 2;          // both operands carry the tensor-wide factor
   const size_t a_off = (size_t)(i0 / 128) * nkbD * TP_SLICE_BYTES;
   int rc;
   g.nkb = nkbD;
@@ -332,27 +333,31 @@ static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_em
   const int nkbD = L.Sp.nkb;
   const bool single = L.nblocks == 1 && rows == B;     // P1/P2/P3 survive between phases
   if (phase == 1) {
+    // one power-of-two factor for both embedding matrices (they are concatenated along K and
+    // shared between products): max|x| over S and I as a device word every consumer reads
     MCLST_CUDA(cudaMemsetAsync(L.flags, 0, 64, st));
     prof_mark(st, "loss_pack");
-    if ((rc = launch_pack_split(spot_emb, B, D, ld_s, false, 1.f, L.Sp, 0, nkbD, L.flags, st))) return rc;
-    if ((rc = launch_pack_split(image_emb, B, D, ld_i, false, 1.f, L.Ip, 0, nkbD, L.flags, st))) return rc;
+    if ((rc = launch_amax_bits(spot_emb, B, D, ld_s, L.flags, st))) return rc;
+    if ((rc = launch_amax_bits(image_emb, B, D, ld_i, L.flags, st))) return rc;
+    if ((rc = launch_pack_split(spot_emb, B, D, ld_s, false, 1.f, L.Sp, 0, nkbD, L.flags, nullptr, st))) return rc;
+    if ((rc = launch_pack_split(image_emb, B, D, ld_i, false, 1.f, L.Ip, 0, nkbD, L.flags, nullptr, st))) return rc;
     if (soft) {
-      if ((rc = launch_pack_split(image_emb, B, D, ld_i, false, 1.f, L.ISp, 0, nkbD, L.flags, st))) return rc;
-      if ((rc = launch_pack_split(spot_emb, B, D, ld_s, false, 1.f, L.ISp, nkbD, nkbD, L.flags, st))) return rc;
+      if ((rc = launch_pack_split(image_emb, B, D, ld_i, false, 1.f, L.ISp, 0, nkbD, L.flags, nullptr, st))) return rc;
+      if ((rc = launch_pack_split(spot_emb, B, D, ld_s, false, 1.f, L.ISp, nkbD, nkbD, L.flags, nullptr, st))) return rc;
     }
     if (d_spot) {
       const int nkbB = (int)(L.B64 / 64);
-      if ((rc = launch_pack_split(image_emb, B, D, ld_i, true, 1.f, L.XT_IS, 0, nkbB, L.flags, st))) return rc;
-      if ((rc = launch_pack_split(spot_emb, B, D, ld_s, true, 1.f, L.XT_SI, 0, nkbB, L.flags, st))) return rc;
+      if ((rc = launch_pack_split(image_emb, B, D, ld_i, true, 1.f, L.XT_IS, 0, nkbB, L.flags, nullptr, st))) return rc;
+      if ((rc = launch_pack_split(spot_emb, B, D, ld_s, true, 1.f, L.XT_SI, 0, nkbB, L.flags, nullptr, st))) return rc;
       if (soft) {
-        if ((rc = launch_pack_split(spot_emb, B, D, ld_s, true, 1.f, L.XT_IS, nkbB, nkbB, L.flags, st))) return rc;
-        if ((rc = launch_pack_split(image_emb, B, D, ld_i, true, 1.f, L.XT_SI, nkbB, nkbB, L.flags, st))) return rc;
+        if ((rc = launch_pack_split(spot_emb, B, D, ld_s, true, 1.f, L.XT_IS, nkbB, nkbB, L.flags, nullptr, st))) return rc;
+        if ((rc = launch_pack_split(image_emb, B, D, ld_i, true, 1.f, L.XT_SI, nkbB, nkbB, L.flags, nullptr, st))) return rc;
       }
     }
-    prof_mark(st, "loss_stats");
     for (int64_t b = 0; b < L.nblocks; ++b) {
       const int64_t i0 = row0 + b * L.R, nr = std::min<int64_t>(L.R, row0 + rows - i0);
       if ((rc = compute_blocks(L, i0, nr, inv_t, a_scale, true, st))) return rc;
+      prof_mark(st, "row_lse");
       row_lse_kernel<<<(unsigned)nr, LS_THREADS, 0, st>>>(L.P1, L.B64, B, i0, L.rl, L.diag);
       MCLST_LAUNCH_CHECK();
       row_lse_kernel<<<(unsigned)nr, LS_THREADS, 0, st>>>(L.P2, L.B64, B, i0, L.cl, nullptr);
@@ -364,37 +369,41 @@ static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_em
     }
   } else if (phase == 2) {
     if (soft) {
-      prof_mark(st, "loss_value");
       for (int64_t b = 0; b < L.nblocks; ++b) {
         const int64_t i0 = row0 + b * L.R, nr = std::min<int64_t>(L.R, row0 + rows - i0);
         if (!single && (rc = compute_blocks(L, i0, nr, inv_t, a_scale, false, st))) return rc;
+        prof_mark(st, "soft_pass2");
         soft_pass2_kernel<<<(unsigned)nr, LS_THREADS, 0, st>>>(L.P1, L.P3, L.B64, B, i0, L.rl, L.cl,
                                                              L.za, L.wbar, L.cs);
         MCLST_LAUNCH_CHECK();
       }
     }
   } else {
-    prof_mark(st, "loss_value");
+    prof_mark(st, "loss_reduce");
     if (soft) loss_reduce_kernel<<<1, LS_THREADS, 0, st>>>(L.wbar, nullptr, nullptr, (int)row0, (int)(row0 + rows), B, loss_out);
     else loss_reduce_kernel<<<1, LS_THREADS, 0, st>>>(L.rl, L.cl, L.diag, (int)row0, (int)(row0 + rows), B, loss_out);
     MCLST_LAUNCH_CHECK();
     if (d_spot) {
-      prof_mark(st, "loss_grad");
       for (int64_t b = 0; b < L.nblocks; ++b) {
         const int64_t i0 = row0 + b * L.R, nr = std::min<int64_t>(L.R, row0 + rows - i0);
         if (!single && (rc = compute_blocks(L, i0, nr, inv_t, a_scale, true, st))) return rc;
         GradParams gp{};
         gp.P1 = L.P1; gp.P2 = L.P2; gp.P3 = L.P3; gp.ld = L.B64; gp.B = B; gp.rows = (int)nr;
         gp.soft = soft; gp.row0 = i0; gp.rl = L.rl; gp.cl = L.cl; gp.za = L.za; gp.wbar = L.wbar;
-        gp.cs = L.cs; gp.inv_t = inv_t; gp.a_scale = a_scale;
+        // the two K halves carry different scalars (1/T and a); the larger one goes into alpha so that
+        // the stored factors stay O(1) whatever the temperature (fp16 range)
+        const float u = std::max(inv_t, a_scale);
+        gp.cs = L.cs; gp.inv_t = inv_t / u; gp.a_scale = a_scale / u;
         gp.ga_hi = L.GA.hi; gp.ga_lo = L.GA.lo; gp.gb_hi = L.GB.hi; gp.gb_lo = L.GB.lo;
         gp.nkb_total = L.GA.nkb; gp.nkb_half = (int)(L.B64 / 64);
         const int64_t rows_pad = (int64_t)align_up((size_t)nr, 128);
         const int64_t threads = rows_pad / GF_ROWS * gp.nkb_half * 8;
+        prof_mark(st, "grad_factor");
         grad_factor_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, st>>>(gp, rows_pad);
         MCLST_LAUNCH_CHECK();
         GemmParams g{};
-        g.nseg = 3; g.batch = 1; g.M = nr; g.N = D; g.nkb = L.GA.nkb; g.alpha = 0.5f / (float)B;
+        g.nseg = 3; g.batch = 1; g.M = nr; g.N = D; g.nkb = L.GA.nkb; g.alpha = 0.5f * u / (float)B;
+        g.amax_bits = L.flags; g.amax_pow = 1;    // only the embedding operand is scaled
         g.a_hi = L.GA.hi; g.a_lo = L.GA.lo; g.b_hi = L.XT_IS.hi; g.b_lo = L.XT_IS.lo;
         g.c = d_spot + (i0 - row0) * ld_ds; g.ldc = ld_ds;
         if ((rc = launch_gemm_tn(g, st))) return rc;

@@ -22,6 +22,13 @@ class GraphedTrainStep:
     created on the default stream invalidates the capture)."""
 
     def __init__(self, model: torch.nn.Module, example_batch: Dict[str, torch.Tensor], warmup: int = 3):
+        for name in ("x_embed", "y_embed"):
+            w = getattr(getattr(model, name, None), "weight", None)
+            if getattr(w, "_mclst_lazy", None) is not None:
+                raise RuntimeError(
+                    "GraphedTrainStep: the position tables are owned by optim.LazyEmbeddingAdam "
+                    "(TrainOptimizer); its step counter is a launch argument, so it cannot be captured. "
+                    "Use a stock torch.optim optimizer with the graphed step.")
         self.model = model
         self.static = {k: v.clone() for k, v in example_batch.items()}
         self.table_rows = getattr(getattr(model, "x_embed", None), "num_embeddings", None)
@@ -40,6 +47,10 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss = model(self.static)
             self.loss.backward()
+        # the replay writes into THESE buffers; ``optimizer.zero_grad()`` (set_to_none=True is the
+        # default, train.py:37) drops them from the parameters, so they are re-attached after
+        # every replay -- otherwise optimizer.step() would silently skip every parameter
+        self.grads = {p: p.grad for p in model.parameters() if p.grad is not None}
 
     def __call__(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         pos = batch.get("position")
@@ -50,4 +61,11 @@ class GraphedTrainStep:
         for k, v in self.static.items():
             v.copy_(batch[k], non_blocking=True)
         self.graph.replay()
+        for p, g in self.grads.items():
+            if p.grad is not g:
+                p.grad = g
         return self.loss
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """Provided for loops that call it on the step object; the replay overwrites every captured
+        gradient anyway, so nothing needs clearing."""

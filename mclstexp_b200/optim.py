@@ -14,7 +14,7 @@ point where they are observed (forward gathers, ``flush()``, ``state_dict()``).
     opt.zero_grad(); loss = model(batch); loss.backward(); opt.step()
 
 No CPU fallback; not compatible with ``graphs.GraphedTrainStep`` (the step counter is a launch
-argument).
+argument; the graphed step raises when it sees lazily-owned tables).
 """
 from __future__ import annotations
 
@@ -114,6 +114,17 @@ class LazyEmbeddingAdam:
     def zero_grad(self, set_to_none: bool = True) -> None:
         self._pending = None
 
+    def set_hyper(self, lr=None, betas=None, eps=None, weight_decay=None) -> None:
+        """Hyper-parameters of the NEXT steps (an LR scheduler changing ``param_groups`` ends up here)."""
+        if lr is not None:
+            self.lr = float(lr)
+        if betas is not None:
+            self.betas = (float(betas[0]), float(betas[1]))
+        if eps is not None:
+            self.eps = float(eps)
+        if weight_decay is not None:
+            self.weight_decay = float(weight_decay)
+
     def step(self) -> None:
         if self._pending is None:
             raise _lib.MclstError("LazyEmbeddingAdam.step(): no gradient recorded (run forward + backward first)")
@@ -139,11 +150,34 @@ class LazyEmbeddingAdam:
         if int(self._err.item()):
             raise IndexError("position index out of range for x_embed / y_embed")
 
+    def mark_all_current(self) -> None:
+        """Declare every row current (after the table VALUES were replaced from outside, e.g.
+        ``load_state_dict``): no missed step may be replayed onto the new values."""
+        for l in self.last:
+            l.fill_(self.steps_done)
+
     def state_dict(self) -> dict:
         self.flush()
         return {"step": self.steps_done, "exp_avg": [t.clone() for t in self.exp_avg],
                 "exp_avg_sq": [t.clone() for t in self.exp_avg_sq],
                 "hyper": {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}}
+
+    def load_state_dict(self, sd: dict) -> None:
+        """Moments and step counter of ``state_dict()``; the per-step scalars of the steps already
+        done are never read again once every row is current, so only the counter is restored."""
+        if len(sd["exp_avg"]) != len(self.tables):
+            raise ValueError("LazyEmbeddingAdam.load_state_dict: table count differs")
+        self.flush()
+        for dst, src in zip(self.exp_avg, sd["exp_avg"]):
+            dst.copy_(src)
+        for dst, src in zip(self.exp_avg_sq, sd["exp_avg_sq"]):
+            dst.copy_(src)
+        self.steps_done = int(sd["step"])
+        if self.steps_done >= self.coef.max_steps:
+            raise ValueError("LazyEmbeddingAdam.load_state_dict: step beyond max_steps")
+        self.set_hyper(**sd.get("hyper", {}))
+        self._pending = None
+        self.mark_all_current()
 
 
 class TrainOptimizer:
@@ -160,18 +194,45 @@ class TrainOptimizer:
         self.dense = torch.optim.Adam(rest, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         self.lazy = LazyEmbeddingAdam(tables, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         model.register_state_dict_pre_hook(lambda module, prefix, keep_vars: self.lazy.flush())
+        # ``model.load_state_dict`` after training has started (resume, load-best): apply every
+        # deferred step to the OLD values first, so that the loaded rows are current by construction
+        # (``last == steps_done``) and no stale step is ever replayed onto them -- stock Adam leaves
+        # loaded weights untouched too
+        model.register_load_state_dict_pre_hook(self._before_model_load)
         # reference-style evaluation calls the embedding modules directly (evel_her2st.py:52-57:
         # ``model.x_embed(x)``), bypassing embed_add's per-row catch-up: bring everything current first
         for emb in (model.x_embed, model.y_embed):
             emb.register_forward_pre_hook(lambda module, args: self.lazy.flush())
+
+        # the tables appear as their own param group so that ``get_lr(optimizer)`` (train.py:41) and
+        # LR schedulers see ONE optimizer; stock Adam never steps them (their .grad stays None)
+        g0 = self.dense.param_groups[0]
+        self.dense.add_param_group({"params": tables, **{k: g0[k] for k in ("lr", "betas", "eps", "weight_decay")}})
+
+    def _before_model_load(self, module, state_dict, prefix, *args) -> None:
+        self.lazy.flush()
+        self.lazy.mark_all_current()
+
+    @property
+    def param_groups(self):
+        return self.dense.param_groups
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         self.dense.zero_grad(set_to_none=set_to_none)
         self.lazy.zero_grad()
 
     def step(self) -> None:
+        g = self.dense.param_groups[-1]                  # the tables' group: scheduler-visible lr
+        self.lazy.set_hyper(g["lr"], g["betas"], g["eps"], g["weight_decay"])
         self.dense.step()
         self.lazy.step()
 
     def flush(self) -> None:
         self.lazy.flush()
+
+    def state_dict(self) -> dict:
+        return {"dense": self.dense.state_dict(), "lazy": self.lazy.state_dict()}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.dense.load_state_dict(sd["dense"])
+        self.lazy.load_state_dict(sd["lazy"])

@@ -114,6 +114,22 @@ def find_matches_spec(spot_embeddings, query_embeddings, top_k=1,
     return vals, idx
 
 
+def find_matches_spec_rows(spot_embeddings, query_embeddings, top_k: int,
+                           bank_chunk: int = 1 << 17) -> Tuple[np.ndarray, np.ndarray]:
+    """``find_matches_spec`` for a FEW query rows against a bank too large to hold as one float64
+    array (the 1M-spot bank of BASELINE cfg4): the similarity is evaluated per bank chunk with
+    ``similarity_spec`` -- identical arithmetic, every (query, spot) pair is independent of the
+    chunking -- and the order is (similarity descending, index ascending)."""
+    q = np.ascontiguousarray(query_embeddings, np.float32)
+    if q.ndim == 1:
+        q = q[None]
+    n = spot_embeddings.shape[0]
+    sims = np.concatenate([similarity_spec(spot_embeddings[c0:c0 + bank_chunk], q)
+                           for c0 in range(0, n, bank_chunk)], axis=1)
+    order = np.argsort(-sims, axis=1, kind="stable")[:, :top_k]
+    return np.take_along_axis(sims, order, axis=1), order.astype(np.int64)
+
+
 def decidable_rows(spot_embeddings, query_embeddings, top_k, gap=DECIDABLE_GAP) -> np.ndarray:
     """Boolean [Q]: rows whose top-(k+1) float64 similarities are pairwise
     separated by more than ``gap`` -- on those rows ANY correct float32

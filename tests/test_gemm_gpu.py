@@ -74,3 +74,51 @@ def test_matmul_batched_head_slices():
     ops.matmul(p, v, b_trans=True, out=ov)                        # [H,B,B] x [H,B(K),dh(N)]
     want = torch.einsum("hij,hjd->hid", p.double(), v.double()).permute(1, 0, 2).reshape(Bt, H * dh)
     assert (out.double() - want).abs().max().item() <= 3e-5 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("sa,sb", [(1e-5, 1.0), (1e-5, 1e-5), (1e4, 1e4), (1e-30, 1e20), (3e30, 1e-12)])
+@pytest.mark.parametrize("a_trans,b_trans", [(False, False), (True, True)])
+def test_matmul_operand_magnitudes(sa, sb, a_trans, b_trans):
+    """fp16 hi/lo halves have a 5-bit exponent: operands are brought into range with exact
+    power-of-two row factors (gemm.cu), so gradients of magnitude 1e-5 and activations of 1e4
+    keep fp32-level accuracy."""
+    g = torch.Generator().manual_seed(21)
+    M, N, K = 130, 270, 200
+    a = (torch.randn((K, M) if a_trans else (M, K), generator=g) * sa).cuda()
+    b = (torch.randn((K, N) if b_trans else (N, K), generator=g) * sb).cuda()
+    opa, opb = (a.T if a_trans else a), (b.T if b_trans else b)
+    want = opa.double() @ opb.double().T
+    got = ops.matmul(a, b, a_trans, b_trans).double()
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() <= 3e-5 * want.abs().max().item()
+
+
+def test_matmul_rows_of_very_different_scale_and_outliers():
+    """Row-wise factors: a 1e5 outlier (beyond fp16's 65504) in one row must neither saturate nor
+    cost the other rows their precision; rows 1e-6 apart in scale are each accurate on their own
+    scale."""
+    g = torch.Generator().manual_seed(22)
+    M, N, K = 96, 140, 300
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(N, K, generator=g)
+    a[3, 17] = 1e5
+    a[10] *= 1e-6
+    b[5] *= 1e6
+    b[7, :] = 0.0
+    want = a.double() @ b.double().T
+    got = ops.matmul_nt(a.cuda(), b.cuda()).cpu().double()
+    # every output element against the scale of ITS row and column
+    ref = a.double().abs().max(1).values[:, None] * b.double().abs().max(1).values[None, :] * K ** 0.5
+    assert ((got - want).abs() <= 3e-5 * ref + 1e-30).all()
+    assert (got[:, 7] == 0).all()
+
+
+def test_matmul_non_finite_inputs_propagate():
+    a = torch.randn(40, 64).cuda()
+    b = torch.randn(50, 64).cuda()
+    a[2, 3] = float("inf")
+    b[4, 5] = float("nan")
+    got = ops.matmul_nt(a, b)
+    assert not torch.isfinite(got[2]).any()          # inf * finite sums: inf or NaN, never a finite lie
+    assert torch.isnan(got[:, 4]).all()
+    assert torch.isfinite(got[[0, 1, 3]][:, [0, 1, 2, 3]]).all()

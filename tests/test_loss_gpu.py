@@ -7,6 +7,7 @@ import torch
 from mclstexp_b200 import loss as mloss, synth
 from oracle import oracle
 from conftest import golden_checksum
+from checkers import assert_grad_close, loss_closed_form_f64
 
 pytestmark = pytest.mark.gpu
 
@@ -21,11 +22,9 @@ def _check(S, I, T, targets, scale, ref=None, env=None):
     (l * 1.0).backward()
     l64, dS64, dI64 = oracle.contrastive_loss_closed_form(S, I, T, targets, scale)
     np.testing.assert_allclose(l.item(), l64, rtol=RTOL)
-    for got, want in ((St.grad, dS64), (It.grad, dI64)):
-        got = got.cpu().numpy()
-        # normwise (per-matrix) relative error, plus elementwise with an absolute floor
-        assert np.linalg.norm(got - want) <= RTOL * np.linalg.norm(want)
-        np.testing.assert_allclose(got, want, rtol=RTOL, atol=RTOL * np.abs(want).max())
+    for name, got, want in (("dS", St.grad, dS64), ("dI", It.grad, dI64)):
+        # norm-wise, max-normalised AND element-wise relative on every entry above 1e-3 max
+        assert_grad_close(got, want, RTOL, name=name)
     if ref is not None:
         np.testing.assert_allclose(l.item(), ref[0], rtol=RTOL)
         np.testing.assert_allclose(St.grad.cpu().numpy(), ref[1], rtol=RTOL, atol=RTOL * np.abs(ref[1]).max())
@@ -59,26 +58,29 @@ def test_loss_shapes(B, D, T, scale_in, targets):
     _check(S, I, T, targets, "div")
 
 
+@pytest.mark.parametrize("B,mb", [(700, 3), (4096, 64)])
 @pytest.mark.parametrize("targets", ["eye", "soft"])
-def test_loss_row_blocked_equals_single_block(targets, monkeypatch):
-    """Force several row blocks (the B=32k path) on a small batch."""
+def test_loss_row_blocked_equals_single_block(targets, B, mb):
+    """Force several row blocks (the streaming path a small scratch budget selects) and compare with
+    the float64 closed form: 3 MiB -> 128-row blocks at B=700; 64 MiB -> 512-row blocks at B=4096."""
     import subprocess, sys, os
     code = f"""
-import numpy as np, torch
+import sys, torch
+sys.path.insert(0, 'tests')
+from checkers import assert_grad_close, loss_closed_form_f64
 from mclstexp_b200 import loss as mloss, synth
-from oracle import oracle
-B, D = 700, 256
-S = synth.embeddings(B, D, 1, 'clustered', centres=9) * 0.5
-I = synth.embeddings(B, D, 2, 'clustered', centres=9) * 0.5
-St = torch.tensor(S, device='cuda', requires_grad=True); It = torch.tensor(I, device='cuda', requires_grad=True)
+B, D = {B}, 256
+S = torch.tensor(synth.embeddings(B, D, 1, 'clustered', centres=9) * 0.5, device='cuda')
+I = torch.tensor(synth.embeddings(B, D, 2, 'clustered', centres=9) * 0.5, device='cuda')
+St = S.clone().requires_grad_(True); It = I.clone().requires_grad_(True)
 l = mloss.contrastive_loss(St, It, 1.0, '{targets}'); l.backward()
-l64, dS64, dI64 = oracle.contrastive_loss_closed_form(S, I, 1.0, '{targets}')
+l64, dS64, dI64 = loss_closed_form_f64(S, I, 1.0, '{targets}')
 assert abs(l.item() - l64) <= 1e-3 * abs(l64), (l.item(), l64)
-assert np.linalg.norm(St.grad.cpu().numpy() - dS64) <= 1e-3 * np.linalg.norm(dS64)
-assert np.linalg.norm(It.grad.cpu().numpy() - dI64) <= 1e-3 * np.linalg.norm(dI64)
+assert_grad_close(St.grad, dS64, 1e-3, name='dS')
+assert_grad_close(It.grad, dI64, 1e-3, name='dI')
 print('ok')
 """
-    env = dict(os.environ, MCLST_LOSS_SCRATCH_MB="3")      # 3 MiB -> R = 128 rows per block
+    env = dict(os.environ, MCLST_LOSS_SCRATCH_MB=str(mb))
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
@@ -90,3 +92,53 @@ def test_loss_no_grad_path():
     l = mloss.contrastive_loss(S, I, 1.0, "soft")
     l64, _, _ = oracle.contrastive_loss_closed_form(S.cpu().numpy(), I.cpu().numpy(), 1.0, "soft")
     np.testing.assert_allclose(l.item(), l64, rtol=RTOL)
+
+
+def test_gpu_checker_equals_cpu_oracle():
+    """Pins tests/checkers.py (float64 on the GPU, row-chunked) against the CPU oracle's closed form."""
+    S = synth.embeddings(300, 64, 1, "clustered", centres=5) * 0.5
+    I = synth.embeddings(300, 64, 2, "clustered", centres=5) * 0.5
+    for targets, scale in (("eye", "div"), ("soft", "div"), ("soft", "mul")):
+        l, dS, dI = loss_closed_form_f64(torch.tensor(S, device="cuda"), torch.tensor(I, device="cuda"),
+                                         0.7, targets, scale, chunk=128)
+        l64, dS64, dI64 = oracle.contrastive_loss_closed_form(S, I, 0.7, targets, scale)
+        assert abs(l - l64) <= 1e-12 * abs(l64)
+        assert_grad_close(dS, dS64, rtol=1e-9, name="dS")
+        assert_grad_close(dI, dI64, rtol=1e-9, name="dI")
+
+
+def _big_inputs(B, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    c = 4.0 * torch.randn(64, 256, generator=g, device="cuda")
+
+    def emb():
+        x = c[torch.randint(0, 64, (B,), generator=g, device="cuda")] + torch.randn(B, 256, generator=g, device="cuda")
+        x = x - x.mean(1, keepdim=True)
+        return x / x.std(1, keepdim=True, unbiased=False)      # LayerNorm-like rows: norm 16, logits to +-256
+    return emb(), emb()
+
+
+@pytest.mark.parametrize("B", [4096, 8192, 32768])
+@pytest.mark.parametrize("targets", ["eye", "soft"])
+def test_loss_at_size_vs_f64(B, targets):
+    """The sizes BASELINE cfg5 is quoted on: loss, dS, dI against the float64
+    closed form evaluated on the GPU in row chunks."""
+    S, I = _big_inputs(B, 100 + B)
+    St, It = S.clone().requires_grad_(True), I.clone().requires_grad_(True)
+    l = mloss.contrastive_loss(St, It, 1.0, targets)
+    l.backward()
+    l64, dS64, dI64 = loss_closed_form_f64(S, I, 1.0, targets, chunk=2048)
+    assert abs(l.item() - l64) <= RTOL * abs(l64), (l.item(), l64)
+    assert_grad_close(St.grad, dS64, RTOL, name=f"dS B={B}")
+    assert_grad_close(It.grad, dI64, RTOL, name=f"dI B={B}")
+
+
+def test_loss_operand_scale_extremes():
+    """Embeddings far from the LayerNorm scale (1e-4 x and 30 x): the split-precision operands must
+    not lose the small ones or saturate the large ones."""
+    for mult, T in ((1e-4, 1e-8), (3000.0, 9e6), (1e5, 1e10), (1.0, 1.0)):
+        S = synth.embeddings(384, 256, 5, "clustered", centres=7) * np.float32(mult)
+        I = synth.embeddings(384, 256, 6, "clustered", centres=7) * np.float32(mult)
+        for targets in ("eye", "soft"):
+            _check(S, I, T, targets, "div")

@@ -112,6 +112,22 @@ def test_cfg2_shaped_step_vs_oracle(targets):
         _close(p.grad, want, k, rtol=2e-3)
 
 
+def test_cfg2_full_size_step_vs_oracle():
+    """BASELINE cfg2 at the size it names: B = 1024 tokens, G = 1000 genes, two
+    attention blocks + heads + soft-target loss, loss and every gradient vs the oracle's autograd."""
+    m = dict(G=1000, E=1024, heads=8, dim_head=64, layers=2, B=1024, T=1.0, kind="st", seed=23)
+    net, sd = _build(m, "soft")
+    feats, expr, pos = _inputs(m)
+    loss = net({"image": feats.cuda(), "expression": expr.cuda(), "position": pos.cuda()})
+    loss.backward()
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = oracle.path_loss_ref(params, feats, expr, pos, m["T"], m["heads"], m["layers"], "soft")
+    ref.backward()
+    np.testing.assert_allclose(loss.item(), ref.item(), rtol=RTOL)
+    for k, p in net.named_parameters():
+        _close(p.grad, params[k].grad.numpy(), k, rtol=2e-3)
+
+
 def test_position_out_of_range_raises():
     m = dict(G=16, E=8, heads=2, dim_head=8, layers=1, B=4, T=1.0, kind="st", seed=3)
     net, _ = _build(m)

@@ -122,3 +122,105 @@ def test_training_steps_with_lazy_tables_match_stock_adam():
         torch.testing.assert_close(sd_new[k], sd_ref[k], rtol=1e-3, atol=5e-5, msg=k)
     with pytest.raises(Exception):
         opt_new.lazy.step()                                      # no gradient recorded
+
+
+def _small_net(dev, G=96):
+    torch.manual_seed(5)
+    net = mm.mclSTExp_Attention("none", 1.0, 128, G, 64, 2, 16, 1)
+    net.image_encoder = nn.Identity()
+    return net.to(dev)
+
+
+def _batch(dev, B, G, g, hi=60):
+    return {"image": torch.randn(B, 128, generator=g, device=dev),
+            "expression": torch.rand(B, G, generator=g, device=dev),
+            "position": torch.randint(0, hi, (B, 2), generator=g, device=dev).float()}
+
+
+def test_load_state_dict_after_lazy_steps_keeps_loaded_rows():
+    """``model.load_state_dict`` once training has started must leave the loaded table rows
+    exactly as loaded (stock Adam would) -- no stale step may be replayed onto them."""
+    dev = torch.device("cuda", 0)
+    G, B = 96, 64
+    net = _small_net(dev, G)
+    best = {k: v.clone() for k, v in net.state_dict().items()}
+    opt = mo.TrainOptimizer(net, lr=1e-3, weight_decay=1e-3)
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    for _ in range(4):
+        opt.zero_grad()
+        net(_batch(dev, B, G, g, hi=20)).backward()
+        opt.step()
+    assert int(opt.lazy.last[0].min()) < opt.lazy.steps_done          # deferred rows exist
+    net.load_state_dict(best)                                          # "load best checkpoint"
+    assert int(opt.lazy.last[0].min()) == opt.lazy.steps_done
+    sd = net.state_dict()                                              # flushes: must be a no-op now
+    for k in ("x_embed.weight", "y_embed.weight"):
+        assert torch.equal(sd[k], best[k]), k
+    opt.zero_grad()                                                    # and training goes on
+    net(_batch(dev, B, G, g, hi=20)).backward()
+    opt.step()
+    assert not torch.equal(net.state_dict()["x_embed.weight"], best["x_embed.weight"])
+
+
+def test_train_optimizer_param_groups_and_state_roundtrip():
+    """train.py:41 reads ``optimizer.param_groups``; schedulers write ``lr`` there; checkpoints carry
+    the optimiser state."""
+    dev = torch.device("cuda", 0)
+    G, B = 96, 64
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)
+    batches = [_batch(dev, B, G, g, hi=16) for _ in range(6)]
+
+    def run(net, opt, bs):
+        for b in bs:
+            opt.zero_grad()
+            net(b).backward()
+            opt.step()
+
+    a = _small_net(dev, G)
+    oa = mo.TrainOptimizer(a, lr=1e-3, weight_decay=1e-3)
+    assert oa.param_groups[0]["lr"] == 1e-3 and len(oa.param_groups) == 2
+    sched = torch.optim.lr_scheduler.StepLR(oa.dense, step_size=1, gamma=0.5)
+    run(a, oa, batches[:3])
+    sched.step()
+    assert oa.param_groups[-1]["lr"] == 5e-4
+    import copy
+    ck_model, ck_opt = {k: v.clone() for k, v in a.state_dict().items()}, copy.deepcopy(oa.state_dict())
+    run(a, oa, batches[3:])
+    assert oa.lazy.lr == 5e-4                                          # the tables follow the schedule
+    b = _small_net(dev, G)
+    ob = mo.TrainOptimizer(b, lr=1e-3, weight_decay=1e-3)
+    b.load_state_dict(ck_model)
+    ob.load_state_dict(ck_opt)
+    run(b, ob, batches[3:])                                            # resumed run == uninterrupted run
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        torch.testing.assert_close(sb[k], sa[k], rtol=1e-6, atol=1e-7, msg=k)
+
+
+def test_graphed_step_with_stock_adam_and_zero_grad_trains():
+    """optimizer.zero_grad() (set_to_none=True by default) between graph replays must not
+    orphan the captured gradient buffers."""
+    from mclstexp_b200.graphs import GraphedTrainStep
+    dev = torch.device("cuda", 0)
+    G, B = 96, 64
+    net = _small_net(dev, G)
+    g = torch.Generator(device=dev)
+    g.manual_seed(6)
+    batch = _batch(dev, B, G, g)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    step = GraphedTrainStep(net, batch)
+    before = {k: p.detach().clone() for k, p in net.named_parameters()}
+    losses = []
+    for _ in range(5):
+        opt.zero_grad()                       # train.py:37
+        losses.append(float(step(batch)))
+        opt.step()
+    changed = [k for k, p in net.named_parameters() if not torch.equal(p.detach(), before[k])]
+    assert len(changed) == len(before), sorted(set(before) - set(changed))
+    assert losses[-1] < losses[0]
+    lazy_net = _small_net(dev, G)
+    mo.TrainOptimizer(lazy_net, lr=1e-3)
+    with pytest.raises(RuntimeError):
+        GraphedTrainStep(lazy_net, batch)
