@@ -48,7 +48,10 @@ enum {
 /* flags of mclst_find_matches / mclst_retrieve */
 enum {
   MCLST_FM_DEFAULT = 0,
-  MCLST_FM_EXACT_ONLY = 1 /* skip the tensor-core candidate pass, brute-force every query */
+  MCLST_FM_EXACT_ONLY = 1, /* skip the tensor-core candidate pass, brute-force every query */
+  MCLST_FM_BANK_PACKED = 2 /* the workspace already holds this bank's packed image (an earlier
+                              mclst_find_matches_pack_bank / _seed / find_matches call on the same
+                              workspace with the same bank, n_bank, dim and top_k): skip the bank pass */
 };
 
 /* contrastive-loss target modes */
@@ -103,6 +106,39 @@ int mclst_find_matches_dist(const float* bank, int64_t n_bank, int64_t ld_bank,
                             int dist_p, void* workspace, size_t workspace_bytes, int flags,
                             mclst_stream_t stream);
 
+/* Staged form of mclst_find_matches_dist, for
+ *  (a) bank shards (one per GPU): every shard runs the SEED pass, the ranks exchange
+ *      a lower bound of the exact GLOBAL k-th best score per query, and every shard's MAIN pass
+ *      filters against it instead of converging its own threshold from scratch;
+ *  (b) a bank kept resident on the device (the serving form of the fold loop, and the hand-off
+ *      from the bank build, evel_her2st.py:44-71,116-117): _pack_bank writes the normalised fp16
+ *      operand image, float64 norms and rounding residuals of the bank rows into the workspace
+ *      once; later _seed / find_matches calls pass MCLST_FM_BANK_PACKED and only pack the queries
+ *      (the bank-derived part of the workspace does not depend on n_query; size the workspace with
+ *      mclst_find_matches_workspace_bytes for the largest query batch).
+ * _seed:  bound_k[q] (nullable) <= the exact score of at least top_k rows of THIS bank;
+ *         bound_part[q] (nullable) likewise for k_part <= top_k rows; -inf or NaN = nothing known.
+ *         For R homogeneous shards min over shards of bound_part with k_part = ceil(top_k / R) is a
+ *         valid (and much tighter) bound of the global k-th best, as is max over shards of bound_k.
+ * _main:  must follow _seed on the same workspace and stream order.  ext_bound (nullable) [n_query]:
+ *         rows provably below it are dropped, so a shard may return FEWER than top_k rows for a
+ *         query: the tail of its list is padded with (value -inf, index 0x7fffffff, distance +inf),
+ *         which loses every mclst_merge_topk comparison. */
+int mclst_find_matches_pack_bank(const float* bank, int64_t n_bank, int64_t ld_bank, int dim,
+                                 int top_k, void* workspace, size_t workspace_bytes,
+                                 mclst_stream_t stream);
+int mclst_find_matches_seed(const float* bank, int64_t n_bank, int64_t ld_bank,
+                            const float* query, int64_t n_query, int64_t ld_query, int dim,
+                            int top_k, int k_part, float* bound_k, float* bound_part,
+                            void* workspace, size_t workspace_bytes, int flags,
+                            mclst_stream_t stream);
+int mclst_find_matches_main(const float* bank, int64_t n_bank, int64_t ld_bank,
+                            const float* query, int64_t n_query, int64_t ld_query, int dim,
+                            int top_k, int64_t index_offset, int64_t* out_indices,
+                            float* out_values, float* out_distances, int dist_p,
+                            const float* ext_bound, void* workspace, size_t workspace_bytes,
+                            int flags, mclst_stream_t stream);
+
 /* Testing aid: the raw similarities of the tensor-core candidate pass (fp16-rounded
  * normalised operands, fp32 accumulation) written to out [n_query, ld_out]; workspace as for
  * mclst_find_matches with top_k = 1.  Not part of the reference surface. */
@@ -154,14 +190,16 @@ int mclst_weighted_gather(const void* expression_key, int64_t n_bank, int64_t ld
 /* Row-sharded form (embedding all-gather over NVLink): spot_emb /
  * image_emb are the ALL-GATHERED [batch, dim] embeddings; this rank owns the rows
  * [row0, row0 + rows) (row0 a multiple of 128).  `stats` is a caller-owned device block
- * [6][batch] float32 (rl, cl, za, wbar, cs, diag) whose local slices each phase fills and
+ * [MCLST_LOSS_STAT_ROWS][batch] float32 (rl, cl, za, wbar, cs, diag, rl_lo, cl_lo, za_lo: the three
+ * log-sum-exp statistics are float PAIRS hi + lo) whose local slices each phase fills and
  * which the caller all-gathers between phases:
- *   phase 1 packs the operands and writes rl, cl, za, diag of the local rows;
- *   phase 2 (after gathering rl, cl, za) writes wbar, cs of the local rows (soft targets);
+ *   phase 1 packs the operands and writes rl, cl, za (+ their lo parts), diag of the local rows;
+ *   phase 2 (after gathering those) writes wbar, cs of the local rows (soft targets);
  *   phase 3 (after gathering wbar, cs) writes this rank's additive loss contribution to
  *           *loss_out and, if d_spot/d_image are given, the gradients of the LOCAL rows
  *           ([rows, dim]); no gradient exchange is needed afterwards.
  * The same workspace must be passed to all three phases. */
+#define MCLST_LOSS_STAT_ROWS 9
 int mclst_contrastive_loss_phase(const float* spot_emb, int64_t ld_s, const float* image_emb,
                                  int64_t ld_i, int batch, int dim, float temperature, int target_mode,
                                  int64_t row0, int64_t rows, int phase, float* stats, float* loss_out,

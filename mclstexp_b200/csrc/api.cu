@@ -178,30 +178,38 @@ extern "C" int mclst_find_matches(const float* bank, int64_t n_bank, int64_t ld_
                                  workspace_bytes, flags, stream);
 }
 
-extern "C" int mclst_find_matches_dist(const float* bank, int64_t n_bank, int64_t ld_bank,
-                                       const float* query, int64_t n_query, int64_t ld_query,
-                                       int dim, int top_k, int64_t index_offset,
-                                       int64_t* out_indices, float* out_values,
-                                       float* out_distances, int dist_p, void* workspace,
-                                       size_t workspace_bytes, int flags, mclst_stream_t stream) {
+// The stages of find_matches.  stage bits: 1 = pack (+ thresholds reset + seed pass, writing the
+// cross-shard bounds when asked), 2 = main pass + re-rank + exact fallback.  The single-call entry
+// runs both; bank shards run them separately with a bound exchange in between.
+static int find_matches_stages(int stages, const float* bank, int64_t n_bank, int64_t ld_bank,
+                               const float* query, int64_t n_query, int64_t ld_query, int dim,
+                               int top_k, int64_t index_offset, int64_t* out_indices,
+                               float* out_values, float* out_distances, int dist_p,
+                               SeedBounds* sb, void* workspace, size_t workspace_bytes, int flags,
+                               cudaStream_t st) {
   MCLST_REQUIRE(dist_p == 1 || dist_p == 2, MCLST_ERR_INVALID, "find_matches: dist_p must be 1 or 2");
-  if (n_query == 0 && n_bank >= 0) return 0;
-  MCLST_REQUIRE(bank && query && out_indices && workspace, MCLST_ERR_INVALID,
-                "find_matches: null pointer");
-  MCLST_REQUIRE(dim >= 1 && ld_bank >= dim && ld_query >= dim, MCLST_ERR_INVALID,
+  MCLST_REQUIRE(bank && workspace && (query || n_query == 0), MCLST_ERR_INVALID, "find_matches: null pointer");
+  MCLST_REQUIRE(!(stages & 2) || out_indices || n_query == 0, MCLST_ERR_INVALID, "find_matches: null output");
+  MCLST_REQUIRE(dim >= 1 && ld_bank >= dim && (ld_query >= dim || n_query == 0), MCLST_ERR_INVALID,
                 "find_matches: bad dim/ld");
   // torch.topk raises when k exceeds the dimension (evel_her2st.py:82)
   MCLST_REQUIRE(top_k >= 1 && top_k <= n_bank, MCLST_ERR_INVALID,
                 "find_matches: top_k %d out of range for %lld bank rows", top_k, (long long)n_bank);
   MCLST_REQUIRE(n_bank < (1ll << 31), MCLST_ERR_UNSUPPORTED, "find_matches: bank shard too large");
-  if (n_query == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
   FmWorkspace w = carve_fm(workspace, workspace_bytes, n_bank, n_query, dim, top_k, flags);
   MCLST_REQUIRE(w.bytes <= workspace_bytes, MCLST_ERR_WORKSPACE,
                 "find_matches: workspace %zu < %zu", workspace_bytes, w.bytes);
-  MCLST_CUDA(cudaMemsetAsync(w.counters, 0, 256, st));
+  const bool packed = (flags & MCLST_FM_BANK_PACKED) != 0;
+  MCLST_REQUIRE(!packed || w.use_tc, MCLST_ERR_INVALID,
+                "find_matches: MCLST_FM_BANK_PACKED needs the tensor-core path (dim <= 256, k <= 896)");
   int rc;
   if (!w.use_tc) {
+    if (stages & 1) {
+      if (sb && sb->bound_k) MCLST_CUDA(cudaMemsetAsync(sb->bound_k, 0xff, (size_t)n_query * 4, st));     // -NaN: "unknown"
+      if (sb && sb->bound_part) MCLST_CUDA(cudaMemsetAsync(sb->bound_part, 0xff, (size_t)n_query * 4, st));
+    }
+    if (!(stages & 2) || n_query == 0) return 0;
+    MCLST_CUDA(cudaMemsetAsync(w.counters, 0, 256, st));
     prof_mark(st, "row_norms");
     if ((rc = launch_row_norms(bank, n_bank, ld_bank, dim, w.bank_nrm, st))) return rc;
     if ((rc = launch_row_norms(query, n_query, ld_query, dim, w.q_nrm, st))) return rc;
@@ -216,15 +224,29 @@ extern "C" int mclst_find_matches_dist(const float* bank, int64_t n_bank, int64_
     return rc;
   }
   const TcWorkspace& t = w.tc;
-  MCLST_CUDA(cudaMemsetAsync(t.stats, 0, 16 * sizeof(uint32_t), st));
-  prof_mark(st, "pack_rows");
-  if ((rc = launch_pack_rows(bank, n_bank, t.n_pad, ld_bank, dim, t.nkb, t.bpack, t.b_nrm,
-                             t.b_resid, t.stats, st))) return rc;
-  if ((rc = launch_pack_rows(query, n_query, t.q_pad, ld_query, dim, t.nkb, t.qpack, t.q_nrm,
-                             t.q_resid, t.stats + 8, st))) return rc;
+  if (stages & 1) {
+    prof_mark(st, "pack_rows");
+    if (!packed) {
+      MCLST_CUDA(cudaMemsetAsync(t.stats, 0, 8 * sizeof(uint32_t), st));
+      if ((rc = launch_pack_rows(bank, n_bank, t.n_pad, ld_bank, dim, t.nkb, t.bpack, t.b_nrm,
+                                 t.b_resid, t.stats, st))) return rc;
+    }
+    if (n_query == 0) { prof_mark(st, "end"); return 0; }
+    MCLST_CUDA(cudaMemsetAsync(w.counters, 0, 256, st));
+    MCLST_CUDA(cudaMemsetAsync(t.stats + 8, 0, 8 * sizeof(uint32_t), st));
+    if ((rc = launch_pack_rows(query, n_query, t.q_pad, ld_query, dim, t.nkb, t.qpack, t.q_nrm,
+                               t.q_resid, t.stats + 8, st))) return rc;
+    if (stages == 1) {          // seed pass alone; the main pass follows in a second call
+      prof_mark(st, "sim_seed");
+      if ((rc = launch_sim_topk(t, n_bank, n_query, top_k, nullptr, 0, st, 1, sb))) return rc;
+      prof_mark(st, "end");
+      return 0;
+    }
+  }
+  if (n_query == 0) return 0;
   prof_mark(st, "sim_topk");
-  if ((rc = launch_sim_topk(t, n_bank, n_query, top_k, nullptr, 0, st))) return rc;
-  if (sim_topk_ablate() != 0) {     // timing experiment, no results
+  if ((rc = launch_sim_topk(t, n_bank, n_query, top_k, nullptr, 0, st, (stages & 1) ? 0 : 2, sb))) return rc;
+  if (sim_topk_ablate() != 0) {     // timing experiment (tuning builds only), no results
     MCLST_CUDA(cudaMemsetAsync(out_indices, 0, (size_t)n_query * top_k * sizeof(int64_t), st));
     prof_mark(st, "end");
     return 0;
@@ -232,7 +254,7 @@ extern "C" int mclst_find_matches_dist(const float* bank, int64_t n_bank, int64_
   prof_mark(st, "rerank");
   if ((rc = launch_rerank(t, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k,
                           index_offset, out_indices, out_values, out_distances, dist_p, w.counters,
-                          st))) return rc;
+                          st, sb && sb->ext_bound))) return rc;
   prof_mark(st, "exact_fallback");
   rc = launch_exact_topk(bank, n_bank, ld_bank, w.bank_nrm, query, ld_query, w.q_nrm, dim,
                          t.fb_list, w.counters, 0, n_query, top_k, index_offset, w.scratch,
@@ -242,6 +264,50 @@ extern "C" int mclst_find_matches_dist(const float* bank, int64_t n_bank, int64_
                                    top_k, index_offset, dist_p, out_distances, t.fb_list, w.counters, st);
   prof_mark(st, "end");
   return rc;
+}
+
+extern "C" int mclst_find_matches_dist(const float* bank, int64_t n_bank, int64_t ld_bank,
+                                       const float* query, int64_t n_query, int64_t ld_query,
+                                       int dim, int top_k, int64_t index_offset,
+                                       int64_t* out_indices, float* out_values,
+                                       float* out_distances, int dist_p, void* workspace,
+                                       size_t workspace_bytes, int flags, mclst_stream_t stream) {
+  if (n_query == 0 && n_bank >= 0 && !(flags & MCLST_FM_BANK_PACKED)) return 0;
+  return find_matches_stages(3, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k, index_offset,
+                             out_indices, out_values, out_distances, dist_p, nullptr, workspace,
+                             workspace_bytes, flags, (cudaStream_t)stream);
+}
+
+extern "C" int mclst_find_matches_pack_bank(const float* bank, int64_t n_bank, int64_t ld_bank, int dim,
+                                            int top_k, void* workspace, size_t workspace_bytes,
+                                            mclst_stream_t stream) {
+  return find_matches_stages(1, bank, n_bank, ld_bank, nullptr, 0, dim, dim, top_k, 0, nullptr, nullptr,
+                             nullptr, 2, nullptr, workspace, workspace_bytes, 0, (cudaStream_t)stream);
+}
+
+extern "C" int mclst_find_matches_seed(const float* bank, int64_t n_bank, int64_t ld_bank,
+                                       const float* query, int64_t n_query, int64_t ld_query, int dim,
+                                       int top_k, int k_part, float* bound_k, float* bound_part,
+                                       void* workspace, size_t workspace_bytes, int flags,
+                                       mclst_stream_t stream) {
+  MCLST_REQUIRE(k_part >= 1 && k_part <= top_k, MCLST_ERR_INVALID, "find_matches_seed: k_part");
+  SeedBounds sb{k_part, bound_k, bound_part, nullptr};
+  return find_matches_stages(1, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k, 0, nullptr,
+                             nullptr, nullptr, 2, &sb, workspace, workspace_bytes, flags,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int mclst_find_matches_main(const float* bank, int64_t n_bank, int64_t ld_bank,
+                                       const float* query, int64_t n_query, int64_t ld_query, int dim,
+                                       int top_k, int64_t index_offset, int64_t* out_indices,
+                                       float* out_values, float* out_distances, int dist_p,
+                                       const float* ext_bound, void* workspace, size_t workspace_bytes,
+                                       int flags, mclst_stream_t stream) {
+  if (n_query == 0) return 0;
+  SeedBounds sb{1, nullptr, nullptr, ext_bound};
+  return find_matches_stages(2, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k, index_offset,
+                             out_indices, out_values, out_distances, dist_p, &sb, workspace,
+                             workspace_bytes, flags, (cudaStream_t)stream);
 }
 
 // Testing aid: the raw tensor-core similarities the candidate pass sees (fp16-rounded

@@ -47,9 +47,13 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 }
 
 // lse[r] = log sum_j exp(P[r, j]) over j < ncols; optionally diag[r] = P[r, row0 + r].
+// The statistic is kept as a float pair hi + lo (|lo| <= ulp(hi)/2): logits reach +-256 here, where
+// one float32 ulp is 3e-5 -- rounding rl / cl / za to a single float puts that much SYSTEMATIC error
+// into every exponent of the row and costs the small gradient entries a digit (measured: 1.5e-3
+// element-wise vs 1e-4 with the pair).  Consumers form exp((x - hi) - lo).
 __global__ void __launch_bounds__(LS_THREADS)
 row_lse_kernel(const float* __restrict__ P, int64_t ld, int ncols, int64_t row0,
-               float* __restrict__ lse, float* __restrict__ diag) {
+               float* __restrict__ lse, float* __restrict__ lse_lo, float* __restrict__ diag) {
   __shared__ float sh[LS_THREADS / 32];
   const int64_t r = blockIdx.x;
   const float* p = P + r * ld;
@@ -69,7 +73,10 @@ row_lse_kernel(const float* __restrict__ P, int64_t ld, int ncols, int64_t row0,
   s = block_sum(m == -INFINITY ? 0.f : s * expf(m - mb), sh);
   m = mb;
   if (threadIdx.x == 0) {
-    lse[row0 + r] = m + logf(s);
+    const double L = (double)m + log((double)s);
+    const float hi = (float)L;
+    lse[row0 + r] = hi;
+    lse_lo[row0 + r] = (hi == hi && fabsf(hi) < INFINITY) ? (float)(L - (double)hi) : 0.f;
     if (diag) diag[row0 + r] = p[row0 + r];
   }
 }
@@ -78,16 +85,17 @@ row_lse_kernel(const float* __restrict__ P, int64_t ld, int ncols, int64_t row0,
 __global__ void __launch_bounds__(LS_THREADS)
 soft_pass2_kernel(const float* __restrict__ P1, const float* __restrict__ P3, int64_t ld, int ncols,
                   int64_t row0, const float* __restrict__ rl, const float* __restrict__ cl,
-                  const float* __restrict__ za, float* __restrict__ wbar, float* __restrict__ cs) {
+                  const float* __restrict__ za, const float* __restrict__ za_lo,
+                  float* __restrict__ wbar, float* __restrict__ cs) {
   __shared__ float sh[LS_THREADS / 32];
   const int64_t r = blockIdx.x, rg = row0 + r;
   const float* p1 = P1 + r * ld;
   const float* p3 = P3 + r * ld;
-  const float rl_r = rl[rg], za_r = za[rg];
+  const float rl_r = rl[rg], za_r = za[rg], zal_r = za_lo[rg];
   float w = 0.f, c = 0.f;
   auto push = [&](float a, float p1j, int j) {
-    w += expf(a - za_r) * (rl_r + __ldg(cl + j) - 2.f * p1j);
-    c += expf(a - __ldg(za + j));
+    w += expf((a - za_r) - zal_r) * (rl_r + __ldg(cl + j) - 2.f * p1j);
+    c += expf((a - __ldg(za + j)) - __ldg(za_lo + j));
   };
   const int n4 = ((ld & 3) == 0) ? (ncols >> 2) : 0;
   for (int j = threadIdx.x; j < n4; j += LS_THREADS) {
@@ -104,12 +112,14 @@ soft_pass2_kernel(const float* __restrict__ P1, const float* __restrict__ P3, in
 // loss = (1/2B) sum_r term_r; term = wbar (soft) or rl + cl - 2 diag (eye).  One block.
 __global__ void __launch_bounds__(LS_THREADS)
 loss_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                   const float* __restrict__ d, int r_begin, int r_end, int B,
+                   const float* __restrict__ d, const float* __restrict__ a_lo,
+                   const float* __restrict__ b_lo, int r_begin, int r_end, int B,
                    float* __restrict__ out) {
   __shared__ double shd[LS_THREADS / 32];
   double acc = 0.0;
   for (int r = r_begin + threadIdx.x; r < r_end; r += LS_THREADS)
-    acc += b ? (double)a[r] + (double)b[r] - 2.0 * (double)d[r] : (double)a[r];
+    acc += b ? ((double)a[r] + (double)a_lo[r]) + ((double)b[r] + (double)b_lo[r]) - 2.0 * (double)d[r]
+             : (double)a[r];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) shd[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -125,7 +135,7 @@ struct GradParams {
   int64_t ld;
   int B, rows, soft;           // rows = valid rows of this block
   int64_t row0;
-  const float *rl, *cl, *za, *wbar, *cs;
+  const float *rl, *cl, *za, *wbar, *cs, *rl_lo, *cl_lo, *za_lo;
   float inv_t, a_scale;
   uint8_t *ga_hi, *ga_lo, *gb_hi, *gb_lo;   // TilePack A operands, K = [B64 | B64] (soft) or [B64] (eye)
   int nkb_total, nkb_half;
@@ -158,13 +168,16 @@ grad_factor_kernel(const GradParams p, int64_t rows_pad) {
   const int64_t rgp = t / chunks;
   const int c = (int)(t - rgp * chunks);
   if (rgp * GF_ROWS >= rows_pad) return;
-  float rl_j[8], cl_j[8], za_j[8], wb_j[8], cs_j[8];
+  float rl_j[8], cl_j[8], za_j[8], wb_j[8], cs_j[8], rll_j[8], cll_j[8], zal_j[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int j = c * 8 + i;
     const bool ok = j < p.B;
     rl_j[i] = ok ? __ldg(p.rl + j) : 0.f;
     cl_j[i] = ok ? __ldg(p.cl + j) : 0.f;
+    rll_j[i] = ok ? __ldg(p.rl_lo + j) : 0.f;
+    cll_j[i] = ok ? __ldg(p.cl_lo + j) : 0.f;
+    zal_j[i] = (ok && p.soft) ? __ldg(p.za_lo + j) : 0.f;
     za_j[i] = (ok && p.soft) ? __ldg(p.za + j) : 0.f;
     wb_j[i] = (ok && p.soft) ? __ldg(p.wbar + j) : 0.f;
     cs_j[i] = (ok && p.soft) ? __ldg(p.cs + j) : 1.f;
@@ -178,6 +191,8 @@ grad_factor_kernel(const GradParams p, int64_t rows_pad) {
     if (r < p.rows) {
       const int64_t rg = p.row0 + r;
       const float rl_r = __ldg(p.rl + rg), cl_r = __ldg(p.cl + rg);
+      const float rll_r = __ldg(p.rl_lo + rg), cll_r = __ldg(p.cl_lo + rg);
+      const float zal_r = p.soft ? __ldg(p.za_lo + rg) : 0.f;
       const float za_r = p.soft ? __ldg(p.za + rg) : 0.f, wb_r = p.soft ? __ldg(p.wbar + rg) : 0.f;
       const float cs_r = p.soft ? __ldg(p.cs + rg) : 1.f;
       // the product rows are B64 wide: two 16-byte loads per array are always in bounds
@@ -199,16 +214,16 @@ grad_factor_kernel(const GradParams p, int64_t rows_pad) {
           float pt_rj, pt_jr;
           if (p.soft) {
             const float a = p3v[i];
-            pt_rj = expf(a - za_r);
-            pt_jr = expf(a - za_j[i]);
+            pt_rj = expf((a - za_r) - zal_r);
+            pt_jr = expf((a - za_j[i]) - zal_j[i]);
             const float da_rj = pt_rj * (rl_r + cl_j[i] - 2.f * p1 - wb_r);
             const float da_jr = pt_jr * (rl_j[i] + cl_r - 2.f * p2 - wb_j[i]);
             gs[i] = (da_rj + da_jr) * p.a_scale;
           } else {
             pt_rj = pt_jr = (rg == j) ? 1.f : 0.f;
           }
-          g1[i] = (expf(p1 - rl_r) + cs_j[i] * expf(p1 - cl_j[i]) - 2.f * pt_rj) * p.inv_t;   // 2B * dLg_rj / T
-          g2[i] = (expf(p2 - rl_j[i]) + cs_r * expf(p2 - cl_r) - 2.f * pt_jr) * p.inv_t;      // 2B * dLg_jr / T
+          g1[i] = (expf((p1 - rl_r) - rll_r) + cs_j[i] * expf((p1 - cl_j[i]) - cll_j[i]) - 2.f * pt_rj) * p.inv_t;   // 2B * dLg_rj / T
+          g2[i] = (expf((p2 - rl_j[i]) - rll_j[i]) + cs_r * expf((p2 - cl_r) - cll_r) - 2.f * pt_jr) * p.inv_t;      // 2B * dLg_jr / T
         }
       }
     }
@@ -232,7 +247,7 @@ struct LossPlan {
   PackedOperand XT_IS, XT_SI;      // [D, 2*B64] (soft) or [D, B64] (eye), transposed packs
   PackedOperand GA, GB;            // [R, 2*B64] / [R, B64]
   float *P1, *P2, *P3;
-  float *rl, *cl, *za, *wbar, *cs, *diag;   // views into the stats block [6][B]
+  float *rl, *cl, *za, *wbar, *cs, *diag, *rl_lo, *cl_lo, *za_lo;   // views into the stats block [9][B]
   float* stats_ws;
   size_t bytes;
 };
@@ -264,7 +279,7 @@ static LossPlan plan_loss(void* ws, size_t cap, int B, int D, int soft, int want
   L.P1 = a.take<float>((size_t)R * L.B64);
   L.P2 = a.take<float>((size_t)R * L.B64);
   L.P3 = soft ? a.take<float>((size_t)R * L.B64) : nullptr;
-  L.stats_ws = a.take<float>((size_t)6 * B);
+  L.stats_ws = a.take<float>((size_t)MCLST_LOSS_STAT_ROWS * B);
   L.bytes = align_up(a.off, 256);
   return L;
 }
@@ -309,6 +324,7 @@ static void bind_stats(LossPlan& L, float* stats) {
   const size_t B = (size_t)L.B;
   L.rl = stats; L.cl = stats + B; L.za = stats + 2 * B; L.wbar = stats + 3 * B; L.cs = stats + 4 * B;
   L.diag = stats + 5 * B;
+  L.rl_lo = stats + 6 * B; L.cl_lo = stats + 7 * B; L.za_lo = stats + 8 * B;
 }
 
 // One phase of the loss for the rows [row0, row0 + rows) of the (all-gathered) batch.
@@ -358,12 +374,12 @@ static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_em
       const int64_t i0 = row0 + b * L.R, nr = std::min<int64_t>(L.R, row0 + rows - i0);
       if ((rc = compute_blocks(L, i0, nr, inv_t, a_scale, true, st))) return rc;
       prof_mark(st, "row_lse");
-      row_lse_kernel<<<(unsigned)nr, LS_THREADS, 0, st>>>(L.P1, L.B64, B, i0, L.rl, L.diag);
+      row_lse_kernel<<<(unsigned)nr, LS_THREADS, 0, st>>>(L.P1, L.B64, B, i0, L.rl, L.rl_lo, L.diag);
       MCLST_LAUNCH_CHECK();
-      row_lse_kernel<<<(unsigned)nr, LS_THREADS, 0, st>>>(L.P2, L.B64, B, i0, L.cl, nullptr);
+      row_lse_kernel<<<(unsigned)nr, LS_THREADS, 0, st>>>(L.P2, L.B64, B, i0, L.cl, L.cl_lo, nullptr);
       MCLST_LAUNCH_CHECK();
       if (soft) {
-        row_lse_kernel<<<(unsigned)nr, LS_THREADS, 0, st>>>(L.P3, L.B64, B, i0, L.za, nullptr);
+        row_lse_kernel<<<(unsigned)nr, LS_THREADS, 0, st>>>(L.P3, L.B64, B, i0, L.za, L.za_lo, nullptr);
         MCLST_LAUNCH_CHECK();
       }
     }
@@ -374,14 +390,14 @@ static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_em
         if (!single && (rc = compute_blocks(L, i0, nr, inv_t, a_scale, false, st))) return rc;
         prof_mark(st, "soft_pass2");
         soft_pass2_kernel<<<(unsigned)nr, LS_THREADS, 0, st>>>(L.P1, L.P3, L.B64, B, i0, L.rl, L.cl,
-                                                             L.za, L.wbar, L.cs);
+                                                             L.za, L.za_lo, L.wbar, L.cs);
         MCLST_LAUNCH_CHECK();
       }
     }
   } else {
     prof_mark(st, "loss_reduce");
-    if (soft) loss_reduce_kernel<<<1, LS_THREADS, 0, st>>>(L.wbar, nullptr, nullptr, (int)row0, (int)(row0 + rows), B, loss_out);
-    else loss_reduce_kernel<<<1, LS_THREADS, 0, st>>>(L.rl, L.cl, L.diag, (int)row0, (int)(row0 + rows), B, loss_out);
+    if (soft) loss_reduce_kernel<<<1, LS_THREADS, 0, st>>>(L.wbar, nullptr, nullptr, nullptr, nullptr, (int)row0, (int)(row0 + rows), B, loss_out);
+    else loss_reduce_kernel<<<1, LS_THREADS, 0, st>>>(L.rl, L.cl, L.diag, L.rl_lo, L.cl_lo, (int)row0, (int)(row0 + rows), B, loss_out);
     MCLST_LAUNCH_CHECK();
     if (d_spot) {
       for (int64_t b = 0; b < L.nblocks; ++b) {
@@ -393,6 +409,7 @@ static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_em
         // the two K halves carry different scalars (1/T and a); the larger one goes into alpha so that
         // the stored factors stay O(1) whatever the temperature (fp16 range)
         const float u = std::max(inv_t, a_scale);
+        gp.rl_lo = L.rl_lo; gp.cl_lo = L.cl_lo; gp.za_lo = L.za_lo;
         gp.cs = L.cs; gp.inv_t = inv_t / u; gp.a_scale = a_scale / u;
         gp.ga_hi = L.GA.hi; gp.ga_lo = L.GA.lo; gp.gb_hi = L.GB.hi; gp.gb_lo = L.GB.lo;
         gp.nkb_total = L.GA.nkb; gp.nkb_half = (int)(L.B64 / 64);

@@ -36,12 +36,19 @@ int sim_topk_ablate();   // timing experiments only: results are garbage when no
 void tc_workspace(Arena& a, int64_t n_bank, int64_t n_query, int dim, int top_k, TcWorkspace& w);
 int launch_pack_rows(const float* x, int64_t rows, int64_t rows_pad, int64_t ld, int dim, int nkb,
                      uint8_t* packed, double* nrm, float* resid, uint32_t* stats, cudaStream_t st);
+// cross-shard exchange around the seed pass (sim_topk.cu): outputs of phase 1, input of phase 2
+struct SeedBounds {
+  int k_part;              // bound_part is about the k_part-th best of this shard's sample
+  float* bound_k;          // [Q] >= k rows of this shard have an exact score >= bound_k[q] (-inf: unknown)
+  float* bound_part;       // [Q] same for k_part rows
+  const float* ext_bound;  // [Q] lower bound of the exact GLOBAL k-th best score, or null
+};
 int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int top_k, float* dump,
-                    int64_t dump_ld, cudaStream_t st);
+                    int64_t dump_ld, cudaStream_t st, int phase = 0, const SeedBounds* sb = nullptr);
 int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64_t ldb,
                   const float* query, int64_t n_query, int64_t ldq, int dim, int top_k,
                   int64_t index_offset, int64_t* out_idx, float* out_val, float* out_dist, int dist_p,
-                  int* counters, cudaStream_t st);
+                  int* counters, cudaStream_t st, bool allow_partial = false);
 // distances of the winners of the queries in qlist (exact-fallback rows) or of all queries
 int launch_neighbor_distances(const float* spot_key, int64_t n_bank, int64_t ld_key, const float* query,
                               int64_t n_query, int64_t ld_query, int dim, const int64_t* indices, int k,

@@ -1135,12 +1135,13 @@ sim_topk_ring_kernel(const SimParams p) {
 __global__ void __launch_bounds__(128)
 seed_threshold_kernel(const float* __restrict__ seed, int n_vals, int64_t Q, int k,
                       const float* __restrict__ q_resid, const uint32_t* __restrict__ bank_stats,
-                      uint32_t* __restrict__ gthr) {
+                      uint32_t* __restrict__ gthr, int k2, float* __restrict__ bound_k,
+                      float* __restrict__ bound_part) {
   const int lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (q >= Q) return;
   const float* v = seed + (size_t)q * n_vals;
-  uint32_t T = 0;
+  uint32_t T = 0, T2 = 0;       // T2: the k2-th largest (k2 <= k), for the cross-shard bound
   if (n_vals <= 1024) {
     // the usual case: the whole sample as ordered keys in registers, 24 compare sweeps
     uint32_t key[32];
@@ -1154,6 +1155,16 @@ seed_threshold_kernel(const float* __restrict__ seed, int n_vals, int64_t Q, int
       c = __reduce_add_sync(0xffffffffu, c);
       if (c >= k) T = cand;
     }
+    if (bound_part) {
+      for (int bit = 31; bit >= 8; --bit) {
+        const uint32_t cand = T2 | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) c += (key[i] >= cand) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= k2) T2 = cand;
+      }
+    }
   } else {
     for (int bit = 31; bit >= 8; --bit) {
       const uint32_t cand = T | (1u << bit);
@@ -1162,11 +1173,48 @@ seed_threshold_kernel(const float* __restrict__ seed, int n_vals, int64_t Q, int
       c = __reduce_add_sync(0xffffffffu, c);
       if (c >= k) T = cand;
     }
+    if (bound_part) {
+      for (int bit = 31; bit >= 8; --bit) {
+        const uint32_t cand = T2 | (1u << bit);
+        int c = 0;
+        for (int i = lane; i < n_vals; i += 32) c += (f2ord(v[i]) >= cand) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= k2) T2 = cand;
+      }
+    }
   }
-  if (lane == 0 && T != 0u) {
-    const float e2 = 2.02f * pair_eps(q_resid[q], __uint_as_float(bank_stats[0]));
-    const float thr = ord2f(T) - e2;
-    if (thr == thr && thr > -INFINITY) gthr[q] = f2ord(thr);
+  if (lane == 0) {
+    const float e1 = 1.01f * pair_eps(q_resid[q], __uint_as_float(bank_stats[0]));
+    if (T != 0u) {
+      const float thr = ord2f(T) - 2.f * e1;
+      if (thr == thr && thr > -INFINITY) gthr[q] = f2ord(thr);
+    }
+    // lower bounds of EXACT scores: at least k (k2) rows of this shard score >= bound
+    if (bound_k) { const float b = ord2f(T) - e1; bound_k[q] = (T != 0u && b == b) ? b : -INFINITY; }
+    if (bound_part) { const float b = ord2f(T2) - e1; bound_part[q] = (T2 != 0u && b == b) ? b : -INFINITY; }
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ x, int64_t n, float v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = v;
+}
+
+// Cross-shard warm start: `bound` is a lower bound of the exact GLOBAL k-th best score of every
+// query (exchanged between the ranks that hold the other bank shards).  A row of this shard whose
+// tensor-core score is below bound - 1.01 eps is strictly worse than k rows somewhere, so the
+// running threshold may start there.
+__global__ void __launch_bounds__(256)
+apply_bound_kernel(const float* __restrict__ bound, int64_t Q, const float* __restrict__ q_resid,
+                   const uint32_t* __restrict__ bank_stats, uint32_t* __restrict__ gthr) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const float b = bound[q];
+  if (!(b > -INFINITY) || !(b < INFINITY)) return;
+  const float thr = b - 1.01f * pair_eps(q_resid[q], __uint_as_float(bank_stats[0]));
+  if (thr == thr && thr > -INFINITY) {
+    const uint32_t key = f2ord(thr);
+    if (key > gthr[q]) gthr[q] = key;
   }
 }
 
@@ -1187,6 +1235,7 @@ struct RerankParams {
   int64_t* out_idx; float* out_val;
   float* out_dist; int dist_p;     // optional: L1 (p=1) / L2 (p=2) distance of each winner to the raw query
   int* fb_list; int* counters;     // counters[0] = fallback count, [1] = resolved here
+  int allow_partial;               // an external bound was applied: fewer than k survivors is legitimate
 };
 
 // exact cosine of one bank row against the query held in qh[] (raw values as doubles):
@@ -1323,10 +1372,12 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
     }
   }
   __syncwarp();
-  if (M < p.k) bad = true;      // cannot happen for finite inputs; the exact path decides
+  // fewer than k survivors: impossible for finite inputs with this shard's own thresholds (the
+  // exact path decides), legitimate under a cross-shard bound (the rest of the list is padding)
+  if (M < p.k && !p.allow_partial) bad = true;
   int n_s = 0;
   if (!bad) {
-    n_s = tighten(M);
+    n_s = (M < p.k) ? M : tighten(M);       // (the band needs k entries to be defined)
     if (n_s > RR_MAX) bad = true;
   }
   if (bad) {
@@ -1406,10 +1457,16 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
     }
   }
   for (int j = lane; j < p.k; j += 32) {
-    const unsigned long long e = ent[j];
-    p.out_idx[q * p.k + j] = (int64_t)(0xffffffffu - (uint32_t)e) + p.index_offset;
-    if (p.out_val) p.out_val[q * p.k + j] = ord2f((uint32_t)(e >> 32));
-    if (want_dist) p.out_dist[q * p.k + j] = pay[slot[j]];
+    if (j < n_s) {
+      const unsigned long long e = ent[j];
+      p.out_idx[q * p.k + j] = (int64_t)(0xffffffffu - (uint32_t)e) + p.index_offset;
+      if (p.out_val) p.out_val[q * p.k + j] = ord2f((uint32_t)(e >> 32));
+      if (want_dist) p.out_dist[q * p.k + j] = pay[slot[j]];
+    } else {                       // padding of a partial list: loses every merge
+      p.out_idx[q * p.k + j] = 0x7fffffffll;
+      if (p.out_val) p.out_val[q * p.k + j] = -INFINITY;
+      if (want_dist) p.out_dist[q * p.k + j] = INFINITY;
+    }
   }
   if (lane == 0) atomicAdd(&p.counters[1], 1);
 }
@@ -1485,13 +1542,15 @@ void tc_workspace(Arena& a, int64_t n_bank, int64_t n_query, int dim, int top_k,
     w.S = plan_lanes(w.q_pad / 128, w.n_pad / ST_BN, sm_count(), std::max(1, 8 / (w.epw / 4))).slots;
   w.SS = w.ring ? w.S : w.S * (w.epw / 4);
   w.cap = tc_cap_for_k(top_k);
+  // everything derived from the bank first: its offsets do not depend on the query count, so a
+  // resident bank (MCLST_FM_BANK_PACKED) stays valid across calls with different query batches
   w.stats = a.take<uint32_t>(16);
-  w.qpack = a.take<uint8_t>(tilepack_bytes(w.q_pad, nkb * 64));
   w.bpack = a.take<uint8_t>(tilepack_bytes(w.n_pad, nkb * 64));
-  w.q_nrm = a.take<double>((size_t)w.q_pad);
-  w.q_resid = a.take<float>((size_t)w.q_pad);
   w.b_nrm = a.take<double>((size_t)w.n_pad);
   w.b_resid = a.take<float>((size_t)w.n_pad);
+  w.qpack = a.take<uint8_t>(tilepack_bytes(w.q_pad, nkb * 64));
+  w.q_nrm = a.take<double>((size_t)w.q_pad);
+  w.q_resid = a.take<float>((size_t)w.q_pad);
   w.gthr = a.take<uint32_t>((size_t)w.q_pad);
   w.cand = a.take<uint2>((size_t)w.q_pad * w.SS * w.cap);
   w.cand_cnt = a.take<int>((size_t)w.q_pad * w.SS);
@@ -1553,7 +1612,9 @@ static int launch_sim_topk_e(int epw, const SimParams& p, dim3 grid, cudaStream_
 }
 
 int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int top_k, float* dump,
-                    int64_t dump_ld, cudaStream_t st) {
+                    int64_t dump_ld, cudaStream_t st, int phase, const SeedBounds* sb) {
+  // phase 0: seed pass + main pass; 1: thresholds reset + seed pass only (optionally writing the
+  // cross-shard bounds of sb); 2: main pass only, after applying sb->ext_bound when given
   SimParams p;
   p.qpack = w.qpack; p.bpack = w.bpack; p.nkb = w.nkb; p.Q = n_query; p.N = n_bank;
   p.tiles_total = (int)(w.n_pad / ST_BN); p.S = w.S; p.k = top_k;
@@ -1564,9 +1625,20 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
   static const int gap_env = env_int("MCLST_SIM_PRUNE_GAP", 1 << 20);
   p.prune_gap = gap_env;
   static const int keep_gthr = env_int("MCLST_SIM_KEEP_GTHR", 0);   // experiment: warm thresholds
-  if (!keep_gthr) MCLST_CUDA(cudaMemsetAsync(w.gthr, 0, (size_t)w.q_pad * sizeof(uint32_t), st));
+  if (!keep_gthr && phase != 2) MCLST_CUDA(cudaMemsetAsync(w.gthr, 0, (size_t)w.q_pad * sizeof(uint32_t), st));
   dim3 grid((unsigned)(w.q_pad / 128), (unsigned)w.S);
-  if (w.n_seed > 0 && dump == nullptr && !keep_gthr && p.ablate == 0) {
+  const bool seeded = w.n_seed > 0 && dump == nullptr && !keep_gthr && p.ablate == 0;
+  if (phase == 1 && !seeded && sb) {       // no sample: no bound to offer
+    if (sb->bound_k) fill_kernel<<<(unsigned)ceil_div(n_query, 256), 256, 0, st>>>(sb->bound_k, n_query, -INFINITY);
+    if (sb->bound_part) fill_kernel<<<(unsigned)ceil_div(n_query, 256), 256, 0, st>>>(sb->bound_part, n_query, -INFINITY);
+    MCLST_LAUNCH_CHECK();
+  }
+  if (phase == 2 && sb && sb->ext_bound) {
+    apply_bound_kernel<<<(unsigned)ceil_div(n_query, 256), 256, 0, st>>>(sb->ext_bound, n_query, w.q_resid,
+                                                                        w.stats, w.gthr);
+    MCLST_LAUNCH_CHECK();
+  }
+  if (seeded && phase != 2) {
     // ---- seed pass (legacy drain, 8 epilogue warps, one CTA per query block)
     SimParams sp = p;
     sp.seed_out = w.seed; sp.n_tiles = w.n_seed; sp.tile_begin = 0;
@@ -1585,9 +1657,11 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
       if (rc) return rc;
     }
     seed_threshold_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, st>>>(
-        w.seed, w.n_seed * 8, n_query, top_k, w.q_resid, w.stats, w.gthr);
+        w.seed, w.n_seed * 8, n_query, top_k, w.q_resid, w.stats, w.gthr, sb ? std::max(1, sb->k_part) : 1,
+        sb ? sb->bound_k : nullptr, sb ? sb->bound_part : nullptr);
     MCLST_LAUNCH_CHECK();
   }
+  if (phase == 1) return 0;
   if (w.ring) {
     auto launch_ring = [&](auto kern) -> int {
       MCLST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RG_SMEM));
@@ -1630,8 +1704,9 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
 int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64_t ldb,
                   const float* query, int64_t n_query, int64_t ldq, int dim, int top_k,
                   int64_t index_offset, int64_t* out_idx, float* out_val, float* out_dist, int dist_p,
-                  int* counters, cudaStream_t st) {
+                  int* counters, cudaStream_t st, bool allow_partial) {
   RerankParams p;
+  p.allow_partial = allow_partial ? 1 : 0;
   p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.SS = w.SS; p.cap = w.cap; p.k = top_k;
   p.Q = n_query; p.N = n_bank; p.bank = bank; p.ldb = ldb; p.bank_nrm = w.b_nrm;
   p.query = query; p.ldq = ldq; p.q_nrm = w.q_nrm; p.q_resid = w.q_resid;

@@ -47,6 +47,20 @@ class BankShard:
     index_offset: int               # global index of local row 0
     n_total: int
     expr_ready: Optional["torch.cuda.Event"] = None   # set when expression_key is still uploading
+    _ws: Optional[dict] = None       # (slot, top_k) -> (workspace holding this shard's packed image, query capacity)
+
+    def workspace(self, slot: int, n_query: int, top_k: int):
+        """(workspace, already_packed) for one of the query blocks in flight: the shard's packed image
+        (normalised fp16 tiles, norms, residuals) is written on first use and stays resident."""
+        from .retrieval import fm_workspace
+        if self._ws is None:
+            self._ws = {}
+        ent = self._ws.get((slot, top_k))
+        if ent is None or ent[1] < n_query:
+            ws = fm_workspace(self.spot_key.shape[0], n_query, self.spot_key.shape[1], top_k, self.spot_key.device)
+            self._ws[(slot, top_k)] = (ws, n_query)
+            return ws, False
+        return ent[0], True
 
     @classmethod
     def from_full(cls, spot_key, expression_key, rank: int, world: int) -> "BankShard":
@@ -125,36 +139,140 @@ class CudaBackend:
         return out
 
 
-def _all_gather_stack(t: torch.Tensor, group) -> torch.Tensor:
+def _all_gather_cat(t: torch.Tensor, group, async_op: bool = False):
+    """[R * rows, ...] = the ranks' tensors concatenated along dim 0, written by ONE collective
+    straight into its final place (no per-rank list, no stack copy)."""
     world = dist.get_world_size(group)
-    out = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(out, t.contiguous(), group=group)
-    return torch.stack(out)
+    t = t.contiguous()
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    work = dist.all_gather_into_tensor(out, t, group=group, async_op=async_op)
+    return out, work
+
+
+def _tc_eligible(shard: BankShard, k: int) -> bool:
+    n, d = shard.spot_key.shape
+    return d <= 256 and k <= 896 and n >= k
+
+
+class _Block:
+    """One query block of a sharded retrieval on its way through the pipeline."""
+    __slots__ = ("q", "ws", "packed", "bounds", "w_bounds", "val", "idx", "dst", "g", "w_g", "expr", "emb",
+                 "w_out", "rows")
 
 
 def retrieve_sharded(shard: BankShard, query: torch.Tensor, top_k: int = 50, mode: str = "inv_sq_l2",
-                     group=None, backend=None, want_emb: bool = False):
+                     group=None, backend=None, want_emb: bool = False, scatter_output: bool = False,
+                     query_blocks: Optional[int] = None):
     """(indices int64 [Q,k], values f32 [Q,k], emb_pred | None, expr_pred f32 [Q,G]) -- identical on
-    every rank and equal to the single-GPU ``retrieve_device`` on the concatenated bank."""
+    every rank and equal to the single-GPU ``retrieve_device`` on the concatenated bank.
+
+    With ``scatter_output`` the partial sums are reduce-scattered instead of all-reduced: every rank
+    keeps only its share of the finished rows and the call returns a fifth value ``rows`` (int64 row
+    numbers into the query batch) -- expr_pred / emb_pred then hold exactly those rows.
+
+    Bank shards (CUDA backend): per query block  seed pass -> all-reduce of per-query bounds of the
+    GLOBAL k-th best score (2 floats per query) -> main pass against that bound -> all-gather of the
+    candidate lists -> merge -> owner-only partial sums -> reduce-scatter / all-reduce.  The queries
+    go in ``query_blocks`` blocks (default 2 when large) so that the collectives of one block run
+    under the top-k kernels of the next."""
     backend = backend or CudaBackend()
     need_dist = mode in ("inv_sq_l1", "inv_sq_l2", "bleep_exp")
     p = 1 if mode == "inv_sq_l1" else 2
-    val, idx, dst = backend.local_topk(shard, query, top_k, p, need_dist)
     world = dist.get_world_size(group) if (dist.is_initialized() and shard.n_total != shard.spot_key.shape[0]) else 1
-    if world > 1:
-        vals = _all_gather_stack(val, group)
-        idxs = _all_gather_stack(idx, group)
-        dsts = _all_gather_stack(dst, group) if need_dist else None
-        val, idx, dst = backend.merge(vals, idxs, dsts, top_k)
-    w = backend.weights(dst, val, mode)
+    Q = query.shape[0]
+    if world == 1:
+        val, idx, dst = backend.local_topk(shard, query, top_k, p, need_dist)
+        w = backend.weights(dst, val, mode)
+        if shard.expr_ready is not None:
+            torch.cuda.current_stream(shard.expression_key.device).wait_event(shard.expr_ready)
+        expr = backend.partial_average(shard.expression_key, shard.index_offset, idx, w)
+        emb = backend.partial_average(shard.spot_key, shard.index_offset, idx, w) if want_emb else None
+        if scatter_output:
+            return idx, val, emb, expr, torch.arange(Q, device=query.device)
+        return idx, val, emb, expr
+    rank = dist.get_rank(group)
+    staged = isinstance(backend, CudaBackend) and _tc_eligible(shard, top_k) and Q > 0
+    nb = query_blocks if query_blocks else (2 if Q >= 8192 else 1)
+    nb = max(1, min(nb, Q)) if Q else 1
+    scatter = scatter_output and dist.get_backend(group) == "nccl"
+    cuts = [Q * b // nb for b in range(nb + 1)]
+    blocks: List[_Block] = []
+    for b in range(nb):
+        blk = _Block()
+        blk.q = query[cuts[b]:cuts[b + 1]]
+        blk.rows = None
+        blocks.append(blk)
+    # -- stage 1: seed pass of every block, bounds exchange in flight
+    if staged:
+        from .retrieval import fm_seed
+        k_part = -(-top_k // world)
+        for b, blk in enumerate(blocks):
+            blk.ws, blk.packed = shard.workspace(b, blk.q.shape[0], top_k)
+            bounds = fm_seed(shard.spot_key, blk.q, top_k, blk.ws, k_part, want_bounds=True, bank_packed=blk.packed)
+            # one MAX all-reduce carries both: row 0 = bound_k (max over shards is valid), row 1 = minus
+            # bound_part (min over shards of the ceil(k/R)-th best: every shard then has that many rows)
+            bounds[1].neg_()
+            blk.bounds = bounds
+            blk.w_bounds = dist.all_reduce(bounds, op=dist.ReduceOp.MAX, group=group, async_op=True)
+    # -- stage 2: main pass (+ candidate all-gather in flight)
+    for blk in blocks:
+        if staged:
+            from .retrieval import fm_main
+            blk.w_bounds.wait()
+            ext = torch.maximum(blk.bounds[0], -blk.bounds[1]).contiguous()
+            blk.val, blk.idx, blk.dst = fm_main(shard.spot_key, blk.q, top_k, blk.ws, shard.index_offset,
+                                                p if need_dist else None, ext, bank_packed=True)
+        else:
+            blk.val, blk.idx, blk.dst = backend.local_topk(shard, blk.q, top_k, p, need_dist)
+        Qb = blk.q.shape[0]
+        # (similarity, distance, index) of every candidate in ONE collective: index as two float32 words
+        parts = [blk.val.view(Qb, top_k, 1), blk.idx.view(torch.float32).view(Qb, top_k, 2)]
+        if need_dist:
+            parts.append(blk.dst.view(Qb, top_k, 1))
+        blk.g, blk.w_g = _all_gather_cat(torch.cat(parts, dim=2), group, async_op=True)
+    # -- stage 3: merge, weights, owner-only partial sums (+ reduction in flight)
     if shard.expr_ready is not None:
         torch.cuda.current_stream(shard.expression_key.device).wait_event(shard.expr_ready)
-    expr = backend.partial_average(shard.expression_key, shard.index_offset, idx, w)
-    emb = backend.partial_average(shard.spot_key, shard.index_offset, idx, w) if want_emb else None
-    if world > 1:
-        dist.all_reduce(expr, group=group)
-        if emb is not None:
-            dist.all_reduce(emb, group=group)
+    for blk in blocks:
+        blk.w_g.wait()
+        Qb = blk.q.shape[0]
+        g = blk.g.view(world, Qb, top_k, -1)
+        vals = g[..., 0].contiguous()
+        idxs = g[..., 1:3].contiguous().view(torch.int64).view(world, Qb, top_k)
+        dsts = g[..., 3].contiguous() if need_dist else None
+        blk.val, blk.idx, blk.dst = backend.merge(vals, idxs, dsts, top_k)
+        w = backend.weights(blk.dst, blk.val, mode)
+        part = backend.partial_average(shard.expression_key, shard.index_offset, blk.idx, w)
+        if want_emb:
+            part = torch.cat([part, backend.partial_average(shard.spot_key, shard.index_offset, blk.idx, w)], dim=1)
+        if scatter and Qb % world == 0:
+            out = torch.empty((Qb // world, part.shape[1]), dtype=part.dtype, device=part.device)
+            blk.w_out = dist.reduce_scatter_tensor(out, part, group=group, async_op=True)
+            blk.expr = out
+        else:
+            blk.w_out = dist.all_reduce(part, group=group, async_op=True)
+            blk.expr = part
+    G = shard.expression_key.shape[1]
+    outs, rows = [], []
+    for b, blk in enumerate(blocks):
+        blk.w_out.wait()
+        Qb = blk.q.shape[0]
+        if scatter_output:
+            if scatter and Qb % world == 0:
+                lo, hi = Qb // world * rank, Qb // world * (rank + 1)
+                outs.append(blk.expr)
+            else:
+                lo, hi = shard_bounds(Qb, world)[rank]
+                outs.append(blk.expr[lo:hi])
+            rows.append(torch.arange(cuts[b] + lo, cuts[b] + hi, device=query.device))
+        else:
+            outs.append(blk.expr)
+    full = torch.cat(outs) if len(outs) > 1 else outs[0]
+    idx = torch.cat([blk.idx for blk in blocks]) if nb > 1 else blocks[0].idx
+    val = torch.cat([blk.val for blk in blocks]) if nb > 1 else blocks[0].val
+    expr, emb = (full[:, :G], full[:, G:]) if want_emb else (full, None)
+    if scatter_output:
+        return idx, val, emb, expr, (torch.cat(rows) if len(rows) > 1 else rows[0])
     return idx, val, emb, expr
 
 
@@ -211,7 +329,7 @@ class _ShardedLoss(torch.autograd.Function):
         nbytes = C.c_size_t()
         check(lib.mclst_contrastive_loss_workspace_bytes(B, D, mode, rows, C.byref(nbytes)), "loss workspace")
         ws = torch.empty(nbytes.value, dtype=torch.uint8, device=S.device)
-        stats = torch.zeros((6, B), dtype=torch.float32, device=S.device)
+        stats = torch.zeros((_lib.LOSS_STAT_ROWS, B), dtype=torch.float32, device=S.device)
         loss = torch.zeros((), dtype=torch.float32, device=S.device)
         dS = torch.empty((rows, D), dtype=torch.float32, device=S.device)
         dI = torch.empty((rows, D), dtype=torch.float32, device=S.device)
@@ -233,7 +351,7 @@ class _ShardedLoss(torch.autograd.Function):
             stats[sel] = full.view(world, len(sel), rows).permute(1, 0, 2).reshape(len(sel), B)
 
         phase(1)
-        gather_rows([0, 1, 2, 5])
+        gather_rows([0, 1, 2, 5, 6, 7, 8])      # rl, cl, za, diag + the lo halves of the three LSE pairs
         if mode != _lib.T_EYE:
             phase(2)
             gather_rows([3, 4])

@@ -23,7 +23,8 @@ from ._lib import WEIGHT_MODES, check, load, ptr, require_cuda, stream_ptr
 
 ArrayLike = Union[np.ndarray, torch.Tensor]
 
-__all__ = ["find_matches", "find_matches_cscc", "find_matches_device", "weighted_topk_average",
+__all__ = ["find_matches", "find_matches_cscc", "find_matches_device", "fm_workspace", "fm_pack_bank", "fm_seed",
+           "fm_main", "weighted_topk_average",
            "weighted_topk_average_device", "retrieve", "retrieve_device", "last_counters", "to_host", "Bank"]
 
 _last_ws: Optional[torch.Tensor] = None
@@ -113,6 +114,63 @@ def find_matches_device(spot_embeddings: torch.Tensor, query_embeddings: torch.T
               "find_matches")
     _last_ws = ws
     return (val, idx, dst) if dist_p else (val, idx)
+
+
+def fm_workspace(n_bank: int, n_query: int, dim: int, top_k: int, device, flags: int = 0) -> torch.Tensor:
+    nbytes = C.c_size_t()
+    check(load().mclst_find_matches_workspace_bytes(n_bank, n_query, dim, top_k, flags, C.byref(nbytes)),
+          "find_matches_workspace_bytes")
+    return torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=device)
+
+
+def fm_pack_bank(bank: torch.Tensor, top_k: int, ws: torch.Tensor) -> None:
+    """Write the packed image of ``bank`` (normalised fp16 operand tiles, float64 norms, rounding
+    residuals) into ``ws`` once; later staged calls pass ``bank_packed=True``."""
+    require_cuda(bank, ws)
+    with torch.cuda.device(bank.device):
+        check(load().mclst_find_matches_pack_bank(ptr(bank), bank.shape[0], bank.stride(0), bank.shape[1],
+                                                  top_k, ptr(ws), ws.numel(), stream_ptr()), "find_matches_pack_bank")
+
+
+def fm_seed(bank: torch.Tensor, qry: torch.Tensor, top_k: int, ws: torch.Tensor, k_part: int = 1,
+            want_bounds: bool = False, bank_packed: bool = False):
+    """Stage 1 of find_matches (pack + seed pass).  With ``want_bounds`` returns a float32 [2, Q]
+    tensor: row 0 = lower bound of this bank's own top_k-th best exact score per query, row 1 = the
+    same for its k_part-th best (-inf where nothing is known)."""
+    require_cuda(bank, qry, ws)
+    Q = qry.shape[0]
+    bounds = torch.empty((2, Q), dtype=torch.float32, device=bank.device) if want_bounds else None
+    flags = _lib.FM_BANK_PACKED if bank_packed else 0
+    with torch.cuda.device(bank.device):
+        check(load().mclst_find_matches_seed(ptr(bank), bank.shape[0], bank.stride(0), ptr(qry), Q, qry.stride(0),
+                                             bank.shape[1], top_k, k_part, ptr(bounds),
+                                             ptr(bounds[1]) if want_bounds else None, ptr(ws), ws.numel(),
+                                             flags, stream_ptr()), "find_matches_seed")
+    if want_bounds:
+        bounds = torch.nan_to_num(bounds, nan=float("-inf"), neginf=float("-inf"), posinf=float("inf"))
+    return bounds
+
+
+def fm_main(bank: torch.Tensor, qry: torch.Tensor, top_k: int, ws: torch.Tensor, index_offset: int = 0,
+            dist_p: Optional[int] = None, ext_bound: Optional[torch.Tensor] = None, bank_packed: bool = False):
+    """Stage 2 (main pass + re-rank + exact fallback) -> (values, indices, distances | None).  Under an
+    external bound a row list may be shorter than top_k; its tail is (-inf, 0x7fffffff, +inf)."""
+    global _last_ws
+    Q = qry.shape[0]
+    dev = bank.device
+    idx = torch.empty((Q, top_k), dtype=torch.int64, device=dev)
+    val = torch.empty((Q, top_k), dtype=torch.float32, device=dev)
+    dst = torch.empty((Q, top_k), dtype=torch.float32, device=dev) if dist_p else None
+    if ext_bound is not None:
+        assert ext_bound.dtype == torch.float32 and ext_bound.is_contiguous() and ext_bound.numel() == Q
+    flags = _lib.FM_BANK_PACKED if bank_packed else 0
+    with torch.cuda.device(dev):
+        check(load().mclst_find_matches_main(ptr(bank), bank.shape[0], bank.stride(0), ptr(qry), Q, qry.stride(0),
+                                             bank.shape[1], top_k, index_offset, ptr(idx), ptr(val), ptr(dst),
+                                             dist_p or 2, ptr(ext_bound), ptr(ws), ws.numel(), flags,
+                                             stream_ptr()), "find_matches_main")
+    _last_ws = ws
+    return val, idx, dst
 
 
 def last_counters() -> dict:
@@ -272,7 +330,11 @@ def retrieve(spot_key: ArrayLike, expression_key: ArrayLike, image_query: ArrayL
 
 class Bank:
     """A bank (spot_key, expression_key) kept resident on the device across many ``retrieve`` calls:
-    the serving form of the fold loop, where only the queries travel per call."""
+    the serving form of the fold loop, where only the queries travel per call -- and the hand-off
+    from the bank build (``embed.embed_bank`` output goes straight in, no ``.npy`` round trip,
+    evel_her2st.py:116-117,146-147).  Besides the raw rows the bank keeps the PACKED image the
+    top-k kernels consume (normalised fp16 operand tiles, float64 norms, rounding residuals), written
+    once per (top_k class, query capacity) instead of on every call."""
 
     def __init__(self, spot_key: ArrayLike, expression_key: ArrayLike, device=None):
         if not torch.cuda.is_available():
@@ -282,14 +344,54 @@ class Bank:
         self.expression_key = _to_dev(expression_key, dev, (torch.float32, torch.float64)).contiguous()
         if self.spot_key.shape[0] != self.expression_key.shape[0]:
             raise ValueError("spot_key and expression_key must have the same number of rows")
+        self._packed: dict = {}          # top_k -> (workspace, query capacity)
 
     def __len__(self) -> int:
         return self.spot_key.shape[0]
 
+    def _workspace(self, n_query: int, top_k: int) -> torch.Tensor:
+        """A workspace holding this bank's packed image, large enough for n_query queries."""
+        ent = self._packed.get(top_k)
+        if ent is None or ent[1] < n_query:
+            cap = max(n_query, 1024)
+            ws = fm_workspace(len(self), cap, self.spot_key.shape[1], top_k, self.spot_key.device)
+            fm_pack_bank(self.spot_key, top_k, ws)
+            ent = self._packed[top_k] = (ws, cap)
+        return ent[0]
+
+    def find_matches(self, query: torch.Tensor, top_k: int = 50, dist_p: Optional[int] = None):
+        """Device-resident (values, indices[, distances]) against the resident packed image."""
+        N, D = self.spot_key.shape
+        eligible = D <= 256 and top_k <= 896 and N >= top_k
+        if not eligible or query.shape[0] == 0:
+            return find_matches_device(self.spot_key, query, top_k, dist_p=dist_p)
+        ws = self._workspace(query.shape[0], top_k)
+        fm_seed(self.spot_key, query, top_k, ws, bank_packed=True)
+        val, idx, dst = fm_main(self.spot_key, query, top_k, ws, dist_p=dist_p, bank_packed=True)
+        return (val, idx, dst) if dist_p else (val, idx)
+
+    def retrieve_device(self, image_query: torch.Tensor, top_k: int = 50, mode: str = "inv_sq_l2",
+                        want_emb: bool = False, out_dtype=torch.float32):
+        need_dist = mode in ("inv_sq_l1", "inv_sq_l2", "bleep_exp")
+        r = self.find_matches(image_query, top_k, dist_p=(1 if mode == "inv_sq_l1" else 2) if need_dist else None)
+        val, idx, dst = (r[0], r[1], r[2]) if need_dist else (r[0], r[1], None)
+        emb, expr = weighted_topk_average_device(self.spot_key, self.expression_key, image_query, idx, mode,
+                                                 val if mode == "similarity" else None, want_emb, out_dtype,
+                                                 distances=dst)
+        return idx, val, emb, expr
+
     def retrieve(self, image_query: ArrayLike, top_k: int = 50, p: int = 2, mode: Optional[str] = None,
                  want_emb: bool = True, out_dtype=torch.float64):
-        with torch.cuda.device(self.spot_key.device):
-            return retrieve(self.spot_key, self.expression_key, image_query, top_k, p, mode, want_emb, out_dtype)
+        """Host (or device) queries in, host arrays out: (indices, emb_pred | None, expr_pred)."""
+        if mode is None:
+            mode = {1: "inv_sq_l1", 2: "inv_sq_l2"}[p]
+        dev = self.spot_key.device
+        with torch.cuda.device(dev):
+            iq = _to_dev(image_query, dev)
+            if iq.dim() == 1:
+                iq = iq[None]
+            idx, _, emb, expr = self.retrieve_device(iq.contiguous(), top_k, mode, want_emb, out_dtype)
+            return tuple(to_host(idx, emb, expr))
 
 
 def debug_similarity(spot_embeddings: ArrayLike, query_embeddings: ArrayLike) -> torch.Tensor:

@@ -68,7 +68,21 @@ def main():
     e1 = float((ex - ex1).abs().max() / ex1.abs().max())
     ok &= same and e1 < 1e-3
     if rank == 0:
-        print(f"from_host shards, Q={Q}: identical={same}, expr rel err {e1:.2e}")
+        print(f"from_host shards, Q={Q} (two pipelined query blocks): identical={same}, expr rel err {e1:.2e}")
+    # the same shard again (its packed image is resident now), finished rows reduce-scattered:
+    # every rank holds its share, the union must be the single-GPU result
+    for nblk in (1, 2, 3):
+        idx, val, _, ex, rows = retrieve_sharded(shard, qry, k, "inv_sq_l2", scatter_output=True, query_blocks=nblk)
+        same = torch.equal(idx, idx1) and torch.equal(val, val1)
+        e1 = float((ex - ex1[rows]).abs().max() / ex1.abs().max())
+        cover = torch.zeros(Q, device=dev)
+        cover[rows] = 1
+        dist.all_reduce(cover)
+        whole = bool((cover == 1).all())
+        ok &= same and e1 < 1e-3 and whole
+        if rank == 0:
+            print(f"resident shard, reduce-scatter, {nblk} block(s): identical={same}, rows cover the batch "
+                  f"exactly once={whole}, expr rel err {e1:.2e}")
     for targets in ("eye", "soft"):
         B, D = 128 * world * 2, 256
         S = torch.tensor(synth.embeddings(B, D, 21, "clustered", centres=9) * 0.5, device=dev)

@@ -122,7 +122,7 @@ def test_shard_bounds_cover_everything():
 # with the three CUDA phases replaced by a NumPy restatement working on the same raw buffers.
 class _PhaseOracleLib:
     """Stands in for libmclst_b200.so: mclst_contrastive_loss_phase on host pointers, float64 inside.
-    stats rows: 0 rl, 1 cl, 2 za, 3 wbar, 4 cs, 5 diag (csrc/loss.cu)."""
+    stats rows: 0 rl, 1 cl, 2 za, 3 wbar, 4 cs, 5 diag, 6-8 lo halves of rl / cl / za (csrc/loss.cu)."""
 
     @staticmethod
     def _view(p, n):
@@ -138,7 +138,7 @@ class _PhaseOracleLib:
                                      d_s, ld_ds, d_i, ld_di, ws, ws_bytes, stream):
         S = self._view(s, B * ld_s).reshape(B, ld_s)[:, :D].astype(np.float64)
         I = self._view(i, B * ld_i).reshape(B, ld_i)[:, :D].astype(np.float64)
-        st = self._view(stats, 6 * B).reshape(6, B)
+        st = self._view(stats, 9 * B).reshape(9, B)
         soft = mode != 0
         a_scale = 0.0 if not soft else (1.0 / (2 * T) if mode == 1 else T / 2.0)
         loc = slice(row0, row0 + rows)
@@ -151,13 +151,17 @@ class _PhaseOracleLib:
         LgT_loc = I[loc] @ S.T / T                     # Lg[j, r] as [r, j]
         A_loc = (I[loc] @ I.T + S[loc] @ S.T) * a_scale if soft else None
         if phase == 1:
-            st[0, loc] = lse(Lg_loc)
-            st[1, loc] = lse(LgT_loc)
+            def put(k, x):                             # float pair: hi in row k, lo in row 6 + k
+                st[k, loc] = x.astype(np.float32)
+                st[6 + k, loc] = (x - st[k, loc].astype(np.float64)).astype(np.float32)
+            put(0, lse(Lg_loc))
+            put(1, lse(LgT_loc))
             st[5, loc] = Lg_loc[np.arange(rows), np.arange(row0, row0 + rows)]
             if soft:
-                st[2, loc] = lse(A_loc)
+                put(2, lse(A_loc))
             return 0
-        rl, cl, za, wbar, cs = (st[k].astype(np.float64) for k in range(5))
+        rl, cl, za = (st[k].astype(np.float64) + st[6 + k].astype(np.float64) for k in range(3))
+        wbar, cs = st[3].astype(np.float64), st[4].astype(np.float64)
         if phase == 2:
             Pt = np.exp(A_loc - za[loc, None])
             st[3, loc] = (Pt * (rl[loc, None] + cl[None, :] - 2 * Lg_loc)).sum(1)

@@ -235,3 +235,96 @@ def test_lane_rounds_bit_exact(N, Q):
     rows = np.arange(0, Q, 997)
     sval, sidx = oracle.find_matches_spec(bank, qry[rows], k)
     np.testing.assert_array_equal(idx.cpu().numpy()[rows], sidx)
+
+
+# ------------------------------------------------------------------ staged find_matches / resident bank
+def _merge(vals, idxs, k):
+    import ctypes as C
+    from mclstexp_b200._lib import check, load, ptr, stream_ptr
+    R, Q, _ = vals.shape
+    ov = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+    oi = torch.empty((Q, k), dtype=torch.int64, device="cuda")
+    check(load().mclst_merge_topk(ptr(vals), ptr(idxs), None, R, Q, k, ptr(ov), ptr(oi), None, stream_ptr()),
+          "merge_topk")
+    return ov, oi
+
+
+@pytest.mark.parametrize("N,Q,k,shards", [(40000, 700, 50, 3), (70000, 9000, 50, 8), (9000, 300, 200, 2),
+                                          (5000, 130, 50, 4)])
+def test_bank_shards_with_bound_exchange_equal_whole_bank(N, Q, k, shards):
+    """The multi-GPU bank-shard protocol replayed on ONE GPU: every shard's seed pass offers its
+    bounds, they are combined exactly as distributed.retrieve_sharded combines them (max of the k-th
+    best bounds, min of the ceil(k/R)-th best bounds), every shard's main pass filters against the
+    global bound (lists may come back short and padded), the merged result must be bit-identical to
+    find_matches on the whole bank -- and to the oracle's spec."""
+    bank = torch.tensor(synth.embeddings(N, 256, 61, "clustered"), device="cuda")
+    qry = torch.tensor(synth.embeddings(Q, 256, 62, "clustered"), device="cuda")
+    wval, widx = retrieval.find_matches_device(bank, qry, k)
+    cuts = [N * s // shards for s in range(shards + 1)]
+    parts = [bank[cuts[s]:cuts[s + 1]].contiguous() for s in range(shards)]
+    k_part = -(-k // shards)
+    wss, bounds = [], []
+    for pb in parts:
+        ws = retrieval.fm_workspace(pb.shape[0], Q, 256, k, pb.device)
+        wss.append(ws)
+        bounds.append(retrieval.fm_seed(pb, qry, k, ws, k_part, want_bounds=True))
+    b = torch.stack(bounds)                                     # [R, 2, Q]
+    ext = torch.maximum(b[:, 0].max(0).values, b[:, 1].min(0).values).contiguous()
+    vals, idxs, short = [], [], 0
+    for s, pb in enumerate(parts):
+        v, i, _ = retrieval.fm_main(pb, qry, k, wss[s], index_offset=cuts[s], ext_bound=ext)
+        short += int((i == 0x7fffffff).any(1).sum())
+        vals.append(v)
+        idxs.append(i)
+    mv, mi = _merge(torch.stack(vals), torch.stack(idxs), k)
+    assert torch.equal(mi, widx) and torch.equal(mv, wval)
+    if N >= 40000:
+        assert short > 0          # the bound really lets shards drop rows that cannot win
+    sval, sidx = oracle.find_matches_spec(bank.cpu().numpy(), qry[:64].cpu().numpy(), k)
+    np.testing.assert_array_equal(mi[:64].cpu().numpy(), sidx)
+    np.testing.assert_array_equal(mv[:64].cpu().numpy(), sval)
+
+
+def test_staged_without_bound_equals_single_call_and_extreme_bounds():
+    bank = torch.tensor(synth.embeddings(20000, 256, 71, "clustered"), device="cuda")
+    qry = torch.tensor(synth.embeddings(500, 256, 72, "clustered"), device="cuda")
+    k = 50
+    wval, widx, wdst = retrieval.find_matches_device(bank, qry, k, dist_p=2)
+    ws = retrieval.fm_workspace(20000, 500, 256, k, bank.device)
+    retrieval.fm_seed(bank, qry, k, ws)
+    v, i, d = retrieval.fm_main(bank, qry, k, ws, dist_p=2)
+    assert torch.equal(i, widx) and torch.equal(v, wval) and torch.equal(d, wdst)
+    # a bound just below the true k-th best changes nothing
+    retrieval.fm_seed(bank, qry, k, ws, bank_packed=True)
+    v, i, d = retrieval.fm_main(bank, qry, k, ws, dist_p=2, ext_bound=(wval[:, -1] - 1e-6).contiguous(),
+                                bank_packed=True)
+    assert torch.equal(i, widx) and torch.equal(v, wval) and torch.equal(d, wdst)
+    # a bound above every score: nothing of this bank can be among the global winners
+    retrieval.fm_seed(bank, qry, k, ws, bank_packed=True)
+    v, i, d = retrieval.fm_main(bank, qry, k, ws, dist_p=2,
+                                ext_bound=torch.full((500,), 2.0, device="cuda"), bank_packed=True)
+    assert bool((i == 0x7fffffff).all()) and bool(torch.isinf(v).all()) and bool((v < 0).all())
+    assert bool(torch.isinf(d).all())
+    # -inf / NaN bounds mean "nothing known"
+    bad = torch.full((500,), float("-inf"), device="cuda")
+    bad[::2] = float("nan")
+    retrieval.fm_seed(bank, qry, k, ws, bank_packed=True)
+    v, i, _ = retrieval.fm_main(bank, qry, k, ws, ext_bound=bad, bank_packed=True)
+    assert torch.equal(i, widx) and torch.equal(v, wval)
+
+
+def test_resident_bank_equals_one_shot_retrieve():
+    """retrieval.Bank keeps the packed image of the bank across calls (query batches of different
+    sizes, capacity growth, two top_k classes) and must return what the one-shot path returns."""
+    N, G = 30000, 300
+    bank = synth.embeddings(N, 256, 81, "clustered")
+    expr = synth.expression(N, G, 82)
+    b = retrieval.Bank(bank, expr)
+    for Q, k, p in ((100, 50, 2), (3000, 50, 1), (700, 50, 2), (64, 200, 2)):
+        qry = synth.embeddings(Q, 256, 90 + Q, "clustered")
+        idx, emb, ex = b.retrieve(qry, top_k=k, p=p)
+        idx1, emb1, ex1 = retrieval.retrieve(bank, expr, qry, top_k=k, p=p)
+        np.testing.assert_array_equal(idx, idx1)
+        np.testing.assert_array_equal(ex, ex1)
+        np.testing.assert_array_equal(emb, emb1)
+    assert set(b._packed) == {50, 200}
