@@ -49,6 +49,8 @@ enum {
 enum {
   MCLST_FM_DEFAULT = 0,
   MCLST_FM_EXACT_ONLY = 1, /* skip the tensor-core candidate pass, brute-force every query */
+  MCLST_FM_NO_SPECULATION = 4, /* start the running top-k thresholds from the guaranteed seed only
+                              (default: a speculative, verified one -- csrc/sim_topk.cu spec_rank) */
   MCLST_FM_BANK_PACKED = 2 /* the workspace already holds this bank's packed image (an earlier
                               mclst_find_matches_pack_bank / _seed / find_matches call on the same
                               workspace with the same bank, n_bank, dim and top_k): skip the bank pass */
@@ -123,7 +125,14 @@ int mclst_find_matches_dist(const float* bank, int64_t n_bank, int64_t ld_bank,
  * _main:  must follow _seed on the same workspace and stream order.  ext_bound (nullable) [n_query]:
  *         rows provably below it are dropped, so a shard may return FEWER than top_k rows for a
  *         query: the tail of its list is padded with (value -inf, index 0x7fffffff, distance +inf),
- *         which loses every mclst_merge_topk comparison. */
+ *         which loses every mclst_merge_topk comparison.
+ * _candidates + _finish: _main in two halves with a second, much tighter exchange in between.
+ *         _candidates runs the tensor-core candidate pass (against ext_bound when given) and
+ *         writes bound_out[q]: a lower bound of this shard's exact top_k-th best score taken from
+ *         its CONVERGED thresholds.  The maximum of bound_out over the shards, passed to _finish,
+ *         lets every shard re-rank (exactly) only the candidates that can still be among the
+ *         global winners -- about (top_k + band) / shards rows instead of top_k + band.  Pass
+ *         _finish a bound at least as tight as the one _candidates got. */
 int mclst_find_matches_pack_bank(const float* bank, int64_t n_bank, int64_t ld_bank, int dim,
                                  int top_k, void* workspace, size_t workspace_bytes,
                                  mclst_stream_t stream);
@@ -138,6 +147,18 @@ int mclst_find_matches_main(const float* bank, int64_t n_bank, int64_t ld_bank,
                             float* out_values, float* out_distances, int dist_p,
                             const float* ext_bound, void* workspace, size_t workspace_bytes,
                             int flags, mclst_stream_t stream);
+
+int mclst_find_matches_candidates(const float* bank, int64_t n_bank, int64_t ld_bank,
+                                  const float* query, int64_t n_query, int64_t ld_query, int dim,
+                                  int top_k, const float* ext_bound, float* bound_out,
+                                  void* workspace, size_t workspace_bytes, int flags,
+                                  mclst_stream_t stream);
+int mclst_find_matches_finish(const float* bank, int64_t n_bank, int64_t ld_bank,
+                              const float* query, int64_t n_query, int64_t ld_query, int dim,
+                              int top_k, int64_t index_offset, int64_t* out_indices,
+                              float* out_values, float* out_distances, int dist_p,
+                              const float* ext_bound, void* workspace, size_t workspace_bytes,
+                              int flags, mclst_stream_t stream);
 
 /* Testing aid: the raw similarities of the tensor-core candidate pass (fp16-rounded
  * normalised operands, fp32 accumulation) written to out [n_query, ld_out]; workspace as for

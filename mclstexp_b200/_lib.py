@@ -18,7 +18,7 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "mclst_b200.h")
 # weight modes / flags (mirrors of the header enums)
 W_INV_SQ_L1, W_INV_SQ_L2, W_SIMILARITY, W_UNIFORM, W_BLEEP_EXP = range(5)
 WEIGHT_MODES = {"inv_sq_l1": 0, "inv_sq_l2": 1, "similarity": 2, "uniform": 3, "bleep_exp": 4}
-FM_DEFAULT, FM_EXACT_ONLY, FM_BANK_PACKED = 0, 1, 2
+FM_DEFAULT, FM_EXACT_ONLY, FM_BANK_PACKED, FM_NO_SPECULATION = 0, 1, 2, 4
 T_EYE, T_SOFT_DIV, T_SOFT_MUL = 0, 1, 2
 LOSS_STAT_ROWS = 9        # MCLST_LOSS_STAT_ROWS: rl, cl, za, wbar, cs, diag, rl_lo, cl_lo, za_lo
 
@@ -59,6 +59,8 @@ def load() -> C.CDLL:
     lib.mclst_find_matches_seed.argtypes = [p, i64, i64, p, i64, i64, i32, i32, i32, p, p, p, sz, i32, p]
     lib.mclst_find_matches_main.argtypes = [p, i64, i64, p, i64, i64, i32, i32, i64, p, p, p, i32, p, p, sz,
                                             i32, p]
+    lib.mclst_find_matches_candidates.argtypes = [p, i64, i64, p, i64, i64, i32, i32, p, p, p, sz, i32, p]
+    lib.mclst_find_matches_finish.argtypes = lib.mclst_find_matches_main.argtypes
     lib.mclst_debug_similarity.argtypes = [p, i64, i64, p, i64, i64, i32, p, i64, p, sz, p]
     lib.mclst_gene_metrics_scratch_doubles.argtypes = [i32, C.POINTER(sz)]
     lib.mclst_gene_metrics.argtypes = [p, i64, i32, p, i64, i32, i64, i32, p, p, p, p, p, p]

@@ -78,6 +78,7 @@ static FmWorkspace carve_fm(void* ws, size_t cap, int64_t n_bank, int64_t n_quer
   w.use_tc = tc_eligible(n_bank, n_query, dim, top_k, flags);
   if (w.use_tc) {
     tc_workspace(a, n_bank, n_query, dim, top_k, w.tc);
+    w.tc.speculate = (flags & MCLST_FM_NO_SPECULATION) ? 0 : 1;
     w.bank_nrm = w.tc.b_nrm;
     w.q_nrm = w.tc.q_nrm;
   } else {
@@ -147,7 +148,7 @@ extern "C" int mclst_read_counters(const void* workspace, int64_t out[4], mclst_
   MCLST_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   out[0] = c[1];   // tensor-core path
   out[1] = c[0];   // exact fallback
-  out[2] = c[2];
+  out[2] = c[2];   // of the fallbacks: speculative seeds that did not verify
   out[3] = c[3];
   return 0;
 }
@@ -179,8 +180,10 @@ extern "C" int mclst_find_matches(const float* bank, int64_t n_bank, int64_t ld_
 }
 
 // The stages of find_matches.  stage bits: 1 = pack (+ thresholds reset + seed pass, writing the
-// cross-shard bounds when asked), 2 = main pass + re-rank + exact fallback.  The single-call entry
-// runs both; bank shards run them separately with a bound exchange in between.
+// cross-shard bounds when asked), 2 = candidate (main tensor-core) pass, 4 = re-rank + exact
+// fallback.  The single-call entry runs all of them; bank shards run them separately with a bound
+// exchange in between (sb->ext_bound is applied at the start of the first stage of a call that is
+// not stage 1; bound_k receives the post-candidate bound when a call ends with stage 2).
 static int find_matches_stages(int stages, const float* bank, int64_t n_bank, int64_t ld_bank,
                                const float* query, int64_t n_query, int64_t ld_query, int dim,
                                int top_k, int64_t index_offset, int64_t* out_indices,
@@ -189,7 +192,7 @@ static int find_matches_stages(int stages, const float* bank, int64_t n_bank, in
                                cudaStream_t st) {
   MCLST_REQUIRE(dist_p == 1 || dist_p == 2, MCLST_ERR_INVALID, "find_matches: dist_p must be 1 or 2");
   MCLST_REQUIRE(bank && workspace && (query || n_query == 0), MCLST_ERR_INVALID, "find_matches: null pointer");
-  MCLST_REQUIRE(!(stages & 2) || out_indices || n_query == 0, MCLST_ERR_INVALID, "find_matches: null output");
+  MCLST_REQUIRE(!(stages & 4) || out_indices || n_query == 0, MCLST_ERR_INVALID, "find_matches: null output");
   MCLST_REQUIRE(dim >= 1 && ld_bank >= dim && (ld_query >= dim || n_query == 0), MCLST_ERR_INVALID,
                 "find_matches: bad dim/ld");
   // torch.topk raises when k exceeds the dimension (evel_her2st.py:82)
@@ -208,7 +211,9 @@ static int find_matches_stages(int stages, const float* bank, int64_t n_bank, in
       if (sb && sb->bound_k) MCLST_CUDA(cudaMemsetAsync(sb->bound_k, 0xff, (size_t)n_query * 4, st));     // -NaN: "unknown"
       if (sb && sb->bound_part) MCLST_CUDA(cudaMemsetAsync(sb->bound_part, 0xff, (size_t)n_query * 4, st));
     }
-    if (!(stages & 2) || n_query == 0) return 0;
+    if ((stages & 2) && !(stages & 4) && sb && sb->bound_k)
+      MCLST_CUDA(cudaMemsetAsync(sb->bound_k, 0xff, (size_t)n_query * 4, st));
+    if (!(stages & 4) || n_query == 0) return 0;
     MCLST_CUDA(cudaMemsetAsync(w.counters, 0, 256, st));
     prof_mark(st, "row_norms");
     if ((rc = launch_row_norms(bank, n_bank, ld_bank, dim, w.bank_nrm, st))) return rc;
@@ -244,8 +249,17 @@ static int find_matches_stages(int stages, const float* bank, int64_t n_bank, in
     }
   }
   if (n_query == 0) return 0;
-  prof_mark(st, "sim_topk");
-  if ((rc = launch_sim_topk(t, n_bank, n_query, top_k, nullptr, 0, st, (stages & 1) ? 0 : 2, sb))) return rc;
+  if (stages & 2) {
+    prof_mark(st, "sim_topk");
+    if ((rc = launch_sim_topk(t, n_bank, n_query, top_k, nullptr, 0, st, (stages & 1) ? 0 : 2, sb))) return rc;
+    if (!(stages & 4)) {
+      if (sb && sb->bound_k && (rc = launch_export_bound(t, n_query, sb->bound_k, st))) return rc;
+      prof_mark(st, "end");
+      return 0;
+    }
+  } else if (sb && sb->ext_bound) {
+    if ((rc = launch_apply_bound(t, n_query, sb->ext_bound, st))) return rc;
+  }
   if (sim_topk_ablate() != 0) {     // timing experiment (tuning builds only), no results
     MCLST_CUDA(cudaMemsetAsync(out_indices, 0, (size_t)n_query * top_k * sizeof(int64_t), st));
     prof_mark(st, "end");
@@ -273,7 +287,7 @@ extern "C" int mclst_find_matches_dist(const float* bank, int64_t n_bank, int64_
                                        float* out_distances, int dist_p, void* workspace,
                                        size_t workspace_bytes, int flags, mclst_stream_t stream) {
   if (n_query == 0 && n_bank >= 0 && !(flags & MCLST_FM_BANK_PACKED)) return 0;
-  return find_matches_stages(3, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k, index_offset,
+  return find_matches_stages(7, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k, index_offset,
                              out_indices, out_values, out_distances, dist_p, nullptr, workspace,
                              workspace_bytes, flags, (cudaStream_t)stream);
 }
@@ -305,7 +319,32 @@ extern "C" int mclst_find_matches_main(const float* bank, int64_t n_bank, int64_
                                        int flags, mclst_stream_t stream) {
   if (n_query == 0) return 0;
   SeedBounds sb{1, nullptr, nullptr, ext_bound};
-  return find_matches_stages(2, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k, index_offset,
+  return find_matches_stages(6, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k, index_offset,
+                             out_indices, out_values, out_distances, dist_p, &sb, workspace,
+                             workspace_bytes, flags, (cudaStream_t)stream);
+}
+
+extern "C" int mclst_find_matches_candidates(const float* bank, int64_t n_bank, int64_t ld_bank,
+                                             const float* query, int64_t n_query, int64_t ld_query,
+                                             int dim, int top_k, const float* ext_bound, float* bound_out,
+                                             void* workspace, size_t workspace_bytes, int flags,
+                                             mclst_stream_t stream) {
+  if (n_query == 0) return 0;
+  SeedBounds sb{1, bound_out, nullptr, ext_bound};
+  return find_matches_stages(2, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k, 0, nullptr,
+                             nullptr, nullptr, 2, &sb, workspace, workspace_bytes, flags,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int mclst_find_matches_finish(const float* bank, int64_t n_bank, int64_t ld_bank,
+                                         const float* query, int64_t n_query, int64_t ld_query, int dim,
+                                         int top_k, int64_t index_offset, int64_t* out_indices,
+                                         float* out_values, float* out_distances, int dist_p,
+                                         const float* ext_bound, void* workspace, size_t workspace_bytes,
+                                         int flags, mclst_stream_t stream) {
+  if (n_query == 0) return 0;
+  SeedBounds sb{1, nullptr, nullptr, ext_bound};
+  return find_matches_stages(4, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k, index_offset,
                              out_indices, out_values, out_distances, dist_p, &sb, workspace,
                              workspace_bytes, flags, (cudaStream_t)stream);
 }

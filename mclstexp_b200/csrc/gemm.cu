@@ -77,8 +77,18 @@ pack_split_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64
   float inv = 1.f;
   if (inv_scale) {
     float amax = 0.f;
-    if (r < rows)
-      for (int64_t k = lane; k < cols; k += 32) amax = fmaxf(amax, fabsf(__ldg(x + r * ld + k)));
+    if (r < rows) {
+      const float* row = x + r * ld;
+      int64_t k = lane;
+      for (; k + 7 * 32 < cols; k += 8 * 32) {          // 8 independent loads in flight
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(row + k + 32 * i);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[i]));
+      }
+      for (; k < cols; k += 32) amax = fmaxf(amax, fabsf(__ldg(row + k)));
+    }
     amax = warp_max(amax);
     scale *= pow2_scale(amax, &inv);
     if (lane == 0) inv_scale[(size_t)blockIdx.z * rows_pad + r] = inv;
@@ -103,29 +113,41 @@ pack_split_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64
 
 // Transposed: out row r = in column r, K index = in row.  Lane <-> out row (contiguous in
 // the input), each thread gathers 8 consecutive K (8 input rows) for one 16-byte chunk.
-// With inv_scale the block first scans its 32 columns for their max|x| (gridDim.y must be 1).
-__global__ void __launch_bounds__(256)
+// With inv_scale the block first scans its 32 columns for their max|x| (gridDim.y must be 1; the
+// block then has 32 warps and keeps 8 independent loads in flight per thread: a serial scan of a
+// 1024-row column cost 70 us per pack and 1.2 ms per training step).
+__global__ void __launch_bounds__(1024)
 pack_split_t_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
                     float scale, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
                     int64_t out_rows_pad, int nkb_total, int kb_offset, int nkb_mine,
                     const uint32_t* __restrict__ amax_bits, float* __restrict__ inv_scale,
                     int64_t x_batch, size_t out_batch) {
-  __shared__ float s_amax[8][32];
+  __shared__ float s_amax[32][32];
   x += (int64_t)blockIdx.z * x_batch;
   hi += (size_t)blockIdx.z * out_batch;
   if (lo) lo += (size_t)blockIdx.z * out_batch;
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * 32 + lane;                    // out row = in column
-  const int cgroup = threadIdx.x >> 5;                                  // 8 chunk lanes per block
+  const int cgroup = threadIdx.x >> 5;                                  // chunk lane
+  const int ngroups = blockDim.x >> 5;                                  // 8 (y-split grid) or 32 (self-scaling)
   float inv = 1.f;
   if (inv_scale) {
     float amax = 0.f;
-    if (r < cols)
-      for (int64_t k = cgroup; k < rows; k += 8) amax = fmaxf(amax, fabsf(__ldg(x + k * ld + r)));
+    if (r < cols) {
+      const float* col = x + r;
+      int64_t k = cgroup;
+      for (; k + 7 * ngroups < rows; k += 8 * ngroups) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(col + (k + i * ngroups) * ld);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[i]));
+      }
+      for (; k < rows; k += ngroups) amax = fmaxf(amax, fabsf(__ldg(col + k * ld)));
+    }
     s_amax[cgroup][lane] = amax;
     __syncthreads();
-#pragma unroll
-    for (int g = 0; g < 8; ++g) amax = fmaxf(amax, s_amax[g][lane]);
+    for (int g = 0; g < ngroups; ++g) amax = fmaxf(amax, s_amax[g][lane]);
     scale *= pow2_scale(amax, &inv);
     if (cgroup == 0 && r < out_rows_pad) inv_scale[(size_t)blockIdx.z * out_rows_pad + r] = inv;
   } else if (amax_bits) {
@@ -133,7 +155,7 @@ pack_split_t_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int
   }
   if (r >= out_rows_pad) return;
   const int nchunks = nkb_mine * 8;
-  for (int c = blockIdx.y * 8 + cgroup; c < nchunks; c += gridDim.y * 8) {
+  for (int c = blockIdx.y * ngroups + cgroup; c < nchunks; c += gridDim.y * ngroups) {
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -184,7 +206,7 @@ int launch_pack_split(const float* x, int64_t rows, int64_t cols, int64_t ld, bo
   } else {
     dim3 grid((unsigned)ceil_div(dst.rows_pad, 32), inv_scale ? 1u : (unsigned)std::min<int64_t>(64, nkb_mine),
               (unsigned)batch);
-    pack_split_t_kernel<<<grid, 256, 0, st>>>(x, rows, cols, ld, scale, dst.hi, dst.lo,
+    pack_split_t_kernel<<<grid, inv_scale ? 1024 : 256, 0, st>>>(x, rows, cols, ld, scale, dst.hi, dst.lo,
                                               dst.rows_pad, dst.nkb, kb_offset, nkb_mine, amax_bits,
                                               inv_scale, x_batch_elems, dst.bytes);
   }
@@ -262,10 +284,19 @@ gemm_tn_kernel(const GemmParams p) {
           // segment 0: hi*hi, 1: lo*hi, 2: hi*lo
           const uint8_t* a = (seg == 1) ? a_lo : a_hi;
           const uint8_t* b = (seg == 2) ? b_lo : b_hi;
+          // A may be two images concatenated along K (the second one shared between products)
+          size_t a_off = ((size_t)mb * nkb + kb) * TP_SLICE_BYTES;
+          if (p.a_nkb1 > 0) {
+            if (kb < p.a_nkb1) a_off = ((size_t)mb * p.a_nkb1 + kb) * TP_SLICE_BYTES;
+            else {
+              a = (seg == 1) ? p.a2_lo : p.a2_hi;
+              a_off = ((size_t)mb * (nkb - p.a_nkb1) + (kb - p.a_nkb1)) * TP_SLICE_BYTES;
+            }
+          }
           mbar_wait(&bar_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bar_full[stage], GM_STAGE_BYTES);
           uint8_t* dst = smem + stage * GM_STAGE_BYTES;
-          bulk_g2s(dst, a + ((size_t)mb * nkb + kb) * TP_SLICE_BYTES, TP_SLICE_BYTES, &bar_full[stage]);
+          bulk_g2s(dst, a + a_off, TP_SLICE_BYTES, &bar_full[stage]);
           if (CL == 1) {
             bulk_g2s(dst + TP_SLICE_BYTES, b + ((size_t)(2 * nb) * nkb + kb) * TP_SLICE_BYTES,
                      TP_SLICE_BYTES, &bar_full[stage]);
@@ -341,12 +372,33 @@ gemm_tn_kernel(const GemmParams p) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * GM_BN;
       const int64_t n0 = (int64_t)nb * GM_BN;
+      // fused row log-sum-exp (loss products): running (max, sum exp) of MY row (TMEM lane) over
+      // the 128 columns this warp drains, written as one partial per (row, tile column, half)
+      float lm = -INFINITY, ls = 0.f;
+      const int64_t my_row = m0 + lane;
 #pragma unroll 1
       for (int c = chalf * 4; c < chalf * 4 + 4; ++c) {
         if (n0 + c * 32 >= p.N || mb >= mt || m0 >= p.M) break;             // uniform
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
+        if (p.lse_part) {
+          const int64_t cbase = n0 + c * 32;
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = (cbase + j < p.N) ? __uint_as_float(v[j]) * alpha : -INFINITY;
+            cm = fmaxf(cm, x);
+            if (p.diag && cbase + j == my_row + p.diag_offset && my_row < p.M) p.diag[my_row] = x;
+          }
+          if (cm > lm) { ls *= __expf(lm - cm); lm = cm; }                  // (exp(-inf) = 0 on the first chunk)
+          if (lm > -INFINITY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cbase + j < p.N) ls += expf(__uint_as_float(v[j]) * alpha - lm);
+          }
+          if (!p.c) continue;                                                // statistics only: nothing to store
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           tile[lane * 8 + (j ^ (lane & 7))] =
@@ -393,6 +445,8 @@ gemm_tn_kernel(const GemmParams p) {
         }
         __syncwarp();
       }
+      if (p.lse_part && mb < mt && my_row < p.M && n0 + chalf * 128 < p.N)
+        p.lse_part[(size_t)(nb * 2 + chalf) * p.lse_ld + my_row] = make_float2(lm, ls);
       // accumulator drained: hand the buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -436,6 +490,11 @@ int launch_gemm_tn(const GemmParams& p, cudaStream_t st) {
   MCLST_REQUIRE(p.M > 0 && p.N > 0 && p.nkb > 0 && (p.nseg == 1 || p.nseg == 3), MCLST_ERR_INVALID,
                 "gemm: bad shape M=%lld N=%lld nkb=%d nseg=%d", (long long)p.M, (long long)p.N, p.nkb, p.nseg);
   MCLST_REQUIRE(p.nseg == 1 || (p.a_lo && p.b_lo), MCLST_ERR_INVALID, "gemm: split needs lo parts");
+  MCLST_REQUIRE(p.c || p.lse_part, MCLST_ERR_INVALID, "gemm: neither an output nor statistics requested");
+  MCLST_REQUIRE(p.a_nkb1 == 0 || (p.a_nkb1 > 0 && p.a_nkb1 < p.nkb && p.a2_hi && (p.nseg == 1 || p.a2_lo) && p.batch <= 1),
+                MCLST_ERR_INVALID, "gemm: bad concatenated A operand");
+  MCLST_REQUIRE(!p.lse_part || (!p.a_scale && !p.b_scale && !p.bias && p.act == 0 && p.batch <= 1),
+                MCLST_ERR_INVALID, "gemm: the fused row statistics take a plain alpha-scaled product");
   GemmParams q = p;
   q.batch = std::max(1, p.batch);
   prof_mark(st, "gemm_tn");

@@ -32,6 +32,18 @@ struct GemmParams {
   size_t a_scale_batch, b_scale_batch;
   const uint32_t* amax_bits;
   int amax_pow;
+  // A = [image 1 | image 2] along K: the first a_nkb1 K blocks come from a_hi / a_lo (an image
+  // with a_nkb1 blocks per row block), the remaining nkb - a_nkb1 from a2_hi / a2_lo.  0 = plain.
+  const uint8_t *a2_hi, *a2_lo;
+  int a_nkb1;
+  // fused row log-sum-exp of the scaled product (loss): lse_part [2 * ceil(N/256)][lse_ld] receives
+  // one (max, sum exp(x - max)) pair per row, tile column and 128-column half (-inf, 0 when that
+  // half lies beyond N is NOT written: merge only the halves that exist); diag (nullable) [M]
+  // receives element (m, m + diag_offset).  c may then be null: statistics only, nothing stored.
+  float2* lse_part;
+  int64_t lse_ld;
+  float* diag;
+  int64_t diag_offset;
 };
 
 size_t packed_operand_bytes(int64_t rows, int64_t k, bool is_b, int64_t* rows_pad, int* nkb);

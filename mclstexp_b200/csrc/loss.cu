@@ -238,6 +238,209 @@ grad_factor_kernel(const GradParams p, int64_t rows_pad) {
   }
 }
 
+
+// ============================================================================ lean single-block path
+// When one row block holds the whole batch, the statistics come out of the product epilogues and
+// every element of the products is read ONCE by each consumer:
+//   P1 (+ row LSE partials + diagonal from the GEMM epilogue), P3 (+ row LSE partials)
+//   column LSE of P1 from a coalesced sweep (replaces the transposed product P2 and its sweep)
+//   wbar / cs sweep (soft targets)
+//   gradient factors per PAIR of mirrored 64 x 64 tiles: Lg_rj and Lg_jr, A_rj = A_jr are in
+//   shared memory together, so each exponential is evaluated once and P3 is read over the upper
+//   triangle only; G1 (dLg), G2 (dLg^T) and the symmetric Gs are written once each (12 B/element
+//   instead of 16 + a third product).
+
+// partial (max, sum exp) pairs [slot][ld] -> float-pair statistic per row.  Slot s covers columns
+// [s * slot_cols, ...): slots starting at or beyond ncols were never written and are skipped.
+struct MergeJob { const float2* part; int slots, slot_cols, ncols; int64_t ld; float *hi, *lo; int n; };
+struct MergeJobs { MergeJob j[3]; };
+
+__global__ void __launch_bounds__(256)
+lse_merge_kernel(const MergeJobs jobs) {
+  const MergeJob& J = jobs.j[blockIdx.y];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= J.n) return;
+  double M = -INFINITY;
+  for (int s = 0; s < J.slots && (int64_t)s * J.slot_cols < J.ncols; ++s)
+    M = fmax(M, (double)J.part[(size_t)s * J.ld + r].x);
+  double S = 0.0;
+  for (int s = 0; s < J.slots && (int64_t)s * J.slot_cols < J.ncols; ++s) {
+    const float2 p = J.part[(size_t)s * J.ld + r];
+    if (p.x > -INFINITY) S += (double)p.y * exp((double)p.x - M);
+  }
+  const double L = M + log(S);
+  const float hi = (float)L;
+  J.hi[r] = hi;
+  J.lo[r] = (hi == hi && fabsf(hi) < INFINITY) ? (float)(L - (double)hi) : 0.f;
+}
+
+// column-wise (max, sum exp) of P [rows, ld] over row chunks of CL_ROWS: thread = column, rows
+// streamed with 8 loads in flight; part [chunk][ld].
+constexpr int CL_ROWS = 1024;
+__global__ void __launch_bounds__(256)
+col_lse_partial_kernel(const float* __restrict__ P, int64_t ld, int rows, int ncols,
+                       float2* __restrict__ part) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r0 = blockIdx.y * CL_ROWS, r1 = min(rows, r0 + CL_ROWS);
+  if (j >= ncols) return;
+  const float* p = P + j;
+  float m = -INFINITY, s = 0.f;
+  int r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(p + (size_t)(r + i) * ld);
+    float cm = v[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) cm = fmaxf(cm, v[i]);
+    if (cm > m) { s *= __expf(m - cm); m = cm; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += expf(v[i] - m);
+  }
+  for (; r < r1; ++r) {
+    const float x = __ldg(p + (size_t)r * ld);
+    if (x > m) { s = s * __expf(m - x) + 1.f; m = x; }
+    else s += expf(x - m);
+  }
+  part[(size_t)blockIdx.y * ld + j] = make_float2(m, s);
+}
+
+struct TileGradParams {
+  const float *P1, *P3;
+  int64_t ld;
+  int B, soft;
+  const float *rl, *cl, *za, *wbar, *cs, *rl_lo, *cl_lo, *za_lo;
+  float inv_t, a_scale;            // normalised so that the stored factors are O(1)
+  uint8_t *g1_hi, *g1_lo, *g2_hi, *g2_lo, *gs_hi, *gs_lo;   // TilePack images [rows_pad, B64], K = batch index
+  int nkb;                         // B64 / 64
+};
+
+constexpr int TG = 64;             // tile edge
+constexpr int TG_LD = TG + 1;
+constexpr int TG_SMEM = (3 * TG * TG_LD + 2 * 8 * TG) * 4;
+
+__global__ void __launch_bounds__(256)
+grad_tiles_kernel(const TileGradParams p) {
+  const int tr = blockIdx.y, tc = blockIdx.x;
+  if (tc < tr) return;                                   // the pair (tr, tc) also serves (tc, tr)
+  extern __shared__ float tg_smem[];
+  float* sA = tg_smem;                                   // P1[tr rows][tc cols]   -> later g_rj
+  float* sB = sA + TG * TG_LD;                           // P1[tc rows][tr cols]   -> later g_jr
+  float* sC = sB + TG * TG_LD;                           // P3[tr rows][tc cols]   -> later h
+  float* st_r = sC + TG * TG_LD;                         // [8][64] statistics of the tr indices
+  float* st_c = st_r + 8 * TG;                           // [8][64] statistics of the tc indices
+  const int t = threadIdx.x;
+  const int64_t R0 = (int64_t)tr * TG, C0 = (int64_t)tc * TG;
+  // ---- load the three tiles (coalesced float4 rows) and the 2 x 64 x 8 statistics
+  for (int q = t; q < TG * TG / 4; q += 256) {
+    const int r = q >> 4, c4 = (q & 15) * 4;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.P1 + (R0 + r) * p.ld + C0 + c4));
+    sA[r * TG_LD + c4] = a.x; sA[r * TG_LD + c4 + 1] = a.y; sA[r * TG_LD + c4 + 2] = a.z; sA[r * TG_LD + c4 + 3] = a.w;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.P1 + (C0 + r) * p.ld + R0 + c4));
+    sB[r * TG_LD + c4] = b.x; sB[r * TG_LD + c4 + 1] = b.y; sB[r * TG_LD + c4 + 2] = b.z; sB[r * TG_LD + c4 + 3] = b.w;
+    if (p.soft) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(p.P3 + (R0 + r) * p.ld + C0 + c4));
+      sC[r * TG_LD + c4] = c.x; sC[r * TG_LD + c4 + 1] = c.y; sC[r * TG_LD + c4 + 2] = c.z; sC[r * TG_LD + c4 + 3] = c.w;
+    }
+  }
+  if (t < 2 * TG) {
+    const int i = t & (TG - 1);
+    const int64_t g = ((t < TG) ? R0 : C0) + i;
+    float* d = (t < TG) ? st_r : st_c;
+    const bool ok = g < p.B;
+    d[0 * TG + i] = ok ? __ldg(p.rl + g) : 0.f;
+    d[1 * TG + i] = ok ? __ldg(p.cl + g) : 0.f;
+    d[2 * TG + i] = ok ? __ldg(p.rl_lo + g) : 0.f;
+    d[3 * TG + i] = ok ? __ldg(p.cl_lo + g) : 0.f;
+    d[4 * TG + i] = (ok && p.soft) ? __ldg(p.za + g) : 0.f;
+    d[5 * TG + i] = (ok && p.soft) ? __ldg(p.za_lo + g) : 0.f;
+    d[6 * TG + i] = (ok && p.soft) ? __ldg(p.wbar + g) : 0.f;
+    d[7 * TG + i] = (ok && p.soft) ? __ldg(p.cs + g) : 1.f;
+  }
+  __syncthreads();
+  // ---- thread (r, 16-column quarter): the 16 (r, j) pairs; both orientations from one set of exps
+  const int r = t >> 2, jq = (t & 3) * 16;
+  const int64_t R = R0 + r;
+  const float rl_r = st_r[r], cl_r = st_r[TG + r], rll_r = st_r[2 * TG + r], cll_r = st_r[3 * TG + r];
+  const float za_r = st_r[4 * TG + r], zal_r = st_r[5 * TG + r], wb_r = st_r[6 * TG + r], cs_r = st_r[7 * TG + r];
+  float g_rj[16], g_jr[16], h[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int j = jq + u;
+    const int64_t J = C0 + j;
+    float a1 = 0.f, a2 = 0.f, hh = 0.f;
+    if (R < p.B && J < p.B) {
+      const float x = sA[r * TG_LD + j], y = sB[j * TG_LD + r];
+      const float rl_j = st_c[j], cl_j = st_c[TG + j], rll_j = st_c[2 * TG + j], cll_j = st_c[3 * TG + j];
+      float p_rj, p_jr;
+      if (p.soft) {
+        const float a = sC[r * TG_LD + j];
+        p_rj = expf((a - za_r) - zal_r);
+        p_jr = expf((a - st_c[4 * TG + j]) - st_c[5 * TG + j]);
+        const float da_rj = p_rj * (rl_r + cl_j - 2.f * x - wb_r);
+        const float da_jr = p_jr * (rl_j + cl_r - 2.f * y - st_c[6 * TG + j]);
+        hh = (da_rj + da_jr) * p.a_scale;
+      } else {
+        p_rj = p_jr = (R == J) ? 1.f : 0.f;
+      }
+      a1 = (expf((x - rl_r) - rll_r) + st_c[7 * TG + j] * expf((x - cl_j) - cll_j) - 2.f * p_rj) * p.inv_t;   // 2B dLg_rj / T
+      a2 = (expf((y - rl_j) - rll_j) + cs_r * expf((y - cl_r) - cll_r) - 2.f * p_jr) * p.inv_t;               // 2B dLg_jr / T
+    }
+    g_rj[u] = a1; g_jr[u] = a2; h[u] = hh;
+  }
+  // as-is tile (tr, tc): row R, K chunks (C0 + jq) / 8 and the next one
+  {
+    const int chunk0 = (int)((C0 + jq) >> 3);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const size_t off = tilepack_chunk_offset(R, chunk0 + half, p.nkb);
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = g_rj[half * 8 + i];
+      store_split(p.g1_hi, p.g1_lo, off, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = g_jr[half * 8 + i];
+      store_split(p.g2_hi, p.g2_lo, off, v);
+      if (p.soft) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = h[half * 8 + i];
+        store_split(p.gs_hi, p.gs_lo, off, v);
+      }
+    }
+  }
+  if (tc == tr) return;                                  // (block-uniform)
+  // ---- mirrored tile (tc, tr): transpose the three result tiles through shared memory
+  __syncthreads();                                       // everyone has read sA / sB / sC
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    sA[r * TG_LD + jq + u] = g_rj[u];
+    sB[r * TG_LD + jq + u] = g_jr[u];
+    sC[r * TG_LD + jq + u] = h[u];
+  }
+  __syncthreads();
+  {
+    const int j = t >> 2, rq = (t & 3) * 16;             // row C0 + j of the mirrored tile, columns R0 + rq ..
+    const int64_t J = C0 + j;
+    const int chunk0 = (int)((R0 + rq) >> 3);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const size_t off = tilepack_chunk_offset(J, chunk0 + half, p.nkb);
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = sB[(rq + half * 8 + i) * TG_LD + j];      // dLg_jr as row j
+      store_split(p.g1_hi, p.g1_lo, off, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = sA[(rq + half * 8 + i) * TG_LD + j];      // dLg_rj as its transpose
+      store_split(p.g2_hi, p.g2_lo, off, v);
+      if (p.soft) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = sC[(rq + half * 8 + i) * TG_LD + j];
+        store_split(p.gs_hi, p.gs_lo, off, v);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- host plan
 struct LossPlan {
   int B, D, soft;
@@ -250,7 +453,19 @@ struct LossPlan {
   float *rl, *cl, *za, *wbar, *cs, *diag, *rl_lo, *cl_lo, *za_lo;   // views into the stats block [9][B]
   float* stats_ws;
   size_t bytes;
+  // lean single-block path
+  bool lean;
+  PackedOperand G1, G2, Gs;        // [R, B64] each
+  float2 *part1, *part3, *partc;   // LSE partials: rows of P1 / P3 [2 * nt256][R], columns of P1 [chunks][B64]
+  int nt256, cchunks;
 };
+
+// MCLST_LOSS_LEAN=0 forces the general (row-blocked / row-sharded) pipeline on a whole batch too:
+// the tests use it to compare the two
+static bool lean_enabled() {
+  const char* e = getenv("MCLST_LOSS_LEAN");
+  return !(e && e[0] == '0');
+}
 
 static LossPlan plan_loss(void* ws, size_t cap, int B, int D, int soft, int want_grad, size_t budget,
                           int64_t rows_local) {
@@ -264,6 +479,9 @@ static LossPlan plan_loss(void* ws, size_t cap, int B, int D, int soft, int want
   R = std::min<int64_t>(R, (int64_t)align_up((size_t)rows_local, 128));
   L.R = R;
   L.nblocks = ceil_div(rows_local, R);
+  L.lean = L.nblocks == 1 && rows_local == B && lean_enabled();
+  L.nt256 = (int)ceil_div(B, 256);
+  L.cchunks = (int)ceil_div(B, CL_ROWS);
   Arena a(ws, cap);
   L.flags = a.take<uint32_t>(16);
   L.Sp = take_operand(a, B, D, true, true, 1);
@@ -273,12 +491,23 @@ static LossPlan plan_loss(void* ws, size_t cap, int B, int D, int soft, int want
   if (want_grad) {
     L.XT_IS = take_operand(a, D, kx, true, true, 1);
     L.XT_SI = take_operand(a, D, kx, true, true, 1);
-    L.GA = take_operand(a, R, kx, false, true, 1);
-    L.GB = take_operand(a, R, kx, false, true, 1);
+    if (L.lean) {
+      L.G1 = take_operand(a, R, L.B64, false, true, 1);
+      L.G2 = take_operand(a, R, L.B64, false, true, 1);
+      if (soft) L.Gs = take_operand(a, R, L.B64, false, true, 1);
+    } else {
+      L.GA = take_operand(a, R, kx, false, true, 1);
+      L.GB = take_operand(a, R, kx, false, true, 1);
+    }
   }
   L.P1 = a.take<float>((size_t)R * L.B64);
-  L.P2 = a.take<float>((size_t)R * L.B64);
+  L.P2 = L.lean ? nullptr : a.take<float>((size_t)R * L.B64);
   L.P3 = soft ? a.take<float>((size_t)R * L.B64) : nullptr;
+  if (L.lean) {
+    L.part1 = a.take<float2>((size_t)2 * L.nt256 * R);
+    L.part3 = soft ? a.take<float2>((size_t)2 * L.nt256 * R) : nullptr;
+    L.partc = a.take<float2>((size_t)L.cchunks * L.B64);
+  }
   L.stats_ws = a.take<float>((size_t)MCLST_LOSS_STAT_ROWS * B);
   L.bytes = align_up(a.off, 256);
   return L;
@@ -370,6 +599,30 @@ static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_em
         if ((rc = launch_pack_split(image_emb, B, D, ld_i, true, 1.f, L.XT_SI, nkbB, nkbB, L.flags, nullptr, st))) return rc;
       }
     }
+    if (L.lean) {
+      // products with the row statistics fused into their epilogues; no transposed product
+      GemmParams g{};
+      g.nseg = 3; g.batch = 1; g.M = B; g.N = B; g.ldc = L.B64; g.amax_bits = L.flags; g.amax_pow = 2;
+      g.nkb = nkbD; g.a_hi = L.Sp.hi; g.a_lo = L.Sp.lo; g.b_hi = L.Ip.hi; g.b_lo = L.Ip.lo;
+      g.c = L.P1; g.alpha = inv_t; g.lse_part = L.part1; g.lse_ld = L.R; g.diag = L.diag; g.diag_offset = 0;
+      if ((rc = launch_gemm_tn(g, st))) return rc;
+      if (soft) {
+        g.nkb = L.ISp.nkb; g.a_hi = L.ISp.hi; g.a_lo = L.ISp.lo; g.b_hi = L.ISp.hi; g.b_lo = L.ISp.lo;
+        g.c = L.P3; g.alpha = a_scale; g.lse_part = L.part3; g.diag = nullptr;
+        if ((rc = launch_gemm_tn(g, st))) return rc;
+      }
+      prof_mark(st, "col_lse");
+      col_lse_partial_kernel<<<dim3((unsigned)ceil_div(B, 256), (unsigned)L.cchunks), 256, 0, st>>>(
+          L.P1, L.B64, B, B, L.partc);
+      MCLST_LAUNCH_CHECK();
+      prof_mark(st, "lse_merge");
+      MergeJobs mj{};
+      mj.j[0] = MergeJob{L.part1, 2 * L.nt256, 128, B, L.R, L.rl, L.rl_lo, B};
+      mj.j[1] = MergeJob{L.partc, L.cchunks, 1, L.cchunks, L.B64, L.cl, L.cl_lo, B};
+      if (soft) mj.j[2] = MergeJob{L.part3, 2 * L.nt256, 128, B, L.R, L.za, L.za_lo, B};
+      lse_merge_kernel<<<dim3((unsigned)ceil_div(B, 256), soft ? 3u : 2u), 256, 0, st>>>(mj);
+      MCLST_LAUNCH_CHECK();
+    } else
     for (int64_t b = 0; b < L.nblocks; ++b) {
       const int64_t i0 = row0 + b * L.R, nr = std::min<int64_t>(L.R, row0 + rows - i0);
       if ((rc = compute_blocks(L, i0, nr, inv_t, a_scale, true, st))) return rc;
@@ -399,7 +652,36 @@ static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_em
     if (soft) loss_reduce_kernel<<<1, LS_THREADS, 0, st>>>(L.wbar, nullptr, nullptr, nullptr, nullptr, (int)row0, (int)(row0 + rows), B, loss_out);
     else loss_reduce_kernel<<<1, LS_THREADS, 0, st>>>(L.rl, L.cl, L.diag, L.rl_lo, L.cl_lo, (int)row0, (int)(row0 + rows), B, loss_out);
     MCLST_LAUNCH_CHECK();
-    if (d_spot) {
+    if (d_spot && L.lean) {
+      const float u = std::max(inv_t, a_scale);
+      TileGradParams tp{};
+      tp.P1 = L.P1; tp.P3 = L.P3; tp.ld = L.B64; tp.B = B; tp.soft = soft;
+      tp.rl = L.rl; tp.cl = L.cl; tp.za = L.za; tp.wbar = L.wbar; tp.cs = L.cs;
+      tp.rl_lo = L.rl_lo; tp.cl_lo = L.cl_lo; tp.za_lo = L.za_lo;
+      tp.inv_t = inv_t / u; tp.a_scale = a_scale / u;
+      tp.g1_hi = L.G1.hi; tp.g1_lo = L.G1.lo; tp.g2_hi = L.G2.hi; tp.g2_lo = L.G2.lo;
+      tp.gs_hi = L.Gs.hi; tp.gs_lo = L.Gs.lo; tp.nkb = L.G1.nkb;
+      static bool attr_set = false;
+      if (!attr_set) {
+        MCLST_CUDA(cudaFuncSetAttribute(grad_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+        attr_set = true;
+      }
+      const unsigned nt = (unsigned)ceil_div(B, TG);
+      prof_mark(st, "grad_tiles");
+      grad_tiles_kernel<<<dim3(nt, nt), 256, TG_SMEM, st>>>(tp);
+      MCLST_LAUNCH_CHECK();
+      GemmParams g{};
+      g.nseg = 3; g.batch = 1; g.M = B; g.N = D; g.alpha = 0.5f * u / (float)B;
+      g.amax_bits = L.flags; g.amax_pow = 1;
+      g.nkb = (soft ? 2 : 1) * L.G1.nkb;
+      if (soft) { g.a_nkb1 = L.G1.nkb; g.a2_hi = L.Gs.hi; g.a2_lo = L.Gs.lo; }
+      g.a_hi = L.G1.hi; g.a_lo = L.G1.lo; g.b_hi = L.XT_IS.hi; g.b_lo = L.XT_IS.lo;
+      g.c = d_spot; g.ldc = ld_ds;
+      if ((rc = launch_gemm_tn(g, st))) return rc;
+      g.a_hi = L.G2.hi; g.a_lo = L.G2.lo; g.b_hi = L.XT_SI.hi; g.b_lo = L.XT_SI.lo;
+      g.c = d_image; g.ldc = ld_di;
+      if ((rc = launch_gemm_tn(g, st))) return rc;
+    } else if (d_spot) {
       for (int64_t b = 0; b < L.nblocks; ++b) {
         const int64_t i0 = row0 + b * L.R, nr = std::min<int64_t>(L.R, row0 + rows - i0);
         if (!single && (rc = compute_blocks(L, i0, nr, inv_t, a_scale, true, st))) return rc;

@@ -32,6 +32,20 @@
 
 namespace mclst {
 
+// Tuning knobs (MCLST_SIM_*): read from the environment only in a tuning build
+// (-DMCLST_TUNING_KNOBS); the product library ignores them, carries only the variants it ships
+// and never calls getenv on the hot path.
+#ifdef MCLST_TUNING_KNOBS
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#define ST_ABLATE(p) ((p).ablate)
+#else
+static constexpr int env_int(const char*, int dflt) { return dflt; }
+#define ST_ABLATE(p) 0
+#endif
+
 using namespace ptx;
 
 // Bound on the tcgen05 fp32 accumulation error for |scores| <= 1, K <= 256.  Measured on
@@ -468,7 +482,7 @@ sim_topk_kernel(const SimParams p) {
         if (lane == 0) mbar_arrive(&bar_tempty[buf]);
         continue;
       }
-      if (p.ablate == 2) {
+      if (ST_ABLATE(p) == 2) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_tempty[buf]);
@@ -483,7 +497,7 @@ sim_topk_kernel(const SimParams p) {
           for (int j = 0; j < 32; ++j)
             if (c * 32 + j < n_valid) p.dump[q * p.dump_ld + col_base + c * 32 + j] = __uint_as_float(va[j]);
         }
-        if (p.ablate == 0)
+        if (ST_ABLATE(p) == 0)
           filter_chunk<CAP>(va, my_buf, my_gthr, cnt, thr, flagged, (uint32_t)(col_base + c * 32),
                             n_valid - c * 32, k, e2, trigger, gap);
         else if ((va[0] ^ va[13] ^ va[31]) == 0x12345678u) cnt++;
@@ -501,7 +515,7 @@ sim_topk_kernel(const SimParams p) {
             if ((c + 1) * 32 + j < n_valid)
               p.dump[q * p.dump_ld + col_base + (c + 1) * 32 + j] = __uint_as_float(vb[j]);
         }
-        if (p.ablate == 0)
+        if (ST_ABLATE(p) == 0)
           filter_chunk<CAP>(vb, my_buf, my_gthr, cnt, thr, flagged,
                             (uint32_t)(col_base + (c + 1) * 32), n_valid - (c + 1) * 32, k, e2, trigger, gap);
         else if ((vb[0] ^ vb[13] ^ vb[31]) == 0x12345678u) cnt++;
@@ -532,10 +546,7 @@ sim_topk_kernel(const SimParams p) {
 // bank tiles at about the same time (one HBM read, the rest L2 hits) exactly like the waves of
 // the grid kernel; tail lanes take their boundary-aligned pieces first and the partial head
 // piece last for the same reason (two aligned groups instead of R unrelated streams).
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
+
 
 struct LanePlan {
   int W, rounds, rest, w, R, M, Lt, slots;
@@ -784,7 +795,7 @@ sim_topk_lanes_kernel(const SimParams p, const LanePlan L) {
           if (lane == 0) mbar_arrive(&bar_tempty[buf]);
           continue;
         }
-        if (p.ablate == 2) {
+        if (ST_ABLATE(p) == 2) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_tempty[buf]);
@@ -795,7 +806,7 @@ sim_topk_lanes_kernel(const SimParams p, const LanePlan L) {
         for (int ch = 0; ch < NCH; ch += 2) {
           tmem_ld_wait();
           tmem_ld_32x32(taddr + (ch + 1) * 32, vb);
-          if (p.ablate == 0)
+          if (ST_ABLATE(p) == 0)
             filter_chunk<CAP>(va, my_buf, my_gthr, cnt, thr, flagged, (uint32_t)(col_base + ch * 32),
                               n_valid - ch * 32, k, e2, trigger, gap);
           else if ((va[0] ^ va[13] ^ va[31]) == 0x12345678u) cnt++;
@@ -807,7 +818,7 @@ sim_topk_lanes_kernel(const SimParams p, const LanePlan L) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[buf]);
           }
-          if (p.ablate == 0)
+          if (ST_ABLATE(p) == 0)
             filter_chunk<CAP>(vb, my_buf, my_gthr, cnt, thr, flagged,
                               (uint32_t)(col_base + (ch + 1) * 32), n_valid - (ch + 1) * 32, k, e2, trigger, gap);
           else if ((vb[0] ^ vb[13] ^ vb[31]) == 0x12345678u) cnt++;
@@ -1003,7 +1014,7 @@ sim_topk_ring_kernel(const SimParams p) {
           float m = __uint_as_float(v[0]);
 #pragma unroll
           for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-          if (p.ablate == 0 && m > thr) {
+          if (ST_ABLATE(p) == 0 && m > thr) {
             // hand the chunk to the row's worker
             const int slot = atomicAdd(&ring_head[wk], 1);
             if (slot - ring_tail[wk] >= RG_SLOTS) {
@@ -1136,7 +1147,10 @@ __global__ void __launch_bounds__(128)
 seed_threshold_kernel(const float* __restrict__ seed, int n_vals, int64_t Q, int k,
                       const float* __restrict__ q_resid, const uint32_t* __restrict__ bank_stats,
                       uint32_t* __restrict__ gthr, int k2, float* __restrict__ bound_k,
-                      float* __restrict__ bound_part) {
+                      float* __restrict__ bound_part, float* __restrict__ spec_out) {
+  // k < top_k is the SPECULATIVE start (see spec_rank): the threshold is then only valid if fewer
+  // than k of the true top rows fell into the sample; spec_out records it so that the re-rank can
+  // verify the outcome with one compare (and send the query to the exact path otherwise).
   const int lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (q >= Q) return;
@@ -1185,14 +1199,33 @@ seed_threshold_kernel(const float* __restrict__ seed, int n_vals, int64_t Q, int
   }
   if (lane == 0) {
     const float e1 = 1.01f * pair_eps(q_resid[q], __uint_as_float(bank_stats[0]));
+    float spec = -INFINITY;
     if (T != 0u) {
       const float thr = ord2f(T) - 2.f * e1;
-      if (thr == thr && thr > -INFINITY) gthr[q] = f2ord(thr);
+      if (thr == thr && thr > -INFINITY) { gthr[q] = f2ord(thr); spec = thr; }
     }
+    if (spec_out) spec_out[q] = spec;
     // lower bounds of EXACT scores: at least k (k2) rows of this shard score >= bound
     if (bound_k) { const float b = ord2f(T) - e1; bound_k[q] = (T != 0u && b == b) ? b : -INFINITY; }
     if (bound_part) { const float b = ord2f(T2) - e1; bound_part[q] = (T2 != 0u && b == b) ? b : -INFINITY; }
   }
+}
+
+// After the candidate pass: the final shared threshold of a query is (lower bound of this shard's
+// k-th best tensor-core score) - 2.02 eps, so threshold + 1.01 eps bounds the exact k-th best from
+// below -- the figure the bank shards exchange before their re-ranks.
+__global__ void __launch_bounds__(256)
+export_bound_kernel(const uint32_t* __restrict__ gthr, int64_t Q, const float* __restrict__ q_resid,
+                    const uint32_t* __restrict__ bank_stats, float* __restrict__ bound) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const uint32_t key = gthr[q];
+  float b = -INFINITY;
+  if (key != 0u) {
+    const float v = ord2f(key) + 1.01f * pair_eps(q_resid[q], __uint_as_float(bank_stats[0]));
+    if (v == v && v < INFINITY) b = v;
+  }
+  bound[q] = b;
 }
 
 __global__ void fill_kernel(float* __restrict__ x, int64_t n, float v) {
@@ -1236,6 +1269,7 @@ struct RerankParams {
   float* out_dist; int dist_p;     // optional: L1 (p=1) / L2 (p=2) distance of each winner to the raw query
   int* fb_list; int* counters;     // counters[0] = fallback count, [1] = resolved here
   int allow_partial;               // an external bound was applied: fewer than k survivors is legitimate
+  const float* spec;               // speculative start threshold per query (NaN / -inf: none)
 };
 
 // exact cosine of one bank row against the query held in qh[] (raw values as doubles):
@@ -1456,6 +1490,18 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
       __syncwarp();
     }
   }
+  // speculative start (spec_rank): every row it dropped scores at most spec + eps exactly, so the
+  // result stands iff the k-th best found lies strictly above that; otherwise the exact path decides
+  {
+    const float sp = p.spec ? p.spec[q] : -INFINITY;
+    if (sp > -INFINITY) {
+      const float vk = (n_s >= p.k) ? ord2f((uint32_t)(ent[p.k - 1] >> 32)) : -INFINITY;
+      if (!(vk > sp + 0.5f * e2)) {
+        if (lane == 0) { p.fb_list[atomicAdd(&p.counters[0], 1)] = (int)q; atomicAdd(&p.counters[2], 1); }
+        return;
+      }
+    }
+  }
   for (int j = lane; j < p.k; j += 32) {
     if (j < n_s) {
       const unsigned long long e = ent[j];
@@ -1484,6 +1530,13 @@ int sim_topk_cluster(int64_t n_query) {
 int sim_topk_ablate() {
   static const int v = env_int("MCLST_SIM_ABLATE", 0);
   return v;
+}
+bool sim_topk_tuning_build() {
+#ifdef MCLST_TUNING_KNOBS
+  return true;
+#else
+  return false;
+#endif
 }
 
 int sim_topk_use_ring() {
@@ -1552,6 +1605,8 @@ void tc_workspace(Arena& a, int64_t n_bank, int64_t n_query, int dim, int top_k,
   w.q_nrm = a.take<double>((size_t)w.q_pad);
   w.q_resid = a.take<float>((size_t)w.q_pad);
   w.gthr = a.take<uint32_t>((size_t)w.q_pad);
+  w.spec = a.take<float>((size_t)w.q_pad);
+  w.speculate = 1;
   w.cand = a.take<uint2>((size_t)w.q_pad * w.SS * w.cap);
   w.cand_cnt = a.take<int>((size_t)w.q_pad * w.SS);
   w.fb_list = a.take<int>((size_t)n_query);
@@ -1604,11 +1659,39 @@ static int launch_sim_topk_t(const SimParams& p, dim3 grid, cudaStream_t st) {
 template <int CAP, int CL>
 static int launch_sim_topk_e(int epw, const SimParams& p, dim3 grid, cudaStream_t st) {
   switch (epw) {
+#ifdef MCLST_TUNING_KNOBS
     case 4: return launch_sim_topk_t<CAP, CL, 4>(p, grid, st);
-    case 8: return launch_sim_topk_t<CAP, CL, 8>(p, grid, st);
     case 16: return launch_sim_topk_t<CAP, CL, 16>(p, grid, st);
+#endif
+    case 8: return launch_sim_topk_t<CAP, CL, 8>(p, grid, st);
   }
   MCLST_REQUIRE(false, MCLST_ERR_UNSUPPORTED, "sim_topk: epilogue warps %d", epw);
+}
+
+// Speculative warm start.  The guaranteed seed threshold is the k-th largest value of the sample
+// (k sampled rows score at least that): global rank ~ k / f for a sampled fraction f, i.e. ~1500
+// at cfg4, where 97 % of the 32-score chunks still hold a passing element.  Starting from the
+// j-th largest instead (rank ~ j / f) is valid exactly when fewer than j of the true top k-1 rows
+// fell into the sample -- X ~ Binomial(k-1, f) for a bank in no particular order.  j is the
+// smallest rank with P(X >= j) < 1e-7 per query; the re-rank checks the outcome (the k-th best
+// exact score found must lie above threshold + eps, else nothing dropped could have mattered is
+// NOT guaranteed and the query is recomputed by the exact path), so a bank whose order defeats the
+// binomial model costs time, never correctness.
+static int spec_rank(int k, double f) {
+  if (!(f > 0.0) || f >= 0.5 || k < 8) return k;
+  const int n = k - 1;
+  // tail[j] = P(X >= j), summed from the top
+  double pmf = 1.0;
+  for (int i = 0; i < n; ++i) pmf *= f;              // P(X = n)
+  double tail = 0.0;
+  int best = k;
+  for (int j = n; j >= 1; --j) {
+    tail += pmf;                                       // now P(X >= j)
+    if (tail < 1e-7) best = j;
+    else break;
+    pmf *= (double)j / (double)(n - j + 1) * (1.0 - f) / f;   // P(X = j-1)
+  }
+  return std::max(4, std::min(best, k));
 }
 
 int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int top_k, float* dump,
@@ -1656,12 +1739,20 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
       int rc = launch_sim_topk_t<256, 1, 8>(sp, sgrid, st);
       if (rc) return rc;
     }
+    // bounds that other shards will rely on must be guaranteed ones: no speculation when staged
+    static const int spec_env = env_int("MCLST_SIM_SPEC", 1);
+    const bool speculate = w.speculate && spec_env && !(sb && (sb->bound_k || sb->bound_part));
+    const int k_seed = speculate ? spec_rank(top_k, (double)w.n_seed / (double)p.tiles_total) : top_k;
     seed_threshold_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, st>>>(
-        w.seed, w.n_seed * 8, n_query, top_k, w.q_resid, w.stats, w.gthr, sb ? std::max(1, sb->k_part) : 1,
-        sb ? sb->bound_k : nullptr, sb ? sb->bound_part : nullptr);
+        w.seed, w.n_seed * 8, n_query, k_seed, w.q_resid, w.stats, w.gthr, sb ? std::max(1, sb->k_part) : 1,
+        sb ? sb->bound_k : nullptr, sb ? sb->bound_part : nullptr, k_seed < top_k ? w.spec : nullptr);
     MCLST_LAUNCH_CHECK();
+    if (k_seed >= top_k) MCLST_CUDA(cudaMemsetAsync(w.spec, 0xff, (size_t)w.q_pad * sizeof(float), st));  // NaN: none
+  } else if (phase != 2) {
+    MCLST_CUDA(cudaMemsetAsync(w.spec, 0xff, (size_t)w.q_pad * sizeof(float), st));
   }
   if (phase == 1) return 0;
+#ifdef MCLST_TUNING_KNOBS
   if (w.ring) {
     auto launch_ring = [&](auto kern) -> int {
       MCLST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RG_SMEM));
@@ -1672,6 +1763,7 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
     if (w.cap == 256) return launch_ring(sim_topk_ring_kernel<256>);
     if (w.cap == 512) return launch_ring(sim_topk_ring_kernel<512>);
   }
+#endif
   if (w.lanes && dump == nullptr) {
     const LanePlan L = plan_lanes(w.q_pad / 128, p.tiles_total, sm_count(), std::max(1, 8 / (w.epw / 4)));
     MCLST_REQUIRE(L.slots == w.S, MCLST_ERR_UNSUPPORTED, "sim_topk: lane plan changed (%d vs %d slots)", L.slots, w.S);
@@ -1685,20 +1777,37 @@ int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int t
       return 0;
     };
     if (w.cap == 256 && w.epw == 8) return launch_lanes(sim_topk_lanes_kernel<256, 8, false>, 64 + 32 * 8);
+    if (w.cap == 1024 && w.epw == 8) return launch_lanes(sim_topk_lanes_kernel<1024, 8, false>, 64 + 32 * 8);
+#ifdef MCLST_TUNING_KNOBS
     if (w.cap == 256 && w.epw == 4) return launch_lanes(sim_topk_lanes_kernel<256, 4, false>, 64 + 32 * 4);
     if (w.cap == 256 && w.epw == 16) return launch_lanes(sim_topk_lanes_kernel<256, 16, false>, 64 + 32 * 16);
-    if (w.cap == 1024 && w.epw == 8) return launch_lanes(sim_topk_lanes_kernel<1024, 8, false>, 64 + 32 * 8);
     if (w.cap == 1024 && w.epw == 4) return launch_lanes(sim_topk_lanes_kernel<1024, 4, false>, 64 + 32 * 4);
+#endif
   }
+  // the (query block x stream) grid kernel: the debug similarity dump, and the lane kernel's
+  // predecessor in tuning builds
   if (w.cap == 256) {
     if (w.cluster == 1) return launch_sim_topk_e<256, 1>(w.epw, p, grid, st);
+#ifdef MCLST_TUNING_KNOBS
     if (w.cluster == 2) return launch_sim_topk_e<256, 2>(w.epw, p, grid, st);
     if (w.cluster == 4) return launch_sim_topk_e<256, 4>(w.epw, p, grid, st);
+#endif
   } else if (w.cap == 1024) {
     // large-k configurations (reference k = 200 / 600) are small problems: one variant
     if (w.cluster == 1) return launch_sim_topk_e<1024, 1>(w.epw, p, grid, st);
   }
   MCLST_REQUIRE(false, MCLST_ERR_UNSUPPORTED, "sim_topk: cap %d cluster %d", w.cap, w.cluster);
+}
+
+int launch_apply_bound(const TcWorkspace& w, int64_t n_query, const float* ext_bound, cudaStream_t st) {
+  apply_bound_kernel<<<(unsigned)ceil_div(n_query, 256), 256, 0, st>>>(ext_bound, n_query, w.q_resid, w.stats, w.gthr);
+  MCLST_LAUNCH_CHECK();
+  return 0;
+}
+int launch_export_bound(const TcWorkspace& w, int64_t n_query, float* bound, cudaStream_t st) {
+  export_bound_kernel<<<(unsigned)ceil_div(n_query, 256), 256, 0, st>>>(w.gthr, n_query, w.q_resid, w.stats, bound);
+  MCLST_LAUNCH_CHECK();
+  return 0;
 }
 
 int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64_t ldb,
@@ -1707,6 +1816,7 @@ int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64
                   int* counters, cudaStream_t st, bool allow_partial) {
   RerankParams p;
   p.allow_partial = allow_partial ? 1 : 0;
+  p.spec = allow_partial ? nullptr : w.spec;
   p.cand = w.cand; p.cand_cnt = w.cand_cnt; p.SS = w.SS; p.cap = w.cap; p.k = top_k;
   p.Q = n_query; p.N = n_bank; p.bank = bank; p.ldb = ldb; p.bank_nrm = w.b_nrm;
   p.query = query; p.ldq = ldq; p.q_nrm = w.q_nrm; p.q_resid = w.q_resid;

@@ -171,8 +171,10 @@ def retrieve_sharded(shard: BankShard, query: torch.Tensor, top_k: int = 50, mod
     numbers into the query batch) -- expr_pred / emb_pred then hold exactly those rows.
 
     Bank shards (CUDA backend): per query block  seed pass -> all-reduce of per-query bounds of the
-    GLOBAL k-th best score (2 floats per query) -> main pass against that bound -> all-gather of the
-    candidate lists -> merge -> owner-only partial sums -> reduce-scatter / all-reduce.  The queries
+    GLOBAL k-th best score (2 floats per query) -> candidate pass against that bound -> all-reduce
+    (MAX) of the bounds the converged thresholds give -> exact re-rank of only the candidates that
+    can still win globally (short, padded lists) -> all-gather of the lists -> merge -> owner-only
+    partial sums -> reduce-scatter / all-reduce.  The queries
     go in ``query_blocks`` blocks (default 2 when large) so that the collectives of one block run
     under the top-k kernels of the next."""
     backend = backend or CudaBackend()
@@ -214,14 +216,23 @@ def retrieve_sharded(shard: BankShard, query: torch.Tensor, top_k: int = 50, mod
             bounds[1].neg_()
             blk.bounds = bounds
             blk.w_bounds = dist.all_reduce(bounds, op=dist.ReduceOp.MAX, group=group, async_op=True)
-    # -- stage 2: main pass (+ candidate all-gather in flight)
-    for blk in blocks:
-        if staged:
-            from .retrieval import fm_main
+    # -- stage 2: candidate pass against the seed bound, second (tight) exchange in flight
+    if staged:
+        from .retrieval import fm_candidates, fm_main
+        for blk in blocks:
             blk.w_bounds.wait()
             ext = torch.maximum(blk.bounds[0], -blk.bounds[1]).contiguous()
+            # every shard's CONVERGED thresholds bound the global k-th best; their maximum decides
+            # which candidates are worth an exact re-rank anywhere
+            blk.bounds = torch.maximum(fm_candidates(shard.spot_key, blk.q, top_k, blk.ws, ext, bank_packed=True), ext)
+            blk.w_bounds = dist.all_reduce(blk.bounds, op=dist.ReduceOp.MAX, group=group, async_op=True)
+    # -- stage 3: re-rank of what can still win (+ candidate all-gather in flight)
+    for blk in blocks:
+        if staged:
+            blk.w_bounds.wait()
             blk.val, blk.idx, blk.dst = fm_main(shard.spot_key, blk.q, top_k, blk.ws, shard.index_offset,
-                                                p if need_dist else None, ext, bank_packed=True)
+                                                p if need_dist else None, blk.bounds, bank_packed=True,
+                                                finish_only=True)
         else:
             blk.val, blk.idx, blk.dst = backend.local_topk(shard, blk.q, top_k, p, need_dist)
         Qb = blk.q.shape[0]
@@ -230,7 +241,7 @@ def retrieve_sharded(shard: BankShard, query: torch.Tensor, top_k: int = 50, mod
         if need_dist:
             parts.append(blk.dst.view(Qb, top_k, 1))
         blk.g, blk.w_g = _all_gather_cat(torch.cat(parts, dim=2), group, async_op=True)
-    # -- stage 3: merge, weights, owner-only partial sums (+ reduction in flight)
+    # -- stage 4: merge, weights, owner-only partial sums (+ reduction in flight)
     if shard.expr_ready is not None:
         torch.cuda.current_stream(shard.expression_key.device).wait_event(shard.expr_ready)
     for blk in blocks:

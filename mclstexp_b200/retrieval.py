@@ -24,7 +24,7 @@ from ._lib import WEIGHT_MODES, check, load, ptr, require_cuda, stream_ptr
 ArrayLike = Union[np.ndarray, torch.Tensor]
 
 __all__ = ["find_matches", "find_matches_cscc", "find_matches_device", "fm_workspace", "fm_pack_bank", "fm_seed",
-           "fm_main", "weighted_topk_average",
+           "fm_candidates", "fm_main", "weighted_topk_average",
            "weighted_topk_average_device", "retrieve", "retrieve_device", "last_counters", "to_host", "Bank"]
 
 _last_ws: Optional[torch.Tensor] = None
@@ -151,10 +151,28 @@ def fm_seed(bank: torch.Tensor, qry: torch.Tensor, top_k: int, ws: torch.Tensor,
     return bounds
 
 
+def fm_candidates(bank: torch.Tensor, qry: torch.Tensor, top_k: int, ws: torch.Tensor,
+                  ext_bound: Optional[torch.Tensor] = None, bank_packed: bool = False) -> torch.Tensor:
+    """Stage 2a: the tensor-core candidate pass alone.  Returns float32 [Q]: a lower bound of this
+    bank's exact top_k-th best score per query, from the converged thresholds (-inf: unknown)."""
+    require_cuda(bank, qry, ws)
+    Q = qry.shape[0]
+    out = torch.empty((Q,), dtype=torch.float32, device=bank.device)
+    flags = _lib.FM_BANK_PACKED if bank_packed else 0
+    with torch.cuda.device(bank.device):
+        check(load().mclst_find_matches_candidates(ptr(bank), bank.shape[0], bank.stride(0), ptr(qry), Q,
+                                                   qry.stride(0), bank.shape[1], top_k, ptr(ext_bound), ptr(out),
+                                                   ptr(ws), ws.numel(), flags, stream_ptr()),
+              "find_matches_candidates")
+    return torch.nan_to_num(out, nan=float("-inf"), neginf=float("-inf"), posinf=float("inf"))
+
+
 def fm_main(bank: torch.Tensor, qry: torch.Tensor, top_k: int, ws: torch.Tensor, index_offset: int = 0,
-            dist_p: Optional[int] = None, ext_bound: Optional[torch.Tensor] = None, bank_packed: bool = False):
-    """Stage 2 (main pass + re-rank + exact fallback) -> (values, indices, distances | None).  Under an
-    external bound a row list may be shorter than top_k; its tail is (-inf, 0x7fffffff, +inf)."""
+            dist_p: Optional[int] = None, ext_bound: Optional[torch.Tensor] = None, bank_packed: bool = False,
+            finish_only: bool = False):
+    """Stage 2 (main pass + re-rank + exact fallback; ``finish_only``: re-rank + fallback after
+    ``fm_candidates``) -> (values, indices, distances | None).  Under an external bound a row list may
+    be shorter than top_k; its tail is (-inf, 0x7fffffff, +inf)."""
     global _last_ws
     Q = qry.shape[0]
     dev = bank.device
@@ -164,11 +182,12 @@ def fm_main(bank: torch.Tensor, qry: torch.Tensor, top_k: int, ws: torch.Tensor,
     if ext_bound is not None:
         assert ext_bound.dtype == torch.float32 and ext_bound.is_contiguous() and ext_bound.numel() == Q
     flags = _lib.FM_BANK_PACKED if bank_packed else 0
+    fn = load().mclst_find_matches_finish if finish_only else load().mclst_find_matches_main
     with torch.cuda.device(dev):
-        check(load().mclst_find_matches_main(ptr(bank), bank.shape[0], bank.stride(0), ptr(qry), Q, qry.stride(0),
-                                             bank.shape[1], top_k, index_offset, ptr(idx), ptr(val), ptr(dst),
-                                             dist_p or 2, ptr(ext_bound), ptr(ws), ws.numel(), flags,
-                                             stream_ptr()), "find_matches_main")
+        check(fn(ptr(bank), bank.shape[0], bank.stride(0), ptr(qry), Q, qry.stride(0),
+                 bank.shape[1], top_k, index_offset, ptr(idx), ptr(val), ptr(dst),
+                 dist_p or 2, ptr(ext_bound), ptr(ws), ws.numel(), flags,
+                 stream_ptr()), "find_matches_finish" if finish_only else "find_matches_main")
     _last_ws = ws
     return val, idx, dst
 
@@ -180,7 +199,7 @@ def last_counters() -> dict:
     out = (C.c_int64 * 4)()
     with torch.cuda.device(_last_ws.device):
         check(load().mclst_read_counters(ptr(_last_ws), out, stream_ptr()), "read_counters")
-    return {"tensor_core": int(out[0]), "exact_fallback": int(out[1])}
+    return {"tensor_core": int(out[0]), "exact_fallback": int(out[1]), "speculation_rejected": int(out[2])}
 
 
 def find_matches(spot_embeddings: ArrayLike, query_embeddings: ArrayLike, top_k: int = 1,

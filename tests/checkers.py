@@ -82,12 +82,17 @@ def loss_closed_form_f64(S, I, temperature, targets="eye", soft_scale="div", chu
     return loss, dS, dI
 
 
-def assert_grad_close(got, want, rtol=1e-3, rel_floor=1e-3, name=""):
-    """Three checks of a gradient matrix against its float64 statement (numpy or torch inputs):
-      * norm-wise:     ||got - want|| <= rtol ||want||
-      * max-normalised: |got - want| <= rtol max|want| everywhere
+def assert_grad_close(got, want, rtol=1e-3, rel_floor=1e-2, abs_cap=5e-5, name=""):
+    """Checks of a gradient matrix against its float64 statement (numpy or torch inputs):
+      * norm-wise:      ||got - want|| <= rtol ||want||
+      * max-normalised: |got - want| <= min(rtol, abs_cap) max|want| EVERYWHERE -- abs_cap = 5e-5 is
+        20 x tighter than the north star's 1e-3 and about 3 x what the reference's own float32
+        formulation achieves against float64 (1.3e-5 .. 1.5e-5 at B = 1024 .. 4096, measured with
+        tools/loss_accuracy.py), so small entries are constrained on the scale float32 allows;
       * element-wise RELATIVE: |got - want| <= rtol |want| on every entry with
-        |want| > rel_floor * max|want|  (small entries are constrained too)
+        |want| > rel_floor max|want|.  rel_floor = 1e-2 is the floor at which the reference's own
+        float32 result still meets 1e-3 (it reads 2e-4 .. 6e-4 there and 2e-3 .. 5e-3 at a floor of
+        1e-3: logits of +-256 carry 1.5e-5 of float32 rounding into every exponent).
     """
     g = torch.as_tensor(got).double().cpu()
     w = torch.as_tensor(want).double().cpu()
@@ -96,7 +101,8 @@ def assert_grad_close(got, want, rtol=1e-3, rel_floor=1e-3, name=""):
     wmax = float(w.abs().max())
     assert float((g - w).norm()) <= rtol * float(w.norm()) + 1e-300, \
         f"{name}: norm-wise {float((g - w).norm() / w.norm()):.3e}"
-    assert float(err.max()) <= rtol * wmax + 1e-300, f"{name}: max-normalised {float(err.max() / wmax):.3e}"
+    assert float(err.max()) <= min(rtol, abs_cap) * wmax + 1e-300, \
+        f"{name}: max-normalised {float(err.max() / wmax):.3e}"
     big = w.abs() > rel_floor * wmax
     rel = (err[big] / w.abs()[big])
     assert rel.numel() == 0 or float(rel.max()) <= rtol, \

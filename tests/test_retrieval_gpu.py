@@ -254,9 +254,10 @@ def _merge(vals, idxs, k):
 def test_bank_shards_with_bound_exchange_equal_whole_bank(N, Q, k, shards):
     """The multi-GPU bank-shard protocol replayed on ONE GPU: every shard's seed pass offers its
     bounds, they are combined exactly as distributed.retrieve_sharded combines them (max of the k-th
-    best bounds, min of the ceil(k/R)-th best bounds), every shard's main pass filters against the
-    global bound (lists may come back short and padded), the merged result must be bit-identical to
-    find_matches on the whole bank -- and to the oracle's spec."""
+    best bounds, min of the ceil(k/R)-th best bounds), every shard's candidate pass filters against
+    the global bound and reports what its converged thresholds imply, the maximum of those decides
+    what each shard still re-ranks (lists come back short and padded), and the merged result must be
+    bit-identical to find_matches on the whole bank -- and to the oracle's spec."""
     bank = torch.tensor(synth.embeddings(N, 256, 61, "clustered"), device="cuda")
     qry = torch.tensor(synth.embeddings(Q, 256, 62, "clustered"), device="cuda")
     wval, widx = retrieval.find_matches_device(bank, qry, k)
@@ -270,9 +271,15 @@ def test_bank_shards_with_bound_exchange_equal_whole_bank(N, Q, k, shards):
         bounds.append(retrieval.fm_seed(pb, qry, k, ws, k_part, want_bounds=True))
     b = torch.stack(bounds)                                     # [R, 2, Q]
     ext = torch.maximum(b[:, 0].max(0).values, b[:, 1].min(0).values).contiguous()
+    # second exchange: the converged thresholds of every shard's candidate pass
+    b2 = torch.stack([torch.maximum(retrieval.fm_candidates(pb, qry, k, wss[s], ext, bank_packed=True), ext)
+                      for s, pb in enumerate(parts)])
+    ext2 = b2.max(0).values.contiguous()
+    assert bool((ext2 <= wval[:, -1] + 1e-6).all())             # a LOWER bound of the true k-th best
     vals, idxs, short = [], [], 0
     for s, pb in enumerate(parts):
-        v, i, _ = retrieval.fm_main(pb, qry, k, wss[s], index_offset=cuts[s], ext_bound=ext)
+        v, i, _ = retrieval.fm_main(pb, qry, k, wss[s], index_offset=cuts[s], ext_bound=ext2, bank_packed=True,
+                                    finish_only=True)
         short += int((i == 0x7fffffff).any(1).sum())
         vals.append(v)
         idxs.append(i)
