@@ -253,7 +253,7 @@ static int find_matches_stages(int stages, const float* bank, int64_t n_bank, in
     prof_mark(st, "sim_topk");
     if ((rc = launch_sim_topk(t, n_bank, n_query, top_k, nullptr, 0, st, (stages & 1) ? 0 : 2, sb))) return rc;
     if (!(stages & 4)) {
-      if (sb && sb->bound_k && (rc = launch_export_bound(t, n_query, sb->bound_k, st))) return rc;
+      if (sb && sb->bound_k && (rc = launch_export_bound(t, n_query, top_k, sb->bound_k, st))) return rc;
       prof_mark(st, "end");
       return 0;
     }

@@ -395,7 +395,7 @@ gemm_tn_kernel(const GemmParams p) {
           if (lm > -INFINITY) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (cbase + j < p.N) ls += expf(__uint_as_float(v[j]) * alpha - lm);
+              if (cbase + j < p.N) ls += __expf(__uint_as_float(v[j]) * alpha - lm);
           }
           if (!p.c) continue;                                                // statistics only: nothing to store
         }

@@ -94,8 +94,8 @@ soft_pass2_kernel(const float* __restrict__ P1, const float* __restrict__ P3, in
   const float rl_r = rl[rg], za_r = za[rg], zal_r = za_lo[rg];
   float w = 0.f, c = 0.f;
   auto push = [&](float a, float p1j, int j) {
-    w += expf((a - za_r) - zal_r) * (rl_r + __ldg(cl + j) - 2.f * p1j);
-    c += expf((a - __ldg(za + j)) - __ldg(za_lo + j));
+    w += __expf((a - za_r) - zal_r) * (rl_r + __ldg(cl + j) - 2.f * p1j);
+    c += __expf((a - __ldg(za + j)) - __ldg(za_lo + j));
   };
   const int n4 = ((ld & 3) == 0) ? (ncols >> 2) : 0;
   for (int j = threadIdx.x; j < n4; j += LS_THREADS) {
@@ -260,15 +260,16 @@ lse_merge_kernel(const MergeJobs jobs) {
   const MergeJob& J = jobs.j[blockIdx.y];
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= J.n) return;
-  double M = -INFINITY;
-  for (int s = 0; s < J.slots && (int64_t)s * J.slot_cols < J.ncols; ++s)
-    M = fmax(M, (double)J.part[(size_t)s * J.ld + r].x);
+  // one pass, running maximum in float (exact), sum in double: only the final logarithm and the
+  // addition need the extra digits (the pair's lo half is below 2e-5 by construction)
+  float M = -INFINITY;
   double S = 0.0;
   for (int s = 0; s < J.slots && (int64_t)s * J.slot_cols < J.ncols; ++s) {
     const float2 p = J.part[(size_t)s * J.ld + r];
-    if (p.x > -INFINITY) S += (double)p.y * exp((double)p.x - M);
+    if (p.x > M) { S *= (double)__expf(M - p.x); M = p.x; }
+    if (p.x > -INFINITY) S += (double)p.y * (double)__expf(p.x - M);
   }
-  const double L = M + log(S);
+  const double L = (double)M + log(S);
   const float hi = (float)L;
   J.hi[r] = hi;
   J.lo[r] = (hi == hi && fabsf(hi) < INFINITY) ? (float)(L - (double)hi) : 0.f;
@@ -276,12 +277,14 @@ lse_merge_kernel(const MergeJobs jobs) {
 
 // column-wise (max, sum exp) of P [rows, ld] over row chunks of CL_ROWS: thread = column, rows
 // streamed with 8 loads in flight; part [chunk][ld].
-constexpr int CL_ROWS = 1024;
-__global__ void __launch_bounds__(256)
-col_lse_partial_kernel(const float* __restrict__ P, int64_t ld, int rows, int ncols,
+// rows per chunk: 1024 for large batches, fewer when that would leave the GPU idle (B = 1024: one
+// chunk per column block was 4 blocks and 59 us of serial latency)
+static int col_chunk_rows(int B) { return B >= 16384 ? 1024 : (B >= 4096 ? 256 : 64); }
+__global__ void __launch_bounds__(128)
+col_lse_partial_kernel(const float* __restrict__ P, int64_t ld, int rows, int ncols, int chunk_rows,
                        float2* __restrict__ part) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r0 = blockIdx.y * CL_ROWS, r1 = min(rows, r0 + CL_ROWS);
+  const int r0 = blockIdx.y * chunk_rows, r1 = min(rows, r0 + chunk_rows);
   if (j >= ncols) return;
   const float* p = P + j;
   float m = -INFINITY, s = 0.f;
@@ -295,12 +298,12 @@ col_lse_partial_kernel(const float* __restrict__ P, int64_t ld, int rows, int nc
     for (int i = 1; i < 8; ++i) cm = fmaxf(cm, v[i]);
     if (cm > m) { s *= __expf(m - cm); m = cm; }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += expf(v[i] - m);
+    for (int i = 0; i < 8; ++i) s += __expf(v[i] - m);
   }
   for (; r < r1; ++r) {
     const float x = __ldg(p + (size_t)r * ld);
     if (x > m) { s = s * __expf(m - x) + 1.f; m = x; }
-    else s += expf(x - m);
+    else s += __expf(x - m);
   }
   part[(size_t)blockIdx.y * ld + j] = make_float2(m, s);
 }
@@ -315,6 +318,8 @@ struct TileGradParams {
   int nkb;                         // B64 / 64
 };
 
+// (exponentials here and in the sweeps use the ex2.approx path: 2 ulp, and the argument's own
+// rounding |a| 2^-24 only matters where exp(a) is negligible)
 constexpr int TG = 64;             // tile edge
 constexpr int TG_LD = TG + 1;
 constexpr int TG_SMEM = (3 * TG * TG_LD + 2 * 8 * TG) * 4;
@@ -375,16 +380,16 @@ grad_tiles_kernel(const TileGradParams p) {
       float p_rj, p_jr;
       if (p.soft) {
         const float a = sC[r * TG_LD + j];
-        p_rj = expf((a - za_r) - zal_r);
-        p_jr = expf((a - st_c[4 * TG + j]) - st_c[5 * TG + j]);
+        p_rj = __expf((a - za_r) - zal_r);
+        p_jr = __expf((a - st_c[4 * TG + j]) - st_c[5 * TG + j]);
         const float da_rj = p_rj * (rl_r + cl_j - 2.f * x - wb_r);
         const float da_jr = p_jr * (rl_j + cl_r - 2.f * y - st_c[6 * TG + j]);
         hh = (da_rj + da_jr) * p.a_scale;
       } else {
         p_rj = p_jr = (R == J) ? 1.f : 0.f;
       }
-      a1 = (expf((x - rl_r) - rll_r) + st_c[7 * TG + j] * expf((x - cl_j) - cll_j) - 2.f * p_rj) * p.inv_t;   // 2B dLg_rj / T
-      a2 = (expf((y - rl_j) - rll_j) + cs_r * expf((y - cl_r) - cll_r) - 2.f * p_jr) * p.inv_t;               // 2B dLg_jr / T
+      a1 = (__expf((x - rl_r) - rll_r) + st_c[7 * TG + j] * __expf((x - cl_j) - cll_j) - 2.f * p_rj) * p.inv_t;   // 2B dLg_rj / T
+      a2 = (__expf((y - rl_j) - rll_j) + cs_r * __expf((y - cl_r) - cll_r) - 2.f * p_jr) * p.inv_t;               // 2B dLg_jr / T
     }
     g_rj[u] = a1; g_jr[u] = a2; h[u] = hh;
   }
@@ -481,7 +486,7 @@ static LossPlan plan_loss(void* ws, size_t cap, int B, int D, int soft, int want
   L.nblocks = ceil_div(rows_local, R);
   L.lean = L.nblocks == 1 && rows_local == B && lean_enabled();
   L.nt256 = (int)ceil_div(B, 256);
-  L.cchunks = (int)ceil_div(B, CL_ROWS);
+  L.cchunks = (int)ceil_div(B, col_chunk_rows(B));
   Arena a(ws, cap);
   L.flags = a.take<uint32_t>(16);
   L.Sp = take_operand(a, B, D, true, true, 1);
@@ -612,8 +617,8 @@ static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_em
         if ((rc = launch_gemm_tn(g, st))) return rc;
       }
       prof_mark(st, "col_lse");
-      col_lse_partial_kernel<<<dim3((unsigned)ceil_div(B, 256), (unsigned)L.cchunks), 256, 0, st>>>(
-          L.P1, L.B64, B, B, L.partc);
+      col_lse_partial_kernel<<<dim3((unsigned)ceil_div(B, 128), (unsigned)L.cchunks), 128, 0, st>>>(
+          L.P1, L.B64, B, B, col_chunk_rows(B), L.partc);
       MCLST_LAUNCH_CHECK();
       prof_mark(st, "lse_merge");
       MergeJobs mj{};

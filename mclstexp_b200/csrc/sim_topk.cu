@@ -1211,21 +1211,50 @@ seed_threshold_kernel(const float* __restrict__ seed, int n_vals, int64_t Q, int
   }
 }
 
-// After the candidate pass: the final shared threshold of a query is (lower bound of this shard's
-// k-th best tensor-core score) - 2.02 eps, so threshold + 1.01 eps bounds the exact k-th best from
-// below -- the figure the bank shards exchange before their re-ranks.
-__global__ void __launch_bounds__(256)
-export_bound_kernel(const uint32_t* __restrict__ gthr, int64_t Q, const float* __restrict__ q_resid,
+// After the candidate pass: a lower bound of this shard's exact k-th best score per query, for the
+// exchange between bank shards before their re-ranks.  Taken from the candidates themselves: the
+// k-th largest tensor-core score among everything the streams kept (radix descent over the keys,
+// held in shared memory), minus eps.  The running threshold alone is not enough -- a stream only
+// tightens it when its buffer fills, which a small shard with a good seed never does.
+constexpr int KB_MAX = 2048;      // candidates examined per query (more: fall back to the threshold)
+__global__ void __launch_bounds__(128)
+export_bound_kernel(const uint2* __restrict__ cand, const int* __restrict__ cand_cnt, int SS, int cap, int k,
+                    const uint32_t* __restrict__ gthr, int64_t Q, const float* __restrict__ q_resid,
                     const uint32_t* __restrict__ bank_stats, float* __restrict__ bound) {
-  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ uint32_t keys[4][KB_MAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * 4 + warp;
   if (q >= Q) return;
-  const uint32_t key = gthr[q];
+  const float e1 = 1.01f * pair_eps(q_resid[q], __uint_as_float(bank_stats[0]));
   float b = -INFINITY;
-  if (key != 0u) {
-    const float v = ord2f(key) + 1.01f * pair_eps(q_resid[q], __uint_as_float(bank_stats[0]));
+  const uint32_t gk = gthr[q];
+  if (gk != 0u) {                      // threshold = (lower bound of the k-th best score) - 2.02 eps
+    const float v = ord2f(gk) + e1;
     if (v == v && v < INFINITY) b = v;
   }
-  bound[q] = b;
+  int M = 0;
+  bool ok = true;
+  for (int s = 0; s < SS && ok; ++s) {
+    const int c = cand_cnt[(size_t)q * SS + s];
+    if (c < 0 || M + c > KB_MAX) { ok = false; break; }
+    const uint2* src = cand + ((size_t)q * SS + s) * cap;
+    for (int i = lane; i < c; i += 32) keys[warp][M + i] = f2ord(__uint_as_float(src[i].x));
+    M += c;
+  }
+  __syncwarp();
+  if (ok && M >= k) {
+    uint32_t T = 0;
+    for (int bit = 31; bit >= 8; --bit) {
+      const uint32_t candT = T | (1u << bit);
+      int c = 0;
+      for (int i = lane; i < M; i += 32) c += (keys[warp][i] >= candT) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= k) T = candT;
+    }
+    const float v = ord2f(T) - e1;
+    if (T != 0u && v == v && v < INFINITY) b = fmaxf(b, v);
+  }
+  if (lane == 0) bound[q] = b;
 }
 
 __global__ void fill_kernel(float* __restrict__ x, int64_t n, float v) {
@@ -1804,8 +1833,9 @@ int launch_apply_bound(const TcWorkspace& w, int64_t n_query, const float* ext_b
   MCLST_LAUNCH_CHECK();
   return 0;
 }
-int launch_export_bound(const TcWorkspace& w, int64_t n_query, float* bound, cudaStream_t st) {
-  export_bound_kernel<<<(unsigned)ceil_div(n_query, 256), 256, 0, st>>>(w.gthr, n_query, w.q_resid, w.stats, bound);
+int launch_export_bound(const TcWorkspace& w, int64_t n_query, int top_k, float* bound, cudaStream_t st) {
+  export_bound_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, st>>>(w.cand, w.cand_cnt, w.SS, w.cap, top_k, w.gthr,
+                                                                     n_query, w.q_resid, w.stats, bound);
   MCLST_LAUNCH_CHECK();
   return 0;
 }

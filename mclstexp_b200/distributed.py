@@ -323,6 +323,9 @@ def make_retrieval_grid(bank_shards: int, world: Optional[int] = None, rank: Opt
 
 
 # ----------------------------------------------------------------------------- loss
+REPLICATE_LOSS_BELOW = 8192      # global batch up to which every rank evaluates the whole loss itself
+
+
 class _ShardedLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, s_loc, i_loc, temperature, mode, group):
@@ -336,6 +339,16 @@ class _ShardedLoss(torch.autograd.Function):
         I = torch.empty((B, D), dtype=torch.float32, device=s_loc.device)
         dist.all_gather_into_tensor(S, s_loc.detach().contiguous(), group=group)
         dist.all_gather_into_tensor(I, i_loc.detach().contiguous(), group=group)
+        if B <= REPLICATE_LOSS_BELOW and hasattr(load(), "mclst_contrastive_loss"):
+            # small global batches: five blocking collectives on tiny tensors cost more than the whole
+            # single-GPU loss (B = 1024 on 8 GPUs measured 3.1 ms sharded vs 0.3 ms on one GPU), so
+            # every rank evaluates the full batch after the one embedding all-gather and keeps the
+            # gradient rows it owns
+            from .loss import contrastive_loss_fwd_bwd
+            loss, dS_full, dI_full = contrastive_loss_fwd_bwd(S, I, temperature, mode, want_grad=True)
+            r0 = rank * rows
+            ctx.save_for_backward(dS_full[r0:r0 + rows], dI_full[r0:r0 + rows])
+            return loss
         lib = load()
         nbytes = C.c_size_t()
         check(lib.mclst_contrastive_loss_workspace_bytes(B, D, mode, rows, C.byref(nbytes)), "loss workspace")

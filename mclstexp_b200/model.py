@@ -17,6 +17,8 @@ There is no CPU fallback: CPU tensors raise.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import warnings
 from typing import Optional
@@ -139,6 +141,29 @@ def layer_norm(x, weight, bias, eps=1e-5):
     return _LayerNorm.apply(x, weight, bias, eps)
 
 
+# Scratch the attention core may spend on score matrices.  Up to this many bytes the [heads, n, n]
+# probabilities of the whole sequence are kept for the backward pass (one softmax, no recompute);
+# beyond it the queries are processed in row blocks -- scores exist only for [heads, R, n] at a
+# time, nothing n x n is ever held, and the backward pass recomputes the block's probabilities
+# (flash-style streaming at row-block granularity).  n = 32768 tokens, 8 heads: 34 GB dense vs
+# 2 x 2 GiB streamed.
+ATTN_SCRATCH_BYTES = int(os.environ.get("MCLST_ATTN_SCRATCH_MB", 4096)) << 20
+
+
+def _attn_block_rows(n: int, heads: int) -> int:
+    """0 = dense (whole sequence at once); else query rows per block."""
+    if heads * n * n * 4 <= ATTN_SCRATCH_BYTES:
+        return 0
+    rows = ATTN_SCRATCH_BYTES // (2 * heads * n * 4)          # two [heads, R, n] temporaries in backward
+    return int(max(128, rows // 128 * 128))
+
+
+def _softmax_rows_(x3: torch.Tensor) -> None:
+    h, r, n = x3.shape
+    with torch.cuda.device(x3.device):
+        check(load().mclst_softmax_forward(ptr(x3), n, h * r, n, stream_ptr()), "softmax_forward")
+
+
 class _AttentionCore(torch.autograd.Function):
     """softmax(q k^T * scale) v for all heads of one token sequence (model.py:52-56).
 
@@ -152,19 +177,29 @@ class _AttentionCore(torch.autograd.Function):
         inner = three_inner // 3
         dh = inner // heads
         q, k, v = (qkv[:, i * inner:(i + 1) * inner].view(n, heads, dh).permute(1, 0, 2) for i in range(3))
-        probs = ops.matmul(q, k, alpha=scale)                       # [h, n, n] dots
-        with torch.cuda.device(qkv.device):
-            check(load().mclst_softmax_forward(ptr(probs), n, heads * n, n, stream_ptr()), "softmax_forward")
         out = torch.empty((n, inner), dtype=torch.float32, device=qkv.device)
-        ops.matmul(probs, v, b_trans=True, out=out.view(n, heads, dh).permute(1, 0, 2))
-        ctx.save_for_backward(qkv, probs)
-        ctx.heads, ctx.scale = heads, scale
+        o = out.view(n, heads, dh).permute(1, 0, 2)
+        R = _attn_block_rows(n, heads)
+        if R == 0:
+            probs = ops.matmul(q, k, alpha=scale)                       # [h, n, n] dots
+            _softmax_rows_(probs)
+            ops.matmul(probs, v, b_trans=True, out=o)
+            ctx.save_for_backward(qkv, probs)
+        else:
+            for r0 in range(0, n, R):
+                r1 = min(n, r0 + R)
+                p = ops.matmul(q[:, r0:r1], k, alpha=scale)             # [h, R, n]
+                _softmax_rows_(p)
+                ops.matmul(p, v, b_trans=True, out=o[:, r0:r1])
+                del p
+            ctx.save_for_backward(qkv)
+        ctx.heads, ctx.scale, ctx.block_rows = heads, scale, R
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        qkv, probs = ctx.saved_tensors
-        heads, scale = ctx.heads, ctx.scale
+        heads, scale, R = ctx.heads, ctx.scale, ctx.block_rows
+        qkv = ctx.saved_tensors[0]
         n, three_inner = qkv.shape
         inner = three_inner // 3
         dh = inner // heads
@@ -173,13 +208,24 @@ class _AttentionCore(torch.autograd.Function):
         do = d_out.view(n, heads, dh).permute(1, 0, 2)
         dqkv = torch.empty_like(qkv)
         dq, dk, dv = (dqkv[:, i * inner:(i + 1) * inner].view(n, heads, dh).permute(1, 0, 2) for i in range(3))
-        ops.matmul(probs, do, a_trans=True, b_trans=True, out=dv)    # P^T dO
-        ds = ops.matmul(do, v)                                       # dP = dO V^T
-        with torch.cuda.device(qkv.device):
-            check(load().mclst_softmax_backward(ptr(probs), ptr(ds), n, heads * n, n, stream_ptr()),
-                  "softmax_backward")
-        ops.matmul(ds, k, b_trans=True, alpha=scale, out=dq)         # dS K
-        ops.matmul(ds, q, a_trans=True, b_trans=True, alpha=scale, out=dk)   # dS^T Q
+        blocks = [(0, n)] if R == 0 else [(r0, min(n, r0 + R)) for r0 in range(0, n, R)]
+        for b, (r0, r1) in enumerate(blocks):
+            if R == 0:
+                probs = ctx.saved_tensors[1]
+            else:                                                    # recompute this block's probabilities
+                probs = ops.matmul(q[:, r0:r1], k, alpha=scale)
+                _softmax_rows_(probs)
+            acc = None if b == 0 else True                           # dK / dV accumulate over the row blocks
+            ops.matmul(probs, do[:, r0:r1], a_trans=True, b_trans=True, out=dv,
+                       residual=dv if acc else None)                 # P^T dO
+            ds = ops.matmul(do[:, r0:r1], v)                         # dP = dO V^T
+            with torch.cuda.device(qkv.device):
+                check(load().mclst_softmax_backward(ptr(probs), ptr(ds), n, heads * (r1 - r0), n, stream_ptr()),
+                      "softmax_backward")
+            ops.matmul(ds, k, b_trans=True, alpha=scale, out=dq[:, r0:r1])       # dS K
+            ops.matmul(ds, q[:, r0:r1], a_trans=True, b_trans=True, alpha=scale, out=dk,
+                       residual=dk if acc else None)                 # dS^T Q
+            del probs, ds
         return dqkv, None, None
 
 

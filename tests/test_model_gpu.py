@@ -193,3 +193,30 @@ def test_embed_bank_equals_per_batch_loop(N, group):
         loop = torch.cat([net.embed_spots(expr[b0:b0 + group].cuda(), pos[b0:b0 + group].cuda())
                           for b0 in range(0, N, group)])
     _close(spot, loop.cpu().numpy(), "fused vs loop", rtol=1e-4)
+
+
+def test_attention_row_block_streaming_equals_dense(monkeypatch):
+    """Beyond the scratch budget the attention core streams the queries in row blocks and keeps no
+    [heads, n, n] tensor (backward recomputes each block's probabilities): same output and gradients
+    as the dense path, and as torch's float64 attention."""
+    torch.manual_seed(3)
+    n, heads, dh = 700, 8, 64
+    qkv = (torch.randn(n, 3 * heads * dh, device="cuda") * 0.5).requires_grad_(True)
+    w = torch.randn(n, heads * dh, device="cuda")
+    out_d = mm.attention_core(qkv, heads, dh ** -0.5)
+    (out_d * w).sum().backward()
+    g_d = qkv.grad.clone()
+    qkv.grad = None
+    monkeypatch.setattr(mm, "ATTN_SCRATCH_BYTES", 1 << 20)
+    assert mm._attn_block_rows(n, heads) == 128
+    out_s = mm.attention_core(qkv, heads, dh ** -0.5)
+    (out_s * w).sum().backward()
+    g_s = qkv.grad.clone()
+    _close(out_s, out_d.detach().cpu().numpy(), "streamed vs dense output", rtol=1e-5)
+    _close(g_s, g_d.cpu().numpy(), "streamed vs dense grad", rtol=1e-5)
+    q64 = qkv.detach().double().requires_grad_(True)
+    q, k, v = (q64[:, i * heads * dh:(i + 1) * heads * dh].view(n, heads, dh).permute(1, 0, 2) for i in range(3))
+    ref = (torch.softmax(q @ k.transpose(1, 2) * dh ** -0.5, -1) @ v).permute(1, 0, 2).reshape(n, heads * dh)
+    (ref * w.double()).sum().backward()
+    _close(out_s, ref.detach().cpu().numpy(), "streamed vs float64 output")
+    _close(g_s, q64.grad.cpu().numpy(), "streamed vs float64 grad")
