@@ -219,19 +219,31 @@ softmax_blockdiag_kernel(float* __restrict__ s, int64_t ld, int cols, int group,
 }
 
 // ---------------------------------------------------------------- column sums (bias grads)
-__global__ void __launch_bounds__(256)
+// 32 columns per block, 32 row lanes, 8 independent loads in flight per thread (a serial walk of a
+// 1024-row column measured 19 us per call, ten calls per training step); fixed summation order.
+__global__ void __launch_bounds__(1024)
 col_sum_kernel(const float* __restrict__ x, int64_t ld, int64_t R, int C, float* __restrict__ out) {
-  __shared__ float sm[8][33];
+  __shared__ float sm[32][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ty = threadIdx.x >> 5;
   float a = 0.f;
-  if (c < C)
-    for (int64_t r = ty; r < R; r += 8) a += x[r * ld + c];
+  if (c < C) {
+    const float* col = x + c;
+    int64_t r = ty;
+    for (; r + 7 * 32 < R; r += 8 * 32) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(col + (r + 32 * i) * ld);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a += v[i];
+    }
+    for (; r < R; r += 32) a += __ldg(col + r * ld);
+  }
   sm[ty][threadIdx.x & 31] = a;
   __syncthreads();
   if (ty == 0 && c < C) {
     float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    for (int i = 0; i < 32; ++i) t += sm[i][threadIdx.x];
     out[c] = t;
   }
 }
@@ -362,7 +374,7 @@ extern "C" int mclst_col_sum(const float* x, int64_t ld, int64_t rows, int cols,
                              mclst_stream_t stream) {
   MCLST_REQUIRE(x && out, MCLST_ERR_INVALID, "col_sum: null");
   prof_mark((cudaStream_t)stream, "col_sum");
-  col_sum_kernel<<<(unsigned)ceil_div(cols, 32), 256, 0, (cudaStream_t)stream>>>(x, ld, rows, cols, out);
+  col_sum_kernel<<<(unsigned)ceil_div(cols, 32), 1024, 0, (cudaStream_t)stream>>>(x, ld, rows, cols, out);
   MCLST_LAUNCH_CHECK();
   return 0;
 }

@@ -236,9 +236,14 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // streamed a 128x256 tile needs 87 FLOP per byte from L2 (16 TB/s at full tensor rate, more than
 // L2 delivers: the CL = 1 kernel measured ~500 TFLOP/s on the loss products); sharing B cuts the
 // traffic per CTA from 48 to 32 KiB per K block.
-template <int CL>
+// BN = 128 halves the tile: a problem with fewer than one 128 x 256 tile per SM (every nn.Linear of
+// the B = 1024 training step: 32 .. 48 tiles on 148 SMs) is bounded by the serial K loop of ONE
+// tile, and a 128-column tile walks it in half the time while twice as many SMs take part.
+template <int CL, int BN>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_tn_kernel(const GemmParams p) {
+  static_assert(BN == 256 || (BN == 128 && CL == 1), "tile widths: 256, or 128 without B sharing");
+  constexpr int STAGE_TX = (1 + BN / 128) * TP_SLICE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + GM_STAGES * GM_STAGE_BYTES);
@@ -249,7 +254,7 @@ gemm_tn_kernel(const GemmParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.nkb;
   const int iters = p.nseg * nkb;
-  const int mt = (int)((p.M + GM_BM - 1) / GM_BM), nt = (int)((p.N + GM_BN - 1) / GM_BN);
+  const int mt = (int)((p.M + GM_BM - 1) / GM_BM), nt = (int)((p.N + BN - 1) / BN);
   const int mg = (mt + CL - 1) / CL;                     // groups of CL vertically adjacent tiles
   const int64_t groups = (int64_t)mg * nt * p.batch;
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
@@ -294,10 +299,13 @@ gemm_tn_kernel(const GemmParams p) {
             }
           }
           mbar_wait(&bar_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&bar_full[stage], GM_STAGE_BYTES);
+          mbar_arrive_expect_tx(&bar_full[stage], STAGE_TX);
           uint8_t* dst = smem + stage * GM_STAGE_BYTES;
           bulk_g2s(dst, a + a_off, TP_SLICE_BYTES, &bar_full[stage]);
-          if (CL == 1) {
+          if (BN == 128) {
+            bulk_g2s(dst + TP_SLICE_BYTES, b + ((size_t)nb * nkb + kb) * TP_SLICE_BYTES,
+                     TP_SLICE_BYTES, &bar_full[stage]);
+          } else if (CL == 1) {
             bulk_g2s(dst + TP_SLICE_BYTES, b + ((size_t)(2 * nb) * nkb + kb) * TP_SLICE_BYTES,
                      TP_SLICE_BYTES, &bar_full[stage]);
             bulk_g2s(dst + 2 * TP_SLICE_BYTES, b + ((size_t)(2 * nb + 1) * nkb + kb) * TP_SLICE_BYTES,
@@ -314,14 +322,14 @@ gemm_tn_kernel(const GemmParams p) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(GM_BM, GM_BN, false);
+      constexpr uint32_t idesc = make_idesc_f16(GM_BM, BN, false);
       uint32_t stage = 0, phase = 0;
       int n = 0;
       for (int64_t g = g0; g < groups; g += gstep, ++n) {
         const int buf = n & 1;
         mbar_wait(&bar_tempty[buf], ((n >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * GM_BN;
+        const uint32_t d_tmem = tmem_base + buf * BN;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
@@ -370,32 +378,49 @@ gemm_tn_kernel(const GemmParams p) {
         rs[it] = alpha * ((p.a_scale && mb < mt) ? __ldg(p.a_scale + (size_t)z * p.a_scale_batch + m0 + it * 4 + sub) : 1.f);
       mbar_wait(&bar_tfull[buf], (n >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * GM_BN;
-      const int64_t n0 = (int64_t)nb * GM_BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
+      const int64_t n0 = (int64_t)nb * BN;
       // fused row log-sum-exp (loss products): running (max, sum exp) of MY row (TMEM lane) over
       // the 128 columns this warp drains, written as one partial per (row, tile column, half)
       float lm = -INFINITY, ls = 0.f;
       const int64_t my_row = m0 + lane;
 #pragma unroll 1
-      for (int c = chalf * 4; c < chalf * 4 + 4; ++c) {
+      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
         if (n0 + c * 32 >= p.N || mb >= mt || m0 >= p.M) break;             // uniform
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
         if (p.lse_part) {
+          // 6 instructions per element: scale + max, then subtract + scale + ex2 + add.  The running
+          // maximum is taken on the scaled values themselves (exact), so the exponent arguments are
+          // small differences; ex2.approx adds 2 ulp to terms that only matter near the maximum.
           const int64_t cbase = n0 + c * 32;
+          const bool full = cbase + 32 <= p.N;
+          float x[32];
           float cm = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float x = (cbase + j < p.N) ? __uint_as_float(v[j]) * alpha : -INFINITY;
-            cm = fmaxf(cm, x);
-            if (p.diag && cbase + j == my_row + p.diag_offset && my_row < p.M) p.diag[my_row] = x;
+            x[j] = __uint_as_float(v[j]) * alpha;
+            if (!full && cbase + j >= p.N) x[j] = -INFINITY;
+            cm = fmaxf(cm, x[j]);
           }
-          if (cm > lm) { ls *= __expf(lm - cm); lm = cm; }                  // (exp(-inf) = 0 on the first chunk)
-          if (lm > -INFINITY) {
+          if (p.diag) {                                   // the one chunk of this warp that crosses the diagonal
+            const int64_t dj = my_row + p.diag_offset - cbase;
+            if (__any_sync(0xffffffffu, dj >= 0 && dj < 32)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cbase + j < p.N) ls += __expf(__uint_as_float(v[j]) * alpha - lm);
+              for (int j = 0; j < 32; ++j)
+                if (dj == j && my_row < p.M) p.diag[my_row] = x[j];
+            }
+          }
+          if (cm > lm) { ls *= exp2f((lm - cm) * 1.4426950408889634f); lm = cm; }   // (0 on the first chunk)
+          if (lm > -INFINITY) {
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              acc0 += exp2f((x[j] - lm) * 1.4426950408889634f);
+              acc1 += exp2f((x[j + 1] - lm) * 1.4426950408889634f);
+            }
+            ls += acc0 + acc1;
           }
           if (!p.c) continue;                                                // statistics only: nothing to store
         }
@@ -459,15 +484,15 @@ gemm_tn_kernel(const GemmParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-template <int CL>
+template <int CL, int BN>
 static int launch_gemm_cl(const GemmParams& q, cudaStream_t st) {
-  auto kern = gemm_tn_kernel<CL>;
+  auto kern = gemm_tn_kernel<CL, BN>;
   static bool attr_set = false;
   if (!attr_set) {
     MCLST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
     attr_set = true;
   }
-  const int64_t mt = ceil_div(q.M, GM_BM), nt = ceil_div(q.N, GM_BN);
+  const int64_t mt = ceil_div(q.M, GM_BM), nt = ceil_div(q.N, BN);
   const int64_t groups = ceil_div(mt, CL) * nt * q.batch;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(CL * std::min<int64_t>(groups, sm_count() / CL)));
@@ -502,7 +527,10 @@ int launch_gemm_tn(const GemmParams& p, cudaStream_t st) {
   const int64_t tiles = ceil_div(p.M, GM_BM) * ceil_div(p.N, GM_BN) * q.batch;
   // pairs pay off once the grid is saturated and there are at least two row tiles to pair
   const bool pair = force == 2 || (force == 0 && p.M > GM_BM && tiles >= 2 * (int64_t)sm_count());
-  return pair ? launch_gemm_cl<2>(q, st) : launch_gemm_cl<1>(q, st);
+  if (pair) return launch_gemm_cl<2, 256>(q, st);
+  // under-filled grid: half-width tiles (the fused row statistics are laid out for 256-wide tiles)
+  const bool narrow = !p.lse_part && tiles < (int64_t)sm_count();
+  return narrow ? launch_gemm_cl<1, 128>(q, st) : launch_gemm_cl<1, 256>(q, st);
 }
 
 // ---- operand bookkeeping --------------------------------------------------------------

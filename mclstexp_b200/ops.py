@@ -9,9 +9,15 @@ import torch
 from ._lib import check, load, ptr, require_cuda, stream_ptr
 
 _ws_cache = {}
+WS_KEEP_MAX = 1 << 30      # scratch above this size is not kept between calls (a B = 32k loss needs ~20 GB)
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Per (device, stream) scratch for the C-ABI calls.  Requests up to WS_KEEP_MAX reuse one cached
+    buffer (the training-step sizes; also what a captured CUDA graph keeps pointing at); larger ones
+    get a fresh tensor that the caching allocator takes back as soon as the caller drops it."""
+    if nbytes > WS_KEEP_MAX:
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
