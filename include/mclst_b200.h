@@ -347,7 +347,9 @@ int mclst_matmul(const float* A, int64_t lda, int a_trans, int64_t a_batch_strid
  *                last_step[row]+1 .. steps_done; with d_out ([batch, genes], the gradient of the
  *                embed-add output) also apply step steps_done + 1 with the row's summed gradient.
  *                first_scratch: table_rows ints.  error_flag (device) is OR-ed with 1 when a
- *                position is outside [0, table_rows).
+ *                position is outside [0, table_rows).  steps_done_dev (nullable, device int):
+ *                when given it overrides steps_done at EXECUTION time, so that a launch captured
+ *                in a CUDA graph follows the counter as training advances.
  *   lazy_flush   every row to steps_done (before state_dict / evaluation reads the table) */
 size_t mclst_adam_coef_bytes(int max_steps);
 int mclst_adam_set_step(void* coef_table, int max_steps, int step, double lr, double beta1,
@@ -357,8 +359,8 @@ int mclst_adam_dense(float* param, const float* grad, float* exp_avg, float* exp
 int mclst_adam_lazy_rows(float* table, float* exp_avg, float* exp_avg_sq, int* last_step,
                          int* first_scratch, int table_rows, int genes, const float* position,
                          int64_t ld_p, int column, int batch, const float* d_out, int64_t ld_d,
-                         const void* coef_table, int steps_done, uint32_t* error_flag,
-                         mclst_stream_t stream);
+                         const void* coef_table, int steps_done, const int* steps_done_dev,
+                         uint32_t* error_flag, mclst_stream_t stream);
 int mclst_adam_lazy_flush(float* table, float* exp_avg, float* exp_avg_sq, int* last_step,
                           int table_rows, int genes, const void* coef_table, int steps_done,
                           mclst_stream_t stream);

@@ -97,7 +97,7 @@ def load() -> C.CDLL:
     lib.mclst_adam_coef_bytes.restype = sz
     lib.mclst_adam_set_step.argtypes = [p, i32, i32, f64, f64, f64, f64, f64, p]
     lib.mclst_adam_dense.argtypes = [p, p, p, p, i64, p, i32, p]
-    lib.mclst_adam_lazy_rows.argtypes = [p, p, p, p, p, i32, i32, p, i64, i32, i32, p, i64, p, i32, p, p]
+    lib.mclst_adam_lazy_rows.argtypes = [p, p, p, p, p, i32, i32, p, i64, i32, i32, p, i64, p, i32, p, p, p]
     lib.mclst_adam_lazy_flush.argtypes = [p, p, p, p, i32, i32, p, i32, p]
     for name in header_symbols():
         fn = getattr(lib, name)          # AttributeError if the .so does not export it

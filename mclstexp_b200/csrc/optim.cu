@@ -66,7 +66,10 @@ lazy_rows_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict
                  int* __restrict__ last, const int* __restrict__ first, const float* __restrict__ pos,
                  int64_t ld_p, int col, int batch, int table_rows, int G,
                  const float* __restrict__ d_out, int64_t ld_d, const AdamCoef* __restrict__ coef,
-                 int upto) {
+                 int upto_arg, const int* __restrict__ upto_dev) {
+  // the step counter may live on the device: a captured CUDA graph replays this launch with the
+  // counter's CURRENT value instead of the one baked into the launch arguments
+  const int upto = upto_dev ? *upto_dev : upto_arg;
   __shared__ int dup[OP_THREADS];
   __shared__ int n_dup;
   const int b = blockIdx.x;
@@ -194,8 +197,8 @@ extern "C" int mclst_adam_dense(float* param, const float* grad, float* exp_avg,
 extern "C" int mclst_adam_lazy_rows(float* table, float* exp_avg, float* exp_avg_sq, int* last_step,
                                     int* first_scratch, int table_rows, int genes, const float* position,
                                     int64_t ld_p, int column, int batch, const float* d_out, int64_t ld_d,
-                                    const void* coef_table, int steps_done, uint32_t* error_flag,
-                                    mclst_stream_t stream) {
+                                    const void* coef_table, int steps_done, const int* steps_done_dev,
+                                    uint32_t* error_flag, mclst_stream_t stream) {
   MCLST_REQUIRE(table && exp_avg && exp_avg_sq && last_step && first_scratch && position && coef_table &&
                 error_flag, MCLST_ERR_INVALID, "adam_lazy_rows: null pointer");
   MCLST_REQUIRE(table_rows >= 1 && genes >= 1 && batch >= 0 && (column == 0 || column == 1) && steps_done >= 0,
@@ -209,7 +212,7 @@ extern "C" int mclst_adam_lazy_rows(float* table, float* exp_avg, float* exp_avg
   MCLST_LAUNCH_CHECK();
   lazy_rows_kernel<<<batch, OP_THREADS, 0, st>>>(table, exp_avg, exp_avg_sq, last_step, first_scratch,
                                                  position, ld_p, column, batch, table_rows, genes, d_out,
-                                                 ld_d, (const AdamCoef*)coef_table, steps_done);
+                                                 ld_d, (const AdamCoef*)coef_table, steps_done, steps_done_dev);
   MCLST_LAUNCH_CHECK();
   return 0;
 }

@@ -22,13 +22,10 @@ class GraphedTrainStep:
     created on the default stream invalidates the capture)."""
 
     def __init__(self, model: torch.nn.Module, example_batch: Dict[str, torch.Tensor], warmup: int = 3):
-        for name in ("x_embed", "y_embed"):
-            w = getattr(getattr(model, name, None), "weight", None)
-            if getattr(w, "_mclst_lazy", None) is not None:
-                raise RuntimeError(
-                    "GraphedTrainStep: the position tables are owned by optim.LazyEmbeddingAdam "
-                    "(TrainOptimizer); its step counter is a launch argument, so it cannot be captured. "
-                    "Use a stock torch.optim optimizer with the graphed step.")
+        # position tables owned by optim.LazyEmbeddingAdam (TrainOptimizer): the captured forward
+        # contains their row catch-up (which follows the optimiser's device-side step counter) and the
+        # captured backward leaves (position, d_out) in static buffers for ``optimizer.step()``
+        self.lazy = getattr(getattr(getattr(model, "x_embed", None), "weight", None), "_mclst_lazy", None)
         self.model = model
         self.static = {k: v.clone() for k, v in example_batch.items()}
         self.table_rows = getattr(getattr(model, "x_embed", None), "num_embeddings", None)
@@ -38,15 +35,20 @@ class GraphedTrainStep:
             for _ in range(warmup):
                 for p in model.parameters():
                     p.grad = None
+                if self.lazy is not None:
+                    self.lazy.zero_grad()
                 model(self.static).backward()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         for p in model.parameters():       # backward inside the capture then ASSIGNS fresh .grad
             p.grad = None                  # buffers from the graph's pool: every replay overwrites them
+        if self.lazy is not None:
+            self.lazy.zero_grad()
         with torch.cuda.graph(self.graph):
             self.loss = model(self.static)
             self.loss.backward()
+        self._lazy_pending = self.lazy._pending if self.lazy is not None else None
         # the replay writes into THESE buffers; ``optimizer.zero_grad()`` (set_to_none=True is the
         # default, train.py:37) drops them from the parameters, so they are re-attached after
         # every replay -- otherwise optimizer.step() would silently skip every parameter
@@ -64,6 +66,8 @@ class GraphedTrainStep:
         for p, g in self.grads.items():
             if p.grad is not g:
                 p.grad = g
+        if self.lazy is not None:                          # the replay refreshed these static buffers
+            self.lazy._pending = self._lazy_pending
         return self.loss
 
     def zero_grad(self, set_to_none: bool = False) -> None:

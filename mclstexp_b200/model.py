@@ -286,7 +286,8 @@ class _EmbedAddLazy(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         (position,) = ctx.saved_tensors
-        if int(ctx.err.item()):
+        # (under CUDA-graph capture GraphedTrainStep validates the positions before every replay)
+        if not torch.cuda.is_current_stream_capturing() and int(ctx.err.item()):
             raise IndexError("position index out of range for x_embed / y_embed (nn.Embedding(65536, dim))")
         d_out = _c2d(d_out)
         ctx.lazy.record(position, d_out)

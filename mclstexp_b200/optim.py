@@ -13,8 +13,9 @@ point where they are observed (forward gathers, ``flush()``, ``state_dict()``).
     opt = TrainOptimizer(model, lr=1e-4, weight_decay=1e-3)     # stock Adam + lazy tables
     opt.zero_grad(); loss = model(batch); loss.backward(); opt.step()
 
-No CPU fallback; not compatible with ``graphs.GraphedTrainStep`` (the step counter is a launch
-argument; the graphed step raises when it sees lazily-owned tables).
+No CPU fallback.  Works with ``graphs.GraphedTrainStep``: the catch-up inside the captured forward
+reads the step counter from device memory, and the graphed step re-arms the recorded
+(position, gradient) pair after every replay; ``step()`` itself runs outside the graph.
 """
 from __future__ import annotations
 
@@ -74,6 +75,9 @@ class LazyEmbeddingAdam:
         self._first = torch.empty(max(t.shape[0] for t in tables), dtype=torch.int32, device=dev)
         self._err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.steps_done = 0
+        # the same counter on the device: kernels captured in a CUDA graph (the catch-up inside a
+        # graphed forward) read it at replay time
+        self._steps_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self._pending: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
         for i, t in enumerate(self.tables):
             t._mclst_lazy = self                                  # picked up by model.embed_add
@@ -96,12 +100,14 @@ class LazyEmbeddingAdam:
                                                ptr(self.last[i]), ptr(self._first), t.shape[0], t.shape[1],
                                                ptr(position), position.stride(0), i, position.shape[0],
                                                ptr(d_out), d_out.stride(0) if d_out is not None else 0,
-                                               ptr(self.coef.buf), self.steps_done, ptr(self._err), stream_ptr()),
+                                               ptr(self.coef.buf), self.steps_done, ptr(self._steps_dev),
+                                               ptr(self._err), stream_ptr()),
                       "adam_lazy_rows")
 
     def catch_up(self, position: torch.Tensor) -> None:
         """Bring the rows a batch is about to read to the current step (called by embed_add)."""
-        if self.steps_done > 0:
+        # (under graph capture the launch must exist even at step 0: the replay follows the device counter)
+        if self.steps_done > 0 or torch.cuda.is_current_stream_capturing():
             self._rows(position, None)
 
     def record(self, position: torch.Tensor, d_out: torch.Tensor) -> None:
@@ -132,6 +138,7 @@ class LazyEmbeddingAdam:
         self.coef.set_step(self.steps_done + 1, self.lr, self.betas, self.eps, self.weight_decay)
         self._rows(position, d_out)
         self.steps_done += 1
+        self._steps_dev.add_(1)
         self._pending = None
 
     def flush(self) -> None:
@@ -173,6 +180,7 @@ class LazyEmbeddingAdam:
         for dst, src in zip(self.exp_avg_sq, sd["exp_avg_sq"]):
             dst.copy_(src)
         self.steps_done = int(sd["step"])
+        self._steps_dev.fill_(self.steps_done)
         if self.steps_done >= self.coef.max_steps:
             raise ValueError("LazyEmbeddingAdam.load_state_dict: step beyond max_steps")
         self.set_hyper(**sd.get("hyper", {}))

@@ -103,8 +103,8 @@ def test_gpu_checker_equals_cpu_oracle():
                                          0.7, targets, scale, chunk=128)
         l64, dS64, dI64 = oracle.contrastive_loss_closed_form(S, I, 0.7, targets, scale)
         assert abs(l - l64) <= 1e-12 * abs(l64)
-        assert_grad_close(dS, dS64, rtol=1e-9, name="dS")
-        assert_grad_close(dI, dI64, rtol=1e-9, name="dI")
+        assert_grad_close(dS, dS64, rtol=1e-9, elem_rtol=1e-9, name="dS")
+        assert_grad_close(dI, dI64, rtol=1e-9, elem_rtol=1e-9, name="dI")
 
 
 def _big_inputs(B, seed):

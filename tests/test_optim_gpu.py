@@ -220,7 +220,31 @@ def test_graphed_step_with_stock_adam_and_zero_grad_trains():
     changed = [k for k, p in net.named_parameters() if not torch.equal(p.detach(), before[k])]
     assert len(changed) == len(before), sorted(set(before) - set(changed))
     assert losses[-1] < losses[0]
-    lazy_net = _small_net(dev, G)
-    mo.TrainOptimizer(lazy_net, lr=1e-3)
-    with pytest.raises(RuntimeError):
-        GraphedTrainStep(lazy_net, batch)
+
+
+def test_graphed_step_with_lazy_tables_equals_eager():
+    """DESIGN section 9 (r1, open): the lazily updated position tables inside a captured training
+    step.  Graph replay + TrainOptimizer must follow the eager TrainOptimizer run exactly (same
+    kernels, same order) over steps that touch different rows."""
+    from mclstexp_b200.graphs import GraphedTrainStep
+    dev = torch.device("cuda", 0)
+    G, B = 96, 64
+    g = torch.Generator(device=dev)
+    g.manual_seed(8)
+    batches = [_batch(dev, B, G, g, hi=(12 if i % 2 else 50)) for i in range(6)]
+    a, b = _small_net(dev, G), _small_net(dev, G)
+    oa, ob = mo.TrainOptimizer(a, lr=1e-3, weight_decay=1e-3), mo.TrainOptimizer(b, lr=1e-3, weight_decay=1e-3)
+    step = GraphedTrainStep(b, batches[0])
+    for bt in batches:
+        oa.zero_grad()
+        la = a(bt)
+        la.backward()
+        oa.step()
+        ob.zero_grad()
+        lb = step(bt)
+        ob.step()
+        assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(la))
+    assert ob.lazy.steps_done == len(batches) and int(ob.lazy._steps_dev) == len(batches)
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        torch.testing.assert_close(sb[k], sa[k], rtol=1e-6, atol=1e-8, msg=k)
