@@ -128,11 +128,13 @@ int mclst_find_matches_dist(const float* bank, int64_t n_bank, int64_t ld_bank,
  *         which loses every mclst_merge_topk comparison.
  * _candidates + _finish: _main in two halves with a second, much tighter exchange in between.
  *         _candidates runs the tensor-core candidate pass (against ext_bound when given) and
- *         writes bound_out[q]: a lower bound of this shard's exact top_k-th best score taken from
- *         its CONVERGED thresholds.  The maximum of bound_out over the shards, passed to _finish,
- *         lets every shard re-rank (exactly) only the candidates that can still be among the
- *         global winners -- about (top_k + band) / shards rows instead of top_k + band.  Pass
- *         _finish a bound at least as tight as the one _candidates got. */
+ *         writes, from the candidates it kept, bound_out[q] / bound_part_out[q] (nullable): lower
+ *         bounds of this shard's exact top_k-th / k_part-th best score.  max over shards of
+ *         bound_out and min over shards of bound_part_out (k_part = ceil(top_k / shards)) both
+ *         bound the global top_k-th best; passed to _finish, the larger lets every shard re-rank
+ *         (exactly) only the candidates that can still be among the global winners -- about
+ *         (top_k + band) / shards rows instead of top_k + band.  Pass _finish a bound at least as
+ *         tight as the one _candidates got. */
 int mclst_find_matches_pack_bank(const float* bank, int64_t n_bank, int64_t ld_bank, int dim,
                                  int top_k, void* workspace, size_t workspace_bytes,
                                  mclst_stream_t stream);
@@ -150,9 +152,9 @@ int mclst_find_matches_main(const float* bank, int64_t n_bank, int64_t ld_bank,
 
 int mclst_find_matches_candidates(const float* bank, int64_t n_bank, int64_t ld_bank,
                                   const float* query, int64_t n_query, int64_t ld_query, int dim,
-                                  int top_k, const float* ext_bound, float* bound_out,
-                                  void* workspace, size_t workspace_bytes, int flags,
-                                  mclst_stream_t stream);
+                                  int top_k, int k_part, const float* ext_bound, float* bound_out,
+                                  float* bound_part_out, void* workspace, size_t workspace_bytes,
+                                  int flags, mclst_stream_t stream);
 int mclst_find_matches_finish(const float* bank, int64_t n_bank, int64_t ld_bank,
                               const float* query, int64_t n_query, int64_t ld_query, int dim,
                               int top_k, int64_t index_offset, int64_t* out_indices,

@@ -59,7 +59,7 @@ def load() -> C.CDLL:
     lib.mclst_find_matches_seed.argtypes = [p, i64, i64, p, i64, i64, i32, i32, i32, p, p, p, sz, i32, p]
     lib.mclst_find_matches_main.argtypes = [p, i64, i64, p, i64, i64, i32, i32, i64, p, p, p, i32, p, p, sz,
                                             i32, p]
-    lib.mclst_find_matches_candidates.argtypes = [p, i64, i64, p, i64, i64, i32, i32, p, p, p, sz, i32, p]
+    lib.mclst_find_matches_candidates.argtypes = [p, i64, i64, p, i64, i64, i32, i32, i32, p, p, p, p, sz, i32, p]
     lib.mclst_find_matches_finish.argtypes = lib.mclst_find_matches_main.argtypes
     lib.mclst_debug_similarity.argtypes = [p, i64, i64, p, i64, i64, i32, p, i64, p, sz, p]
     lib.mclst_gene_metrics_scratch_doubles.argtypes = [i32, C.POINTER(sz)]

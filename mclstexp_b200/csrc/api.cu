@@ -213,6 +213,8 @@ static int find_matches_stages(int stages, const float* bank, int64_t n_bank, in
     }
     if ((stages & 2) && !(stages & 4) && sb && sb->bound_k)
       MCLST_CUDA(cudaMemsetAsync(sb->bound_k, 0xff, (size_t)n_query * 4, st));
+    if ((stages & 2) && !(stages & 4) && sb && sb->bound_part)
+      MCLST_CUDA(cudaMemsetAsync(sb->bound_part, 0xff, (size_t)n_query * 4, st));
     if (!(stages & 4) || n_query == 0) return 0;
     MCLST_CUDA(cudaMemsetAsync(w.counters, 0, 256, st));
     prof_mark(st, "row_norms");
@@ -253,7 +255,7 @@ static int find_matches_stages(int stages, const float* bank, int64_t n_bank, in
     prof_mark(st, "sim_topk");
     if ((rc = launch_sim_topk(t, n_bank, n_query, top_k, nullptr, 0, st, (stages & 1) ? 0 : 2, sb))) return rc;
     if (!(stages & 4)) {
-      if (sb && sb->bound_k && (rc = launch_export_bound(t, n_query, top_k, sb->bound_k, st))) return rc;
+      if (sb && sb->bound_k && (rc = launch_export_bound(t, n_query, top_k, sb->bound_k, sb->k_part, sb->bound_part, st))) return rc;
       prof_mark(st, "end");
       return 0;
     }
@@ -326,11 +328,12 @@ extern "C" int mclst_find_matches_main(const float* bank, int64_t n_bank, int64_
 
 extern "C" int mclst_find_matches_candidates(const float* bank, int64_t n_bank, int64_t ld_bank,
                                              const float* query, int64_t n_query, int64_t ld_query,
-                                             int dim, int top_k, const float* ext_bound, float* bound_out,
-                                             void* workspace, size_t workspace_bytes, int flags,
-                                             mclst_stream_t stream) {
+                                             int dim, int top_k, int k_part, const float* ext_bound,
+                                             float* bound_out, float* bound_part_out, void* workspace,
+                                             size_t workspace_bytes, int flags, mclst_stream_t stream) {
   if (n_query == 0) return 0;
-  SeedBounds sb{1, bound_out, nullptr, ext_bound};
+  MCLST_REQUIRE(bound_out, MCLST_ERR_INVALID, "find_matches_candidates: null bound_out");
+  SeedBounds sb{k_part, bound_out, bound_part_out, ext_bound};
   return find_matches_stages(2, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k, 0, nullptr,
                              nullptr, nullptr, 2, &sb, workspace, workspace_bytes, flags,
                              (cudaStream_t)stream);

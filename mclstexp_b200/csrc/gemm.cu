@@ -62,17 +62,17 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4* h, uint4* l) 
 // Non-transposed: out row r = in row r, K index = in column.  One warp per row.
 // inv_scale != null: per-row factor (computed here, inverse stored); else amax_bits != null: the
 // tensor-wide factor; else none.
-__global__ void __launch_bounds__(256)
-pack_split_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
-                  float scale, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
-                  int64_t rows_pad, int nkb_total, int kb_offset, int nkb_mine,
-                  const uint32_t* __restrict__ amax_bits, float* __restrict__ inv_scale,
-                  int64_t x_batch, size_t out_batch) {
-  x += (int64_t)blockIdx.z * x_batch;
-  hi += (size_t)blockIdx.z * out_batch;
-  if (lo) lo += (size_t)blockIdx.z * out_batch;
+__device__ __forceinline__ void
+pack_plain_block(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                 float scale, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
+                 int64_t rows_pad, int nkb_total, int kb_offset, int nkb_mine,
+                 const uint32_t* __restrict__ amax_bits, float* __restrict__ inv_scale,
+                 int64_t x_batch, size_t out_batch, unsigned bx, unsigned bz) {
+  x += (int64_t)bz * x_batch;
+  hi += (size_t)bz * out_batch;
+  if (lo) lo += (size_t)bz * out_batch;
   const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t r = (int64_t)bx * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows_pad) return;
   float inv = 1.f;
   if (inv_scale) {
@@ -91,7 +91,7 @@ pack_split_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64
     }
     amax = warp_max(amax);
     scale *= pow2_scale(amax, &inv);
-    if (lane == 0) inv_scale[(size_t)blockIdx.z * rows_pad + r] = inv;
+    if (lane == 0) inv_scale[(size_t)bz * rows_pad + r] = inv;
   } else if (amax_bits) {
     scale *= pow2_scale(__uint_as_float(__ldg(amax_bits)), &inv);
   }
@@ -111,23 +111,33 @@ pack_split_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64
   }
 }
 
+__global__ void __launch_bounds__(256)
+pack_split_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                  float scale, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
+                  int64_t rows_pad, int nkb_total, int kb_offset, int nkb_mine,
+                  const uint32_t* __restrict__ amax_bits, float* __restrict__ inv_scale,
+                  int64_t x_batch, size_t out_batch) {
+  pack_plain_block(x, rows, cols, ld, scale, hi, lo, rows_pad, nkb_total, kb_offset, nkb_mine, amax_bits,
+                   inv_scale, x_batch, out_batch, blockIdx.x, blockIdx.z);
+}
+
 // Transposed: out row r = in column r, K index = in row.  Lane <-> out row (contiguous in
 // the input), each thread gathers 8 consecutive K (8 input rows) for one 16-byte chunk.
 // With inv_scale the block first scans its 32 columns for their max|x| (gridDim.y must be 1; the
 // block then has 32 warps and keeps 8 independent loads in flight per thread: a serial scan of a
 // 1024-row column cost 70 us per pack and 1.2 ms per training step).
-__global__ void __launch_bounds__(1024)
-pack_split_t_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
-                    float scale, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
-                    int64_t out_rows_pad, int nkb_total, int kb_offset, int nkb_mine,
-                    const uint32_t* __restrict__ amax_bits, float* __restrict__ inv_scale,
-                    int64_t x_batch, size_t out_batch) {
-  __shared__ float s_amax[32][32];
-  x += (int64_t)blockIdx.z * x_batch;
-  hi += (size_t)blockIdx.z * out_batch;
-  if (lo) lo += (size_t)blockIdx.z * out_batch;
+__device__ __forceinline__ void
+pack_trans_block(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                 float scale, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
+                 int64_t out_rows_pad, int nkb_total, int kb_offset, int nkb_mine,
+                 const uint32_t* __restrict__ amax_bits, float* __restrict__ inv_scale,
+                 int64_t x_batch, size_t out_batch, unsigned bx, unsigned by, unsigned ny, unsigned bz,
+                 float (*s_amax)[32]) {
+  x += (int64_t)bz * x_batch;
+  hi += (size_t)bz * out_batch;
+  if (lo) lo += (size_t)bz * out_batch;
   const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * 32 + lane;                    // out row = in column
+  const int64_t r = (int64_t)bx * 32 + lane;                            // out row = in column
   const int cgroup = threadIdx.x >> 5;                                  // chunk lane
   const int ngroups = blockDim.x >> 5;                                  // 8 (y-split grid) or 32 (self-scaling)
   float inv = 1.f;
@@ -149,13 +159,13 @@ pack_split_t_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int
     __syncthreads();
     for (int g = 0; g < ngroups; ++g) amax = fmaxf(amax, s_amax[g][lane]);
     scale *= pow2_scale(amax, &inv);
-    if (cgroup == 0 && r < out_rows_pad) inv_scale[(size_t)blockIdx.z * out_rows_pad + r] = inv;
+    if (cgroup == 0 && r < out_rows_pad) inv_scale[(size_t)bz * out_rows_pad + r] = inv;
   } else if (amax_bits) {
     scale *= pow2_scale(__uint_as_float(__ldg(amax_bits)), &inv);
   }
   if (r >= out_rows_pad) return;
   const int nchunks = nkb_mine * 8;
-  for (int c = blockIdx.y * ngroups + cgroup; c < nchunks; c += gridDim.y * ngroups) {
+  for (int c = by * ngroups + cgroup; c < nchunks; c += ny * ngroups) {
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -168,6 +178,65 @@ pack_split_t_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int
     *reinterpret_cast<uint4*>(hi + off) = h;
     if (lo) *reinterpret_cast<uint4*>(lo + off) = l;
   }
+}
+
+__global__ void __launch_bounds__(1024)
+pack_split_t_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                    float scale, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo,
+                    int64_t out_rows_pad, int nkb_total, int kb_offset, int nkb_mine,
+                    const uint32_t* __restrict__ amax_bits, float* __restrict__ inv_scale,
+                    int64_t x_batch, size_t out_batch) {
+  __shared__ float s_amax[32][32];
+  pack_trans_block(x, rows, cols, ld, scale, hi, lo, out_rows_pad, nkb_total, kb_offset, nkb_mine, amax_bits,
+                   inv_scale, x_batch, out_batch, blockIdx.x, blockIdx.y, gridDim.y, blockIdx.z, s_amax);
+}
+
+// Both operands of one matmul in ONE launch (the training step is launch-bound: 51 products, two
+// packs each): blocks [0, a.blocks) pack A, the rest pack B, each plain or transposed, 32 warps,
+// per-row factors.
+struct PackJob {
+  const float* x;
+  int64_t rows, cols, ld, rows_pad, x_batch;
+  uint8_t *hi, *lo;
+  float* inv_scale;
+  size_t out_batch;
+  int nkb, transpose, blocks_x, blocks;      // blocks = blocks_x * batch
+};
+__global__ void __launch_bounds__(1024)
+pack_pair_kernel(const PackJob a, const PackJob b) {
+  __shared__ float s_amax[32][32];
+  const bool first = blockIdx.x < (unsigned)a.blocks;
+  const PackJob& j = first ? a : b;
+  const unsigned id = first ? blockIdx.x : blockIdx.x - (unsigned)a.blocks;
+  const unsigned bx = id % (unsigned)j.blocks_x, bz = id / (unsigned)j.blocks_x;
+  if (j.transpose)
+    pack_trans_block(j.x, j.rows, j.cols, j.ld, 1.f, j.hi, j.lo, j.rows_pad, j.nkb, 0, j.nkb, nullptr,
+                     j.inv_scale, j.x_batch, j.out_batch, bx, 0, 1, bz, s_amax);
+  else
+    pack_plain_block(j.x, j.rows, j.cols, j.ld, 1.f, j.hi, j.lo, j.rows_pad, j.nkb, 0, j.nkb, nullptr,
+                     j.inv_scale, j.x_batch, j.out_batch, bx, bz);
+}
+
+static PackJob make_pack_job(const float* x, int64_t rows, int64_t cols, int64_t ld, bool transpose,
+                             const PackedOperand& dst, int batch, int64_t x_batch_elems) {
+  PackJob j{};
+  j.x = x; j.rows = rows; j.cols = cols; j.ld = ld; j.rows_pad = dst.rows_pad; j.x_batch = x_batch_elems;
+  j.hi = dst.hi; j.lo = dst.lo; j.inv_scale = dst.inv_scale; j.out_batch = dst.bytes; j.nkb = dst.nkb;
+  j.transpose = transpose ? 1 : 0;
+  j.blocks_x = (int)ceil_div(dst.rows_pad, 32);      // 32 rows (plain: one per warp) or 32 columns per block
+  j.blocks = j.blocks_x * batch;
+  return j;
+}
+
+int launch_pack_pair(const float* A, int64_t a_rows, int64_t a_cols, int64_t lda, bool a_trans,
+                     const PackedOperand& pa, int64_t a_batch_elems, const float* B, int64_t b_rows,
+                     int64_t b_cols, int64_t ldb, bool b_trans, const PackedOperand& pb,
+                     int64_t b_batch_elems, int batch, cudaStream_t st) {
+  const PackJob ja = make_pack_job(A, a_rows, a_cols, lda, a_trans, pa, batch, a_batch_elems);
+  const PackJob jb = make_pack_job(B, b_rows, b_cols, ldb, b_trans, pb, batch, b_batch_elems);
+  pack_pair_kernel<<<(unsigned)(ja.blocks + jb.blocks), 1024, 0, st>>>(ja, jb);
+  MCLST_LAUNCH_CHECK();
+  return 0;
 }
 
 // max|x| of a tensor as the bit pattern of a non-negative float (orders like an unsigned integer);
@@ -584,10 +653,9 @@ extern "C" int mclst_matmul(const float* A, int64_t lda, int a_trans, int64_t a_
   int rc;
   prof_mark(st, "pack_split");
   // a_trans: A is stored [K, M] (operand rows are its columns); likewise b_trans: B stored [K, N]
-  if ((rc = launch_pack_split(A, a_trans ? K : M, a_trans ? M : K, lda, a_trans != 0, 1.f, pa, 0,
-                              pa.nkb, nullptr, pa.inv_scale, st, batch, a_batch_stride))) return rc;
-  if ((rc = launch_pack_split(B, b_trans ? K : N, b_trans ? N : K, ldb, b_trans != 0, 1.f, pb, 0,
-                              pb.nkb, nullptr, pb.inv_scale, st, batch, b_batch_stride))) return rc;
+  if ((rc = launch_pack_pair(A, a_trans ? K : M, a_trans ? M : K, lda, a_trans != 0, pa, a_batch_stride,
+                             B, b_trans ? K : N, b_trans ? N : K, ldb, b_trans != 0, pb, b_batch_stride,
+                             batch, st))) return rc;
   GemmParams g{};
   g.a_hi = pa.hi; g.a_lo = pa.lo; g.b_hi = pb.hi; g.b_lo = pb.lo;
   g.a_batch_bytes = pa.bytes; g.b_batch_bytes = pb.bytes;

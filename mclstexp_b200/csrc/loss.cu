@@ -581,7 +581,9 @@ static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_em
   bind_stats(L, stats ? stats : L.stats_ws);
   int rc;
   const int nkbD = L.Sp.nkb;
-  const bool single = L.nblocks == 1 && rows == B;     // P1/P2/P3 survive between phases
+  // one row block holds every row this call owns (the whole batch, or this rank's slice of it):
+  // P1 / P2 / P3 survive in the workspace between the phases and nothing is recomputed
+  const bool single = L.nblocks == 1;
   if (phase == 1) {
     // one power-of-two factor for both embedding matrices (they are concatenated along K and
     // shared between products): max|x| over S and I as a device word every consumer reads

@@ -48,7 +48,8 @@ struct SeedBounds {
 int launch_sim_topk(const TcWorkspace& w, int64_t n_bank, int64_t n_query, int top_k, float* dump,
                     int64_t dump_ld, cudaStream_t st, int phase = 0, const SeedBounds* sb = nullptr);
 int launch_apply_bound(const TcWorkspace& w, int64_t n_query, const float* ext_bound, cudaStream_t st);
-int launch_export_bound(const TcWorkspace& w, int64_t n_query, int top_k, float* bound, cudaStream_t st);
+int launch_export_bound(const TcWorkspace& w, int64_t n_query, int top_k, float* bound, int k_part,
+                        float* bound_part, cudaStream_t st);
 int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64_t ldb,
                   const float* query, int64_t n_query, int64_t ldq, int dim, int top_k,
                   int64_t index_offset, int64_t* out_idx, float* out_val, float* out_dist, int dist_p,

@@ -1220,7 +1220,8 @@ constexpr int KB_MAX = 2048;      // candidates examined per query (more: fall b
 __global__ void __launch_bounds__(128)
 export_bound_kernel(const uint2* __restrict__ cand, const int* __restrict__ cand_cnt, int SS, int cap, int k,
                     const uint32_t* __restrict__ gthr, int64_t Q, const float* __restrict__ q_resid,
-                    const uint32_t* __restrict__ bank_stats, float* __restrict__ bound) {
+                    const uint32_t* __restrict__ bank_stats, float* __restrict__ bound, int k_part,
+                    float* __restrict__ bound_part) {
   __shared__ uint32_t keys[4][KB_MAX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * 4 + warp;
@@ -1254,7 +1255,26 @@ export_bound_kernel(const uint2* __restrict__ cand, const int* __restrict__ cand
     const float v = ord2f(T) - e1;
     if (T != 0u && v == v && v < INFINITY) b = fmaxf(b, v);
   }
-  if (lane == 0) bound[q] = b;
+  // the k_part-th best of this shard (k_part = ceil(k / shards)): the MINIMUM of these over the
+  // shards bounds the global k-th best too, and for shards of similar content it sits at global
+  // rank ~k instead of ~k * shards
+  float bp = b;
+  if (bound_part && ok && M >= k_part) {
+    uint32_t T = 0;
+    for (int bit = 31; bit >= 8; --bit) {
+      const uint32_t candT = T | (1u << bit);
+      int c = 0;
+      for (int i = lane; i < M; i += 32) c += (keys[warp][i] >= candT) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= k_part) T = candT;
+    }
+    const float v = ord2f(T) - e1;
+    if (T != 0u && v == v && v < INFINITY) bp = fmaxf(bp, v);
+  }
+  if (lane == 0) {
+    bound[q] = b;
+    if (bound_part) bound_part[q] = bp;
+  }
 }
 
 __global__ void fill_kernel(float* __restrict__ x, int64_t n, float v) {
@@ -1639,10 +1659,12 @@ void tc_workspace(Arena& a, int64_t n_bank, int64_t n_query, int dim, int top_k,
   w.cand = a.take<uint2>((size_t)w.q_pad * w.SS * w.cap);
   w.cand_cnt = a.take<int>((size_t)w.q_pad * w.SS);
   w.fb_list = a.take<int>((size_t)n_query);
-  // seed pass: a strided 1/32 sample of the bank tiles, at most 64 tiles, at least 2k chunks
+  // seed pass: a strided sample of the bank tiles -- 1/24 of them, at most 128 (3.3 % of the main
+  // pass at 1M rows; a 125k-row shard of an 8-GPU run samples 20 tiles, 4 %, where a fixed 1/8 cost
+  // 12 %), at least 2k chunk maxima
   const int64_t tiles = w.n_pad / ST_BN;
   static const int seed_max = env_int("MCLST_SIM_SEED_TILES", 128);
-  int n_seed = (int)std::min<int64_t>(seed_max, tiles / 8);
+  int n_seed = (int)std::min<int64_t>(seed_max, std::max<int64_t>(tiles / 24, std::min<int64_t>(tiles / 8, (2 * top_k + 7) / 8)));
   static const int seed_env = env_int("MCLST_SIM_SEED", 1);
   if (!seed_env || n_seed * 8 < 2 * top_k) n_seed = 0;
   w.n_seed = n_seed;
@@ -1833,9 +1855,11 @@ int launch_apply_bound(const TcWorkspace& w, int64_t n_query, const float* ext_b
   MCLST_LAUNCH_CHECK();
   return 0;
 }
-int launch_export_bound(const TcWorkspace& w, int64_t n_query, int top_k, float* bound, cudaStream_t st) {
+int launch_export_bound(const TcWorkspace& w, int64_t n_query, int top_k, float* bound, int k_part,
+                        float* bound_part, cudaStream_t st) {
   export_bound_kernel<<<(unsigned)ceil_div(n_query, 4), 128, 0, st>>>(w.cand, w.cand_cnt, w.SS, w.cap, top_k, w.gthr,
-                                                                     n_query, w.q_resid, w.stats, bound);
+                                                                     n_query, w.q_resid, w.stats, bound,
+                                                                     std::max(1, std::min(k_part, top_k)), bound_part);
   MCLST_LAUNCH_CHECK();
   return 0;
 }

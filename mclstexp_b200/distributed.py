@@ -222,16 +222,21 @@ def retrieve_sharded(shard: BankShard, query: torch.Tensor, top_k: int = 50, mod
         for blk in blocks:
             blk.w_bounds.wait()
             ext = torch.maximum(blk.bounds[0], -blk.bounds[1]).contiguous()
-            # every shard's CONVERGED thresholds bound the global k-th best; their maximum decides
-            # which candidates are worth an exact re-rank anywhere
-            blk.bounds = torch.maximum(fm_candidates(shard.spot_key, blk.q, top_k, blk.ws, ext, bank_packed=True), ext)
-            blk.w_bounds = dist.all_reduce(blk.bounds, op=dist.ReduceOp.MAX, group=group, async_op=True)
+            # what every shard actually kept bounds the global k-th best much more tightly: the same
+            # two figures (k-th best: max over shards; ceil(k/R)-th best: min over shards, sent
+            # negated) from the candidate buffers, one more MAX all-reduce
+            b2 = fm_candidates(shard.spot_key, blk.q, top_k, blk.ws, ext, bank_packed=True, k_part=k_part)
+            b2[0] = torch.maximum(b2[0], ext)
+            b2[1].neg_()
+            blk.bounds = b2
+            blk.w_bounds = dist.all_reduce(b2, op=dist.ReduceOp.MAX, group=group, async_op=True)
     # -- stage 3: re-rank of what can still win (+ candidate all-gather in flight)
     for blk in blocks:
         if staged:
             blk.w_bounds.wait()
+            ext2 = torch.maximum(blk.bounds[0], -blk.bounds[1]).contiguous()
             blk.val, blk.idx, blk.dst = fm_main(shard.spot_key, blk.q, top_k, blk.ws, shard.index_offset,
-                                                p if need_dist else None, blk.bounds, bank_packed=True,
+                                                p if need_dist else None, ext2, bank_packed=True,
                                                 finish_only=True)
         else:
             blk.val, blk.idx, blk.dst = backend.local_topk(shard, blk.q, top_k, p, need_dist)

@@ -152,17 +152,19 @@ def fm_seed(bank: torch.Tensor, qry: torch.Tensor, top_k: int, ws: torch.Tensor,
 
 
 def fm_candidates(bank: torch.Tensor, qry: torch.Tensor, top_k: int, ws: torch.Tensor,
-                  ext_bound: Optional[torch.Tensor] = None, bank_packed: bool = False) -> torch.Tensor:
-    """Stage 2a: the tensor-core candidate pass alone.  Returns float32 [Q]: a lower bound of this
-    bank's exact top_k-th best score per query, from the converged thresholds (-inf: unknown)."""
+                  ext_bound: Optional[torch.Tensor] = None, bank_packed: bool = False,
+                  k_part: int = 1) -> torch.Tensor:
+    """Stage 2a: the tensor-core candidate pass alone.  Returns float32 [2, Q]: lower bounds of this
+    bank's exact top_k-th (row 0) and k_part-th (row 1) best score per query, from the candidates it
+    kept (-inf: unknown)."""
     require_cuda(bank, qry, ws)
     Q = qry.shape[0]
-    out = torch.empty((Q,), dtype=torch.float32, device=bank.device)
+    out = torch.empty((2, Q), dtype=torch.float32, device=bank.device)
     flags = _lib.FM_BANK_PACKED if bank_packed else 0
     with torch.cuda.device(bank.device):
         check(load().mclst_find_matches_candidates(ptr(bank), bank.shape[0], bank.stride(0), ptr(qry), Q,
-                                                   qry.stride(0), bank.shape[1], top_k, ptr(ext_bound), ptr(out),
-                                                   ptr(ws), ws.numel(), flags, stream_ptr()),
+                                                   qry.stride(0), bank.shape[1], top_k, k_part, ptr(ext_bound),
+                                                   ptr(out), ptr(out[1]), ptr(ws), ws.numel(), flags, stream_ptr()),
               "find_matches_candidates")
     return torch.nan_to_num(out, nan=float("-inf"), neginf=float("-inf"), posinf=float("inf"))
 

@@ -272,9 +272,9 @@ def test_bank_shards_with_bound_exchange_equal_whole_bank(N, Q, k, shards):
     b = torch.stack(bounds)                                     # [R, 2, Q]
     ext = torch.maximum(b[:, 0].max(0).values, b[:, 1].min(0).values).contiguous()
     # second exchange: the converged thresholds of every shard's candidate pass
-    b2 = torch.stack([torch.maximum(retrieval.fm_candidates(pb, qry, k, wss[s], ext, bank_packed=True), ext)
-                      for s, pb in enumerate(parts)])
-    ext2 = b2.max(0).values.contiguous()
+    b2 = torch.stack([retrieval.fm_candidates(pb, qry, k, wss[s], ext, bank_packed=True, k_part=k_part)
+                      for s, pb in enumerate(parts)])                                # [R, 2, Q]
+    ext2 = torch.maximum(torch.maximum(b2[:, 0].max(0).values, b2[:, 1].min(0).values), ext).contiguous()
     assert bool((ext2 <= wval[:, -1] + 1e-6).all())             # a LOWER bound of the true k-th best
     vals, idxs, short = [], [], 0
     for s, pb in enumerate(parts):
