@@ -370,6 +370,17 @@ gemm_tn_kernel(const GemmParams p) {
           mbar_wait(&bar_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bar_full[stage], STAGE_TX);
           uint8_t* dst = smem + stage * GM_STAGE_BYTES;
+          if (p.a1_mn > 0 && kb < p.a_nkb1) {
+            // transposed image: 64 of its rows (K') x the 128 columns of output tile mb = the lower
+            // or upper 8 atoms of two neighbouring K slices of row block kb / 2
+            const uint8_t* img = (seg == 1) ? a_lo : a_hi;
+            const int s0 = 2 * mb, s1 = min(2 * mb + 1, p.a1_mn - 1);
+            const size_t rb_off = (size_t)(kb >> 1) * p.a1_mn;
+            const size_t half = (size_t)(kb & 1) * (TP_SLICE_BYTES / 2);
+            bulk_g2s(dst, img + (rb_off + s0) * TP_SLICE_BYTES + half, TP_SLICE_BYTES / 2, &bar_full[stage]);
+            bulk_g2s(dst + TP_SLICE_BYTES / 2, img + (rb_off + s1) * TP_SLICE_BYTES + half, TP_SLICE_BYTES / 2,
+                     &bar_full[stage]);
+          } else
           bulk_g2s(dst, a + a_off, TP_SLICE_BYTES, &bar_full[stage]);
           if (BN == 128) {
             bulk_g2s(dst + TP_SLICE_BYTES, b + ((size_t)nb * nkb + kb) * TP_SLICE_BYTES,
@@ -404,10 +415,20 @@ gemm_tn_kernel(const GemmParams p) {
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * GM_STAGE_BYTES);
           const uint32_t b_addr = a_addr + TP_SLICE_BYTES;
+          const int kb_it = it % nkb;
+          if (p.a1_mn > 0 && kb_it < p.a_nkb1) {
+            // A read MN-major: 16 K' = two 8-row atoms (2 KiB) per instruction; the two 64-column
+            // halves of the tile lie 8 KiB apart
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              mma_f16_ss(d_tmem, make_smem_desc_sw128_mn(a_addr + k4 * 2048, TP_SLICE_BYTES / 2, 1024),
+                         make_smem_desc_sw128(b_addr + k4 * 32), idesc_a_mn_major(idesc), (it | k4) != 0 ? 1u : 0u);
+          } else {
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)
             mma_f16_ss(d_tmem, make_smem_desc_sw128(a_addr + k4 * 32),
                        make_smem_desc_sw128(b_addr + k4 * 32), idesc, (it | k4) != 0 ? 1u : 0u);
+          }
           if (CL == 1) mma_commit(&bar_empty[stage]);
           else mma_commit_mcast(&bar_empty[stage], kMask);
           if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
@@ -585,8 +606,10 @@ int launch_gemm_tn(const GemmParams& p, cudaStream_t st) {
                 "gemm: bad shape M=%lld N=%lld nkb=%d nseg=%d", (long long)p.M, (long long)p.N, p.nkb, p.nseg);
   MCLST_REQUIRE(p.nseg == 1 || (p.a_lo && p.b_lo), MCLST_ERR_INVALID, "gemm: split needs lo parts");
   MCLST_REQUIRE(p.c || p.lse_part, MCLST_ERR_INVALID, "gemm: neither an output nor statistics requested");
-  MCLST_REQUIRE(p.a_nkb1 == 0 || (p.a_nkb1 > 0 && p.a_nkb1 < p.nkb && p.a2_hi && (p.nseg == 1 || p.a2_lo) && p.batch <= 1),
+  MCLST_REQUIRE(p.a_nkb1 == 0 || (p.a_nkb1 > 0 && p.a_nkb1 <= p.nkb && p.batch <= 1 &&
+                                  (p.a_nkb1 == p.nkb || (p.a2_hi && (p.nseg == 1 || p.a2_lo)))),
                 MCLST_ERR_INVALID, "gemm: bad concatenated A operand");
+  MCLST_REQUIRE(p.a1_mn == 0 || (p.a_nkb1 > 0 && p.a1_mn > 0), MCLST_ERR_INVALID, "gemm: transposed A needs a_nkb1");
   MCLST_REQUIRE(!p.lse_part || (!p.a_scale && !p.b_scale && !p.bias && p.act == 0 && p.batch <= 1),
                 MCLST_ERR_INVALID, "gemm: the fused row statistics take a plain alpha-scaled product");
   GemmParams q = p;

@@ -36,6 +36,10 @@ struct GemmParams {
   // with a_nkb1 blocks per row block), the remaining nkb - a_nkb1 from a2_hi / a2_lo.  0 = plain.
   const uint8_t *a2_hi, *a2_lo;
   int a_nkb1;
+  // a1_mn != 0: image 1 is consumed TRANSPOSED (MN-major descriptors): it is stored [K', M] with
+  // a1_mn = its K blocks per row block (its row-major width / 64); output row m then is image
+  // column m and the contraction runs over the image's rows.  Needs a_nkb1 > 0.
+  int a1_mn;
   // fused row log-sum-exp of the scaled product (loss): lse_part [2 * ceil(N/256)][lse_ld] receives
   // one (max, sum exp(x - max)) pair per row, tile column and 128-column half (-inf, 0 when that
   // half lies beyond N is NOT written: merge only the halves that exist); diag (nullable) [M]

@@ -324,7 +324,7 @@ constexpr int TG = 64;             // tile edge
 constexpr int TG_LD = TG + 1;
 constexpr int TG_SMEM = (3 * TG * TG_LD + 2 * 8 * TG) * 4;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 grad_tiles_kernel(const TileGradParams p) {
   const int tr = blockIdx.y, tc = blockIdx.x;
   if (tc < tr) return;                                   // the pair (tr, tc) also serves (tc, tr)
@@ -403,9 +403,11 @@ grad_tiles_kernel(const TileGradParams p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = g_rj[half * 8 + i];
       store_split(p.g1_hi, p.g1_lo, off, v);
+      if (p.g2_hi) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = g_jr[half * 8 + i];
-      store_split(p.g2_hi, p.g2_lo, off, v);
+        for (int i = 0; i < 8; ++i) v[i] = g_jr[half * 8 + i];
+        store_split(p.g2_hi, p.g2_lo, off, v);
+      }
       if (p.soft) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = h[half * 8 + i];
@@ -434,9 +436,11 @@ grad_tiles_kernel(const TileGradParams p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = sB[(rq + half * 8 + i) * TG_LD + j];      // dLg_jr as row j
       store_split(p.g1_hi, p.g1_lo, off, v);
+      if (p.g2_hi) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = sA[(rq + half * 8 + i) * TG_LD + j];      // dLg_rj as its transpose
-      store_split(p.g2_hi, p.g2_lo, off, v);
+        for (int i = 0; i < 8; ++i) v[i] = sA[(rq + half * 8 + i) * TG_LD + j];    // dLg_rj as its transpose
+        store_split(p.g2_hi, p.g2_lo, off, v);
+      }
       if (p.soft) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = sC[(rq + half * 8 + i) * TG_LD + j];
@@ -471,6 +475,13 @@ static bool lean_enabled() {
   const char* e = getenv("MCLST_LOSS_LEAN");
   return !(e && e[0] == '0');
 }
+// dI = dLg^T S + Gs I reads the dLg image TRANSPOSED (MN-major tcgen05 descriptors) instead of a
+// second, transposed copy of it: 4 of the 12 bytes per element the factor kernel writes.
+// MCLST_LOSS_MN=0 keeps the explicit copy (the tests compare the two).
+static bool mn_enabled() {
+  const char* e = getenv("MCLST_LOSS_MN");
+  return !(e && e[0] == '0');
+}
 
 static LossPlan plan_loss(void* ws, size_t cap, int B, int D, int soft, int want_grad, size_t budget,
                           int64_t rows_local) {
@@ -498,7 +509,7 @@ static LossPlan plan_loss(void* ws, size_t cap, int B, int D, int soft, int want
     L.XT_SI = take_operand(a, D, kx, true, true, 1);
     if (L.lean) {
       L.G1 = take_operand(a, R, L.B64, false, true, 1);
-      L.G2 = take_operand(a, R, L.B64, false, true, 1);
+      if (!mn_enabled()) L.G2 = take_operand(a, R, L.B64, false, true, 1);
       if (soft) L.Gs = take_operand(a, R, L.B64, false, true, 1);
     } else {
       L.GA = take_operand(a, R, kx, false, true, 1);
@@ -685,7 +696,13 @@ static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_em
       g.a_hi = L.G1.hi; g.a_lo = L.G1.lo; g.b_hi = L.XT_IS.hi; g.b_lo = L.XT_IS.lo;
       g.c = d_spot; g.ldc = ld_ds;
       if ((rc = launch_gemm_tn(g, st))) return rc;
-      g.a_hi = L.G2.hi; g.a_lo = L.G2.lo; g.b_hi = L.XT_SI.hi; g.b_lo = L.XT_SI.lo;
+      if (L.G2.hi) {
+        g.a_hi = L.G2.hi; g.a_lo = L.G2.lo;
+      } else {                               // dLg^T: the same image, read MN-major
+        g.a1_mn = L.G1.nkb;
+        g.a_nkb1 = L.G1.nkb;                 // (eye targets: image 1 is the whole K range)
+      }
+      g.b_hi = L.XT_SI.hi; g.b_lo = L.XT_SI.lo;
       g.c = d_image; g.ldc = ld_di;
       if ((rc = launch_gemm_tn(g, st))) return rc;
     } else if (d_spot) {

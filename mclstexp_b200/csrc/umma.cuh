@@ -185,6 +185,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
          (2ull << 61);
 }
 
+// Same atoms read MN-major (the operand TRANSPOSED): the 128-byte rows run along M/N (64 halves),
+// each of the 8 rows of an atom is one K index.  Canonical layout (cute/atom/mma_traits_sm100.hpp,
+// make_umma_desc<Major::MN>, SWIZZLE_128B, in 16-byte units): ((8,n),(8,k)):((1,LBO),(8,SBO)) --
+// LBO = byte distance between consecutive 64-element M/N blocks, SBO = between 8-row K groups.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                            uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t idesc_a_mn_major(uint32_t idesc) { return idesc | (1u << 15); }
+
 }  // namespace ptx
 
 // ---------------------------------------------------------------- packed operand layout
