@@ -170,6 +170,11 @@ int mclst_debug_similarity(const float* bank, int64_t n_bank, int64_t ld_bank,
                            float* out, int64_t ld_out, void* workspace, size_t workspace_bytes,
                            mclst_stream_t stream);
 
+/* Testing aid (host only): the rank j <= top_k of the sample value the speculative seed threshold
+ * starts from when a fraction `sampled_fraction` of the bank tiles is sampled: the smallest j with
+ * P(Binomial(top_k - 1, sampled_fraction) >= j) < 1e-7 (csrc/sim_topk.cu, spec_rank). */
+int mclst_debug_spec_rank(int top_k, double sampled_fraction);
+
 /* Testing aid (host only, no device needed): the work decomposition of the persistent top-k
  * kernel for query_blocks x bank_tiles on `lanes` SMs with at most max_slots candidate streams
  * per query block.  Writes up to max_units records {lane, query_block, tile_begin, tile_end,

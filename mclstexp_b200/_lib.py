@@ -92,6 +92,7 @@ def load() -> C.CDLL:
     lib.mclst_neighbor_distances.argtypes = [p, i64, i64, p, i64, i64, i32, p, i32, i64, i32, p, p]
     lib.mclst_weighted_gather.argtypes = [p, i64, i64, i32, i32, p, p, i64, i32, i64, p, p]
     f64 = C.c_double
+    lib.mclst_debug_spec_rank.argtypes = [i32, f64]
     lib.mclst_debug_lane_plan.argtypes = [i64, i64, i32, i32, p, i64, C.POINTER(i64), C.POINTER(i32)]
     lib.mclst_adam_coef_bytes.argtypes = [i32]
     lib.mclst_adam_coef_bytes.restype = sz

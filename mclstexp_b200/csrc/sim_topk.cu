@@ -1728,19 +1728,18 @@ static int launch_sim_topk_e(int epw, const SimParams& p, dim3 grid, cudaStream_
 // exact score found must lie above threshold + eps, else nothing dropped could have mattered is
 // NOT guaranteed and the query is recomputed by the exact path), so a bank whose order defeats the
 // binomial model costs time, never correctness.
-static int spec_rank(int k, double f) {
+int spec_rank(int k, double f) {
   if (!(f > 0.0) || f >= 0.5 || k < 8) return k;
   const int n = k - 1;
-  // tail[j] = P(X >= j), summed from the top
-  double pmf = 1.0;
-  for (int i = 0; i < n; ++i) pmf *= f;              // P(X = n)
+  // P(X >= j) summed from the top, every term from its logarithm (f^n underflows a double long
+  // before the terms that matter: k = 200, f = 0.03)
+  const double lf = log(f), l1f = log1p(-f), lgn = lgamma((double)n + 1.0);
   double tail = 0.0;
   int best = k;
   for (int j = n; j >= 1; --j) {
-    tail += pmf;                                       // now P(X >= j)
+    tail += exp(lgn - lgamma((double)j + 1.0) - lgamma((double)(n - j) + 1.0) + j * lf + (n - j) * l1f);
     if (tail < 1e-7) best = j;
     else break;
-    pmf *= (double)j / (double)(n - j + 1) * (1.0 - f) / f;   // P(X = j-1)
   }
   return std::max(4, std::min(best, k));
 }
@@ -1902,6 +1901,10 @@ int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64
 }
 
 }  // namespace mclst
+
+extern "C" int mclst_debug_spec_rank(int top_k, double sampled_fraction) {
+  return mclst::spec_rank(top_k, sampled_fraction);
+}
 
 extern "C" int mclst_debug_lane_plan(int64_t query_blocks, int64_t bank_tiles, int lanes, int max_slots,
                                      int* units, int64_t max_units, int64_t* n_units, int* slots) {

@@ -98,3 +98,21 @@ def test_lane_plan_covers_every_tile_once():
         assert (cover == 1).all(), (qt, tiles, lanes, max_slots)
         if tiles > 1000 and lanes == 148:
             assert load.max() <= 1.001 * qt * tiles / lanes + 1
+
+
+def test_speculative_seed_rank_is_the_binomial_tail():
+    """csrc/sim_topk.cu spec_rank: the speculative start threshold is the j-th largest sample value,
+    j = the smallest rank with P(Binomial(k - 1, f) >= j) < 1e-7 (never above k, never below 4)."""
+    from scipy.stats import binom
+    lib = _lib.load()
+    for k in (8, 50, 200, 600):
+        for f in (0.001, 128 / 3907, 1 / 24, 0.125, 0.3):
+            j = lib.mclst_debug_spec_rank(k, f)
+            assert 4 <= j <= k
+            tail = lambda jj: float(binom.sf(jj - 1, k - 1, f))          # P(X >= jj)
+            if j < k:
+                assert tail(j) < 1e-7
+            if j > 4:
+                assert tail(j - 1) >= 1e-7 or j == k
+    assert lib.mclst_debug_spec_rank(50, 0.6) == 50                      # sampling most of the bank: no speculation
+    assert lib.mclst_debug_spec_rank(5, 0.03) == 5                       # tiny k: none either
