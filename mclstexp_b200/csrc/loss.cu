@@ -161,7 +161,7 @@ __device__ __forceinline__ void store_split(uint8_t* hi, uint8_t* lo, size_t off
 // loads per 8 elements next to 6 vector loads of data).  Gradients of magnitude ~1/B are scaled
 // by 2B before the fp16 split (keeps them in fp16's normal range); the GEMM alpha undoes it.
 constexpr int GF_ROWS = 8;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 grad_factor_kernel(const GradParams p, int64_t rows_pad) {
   const int chunks = p.nkb_half * 8;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1659,12 +1659,13 @@ void tc_workspace(Arena& a, int64_t n_bank, int64_t n_query, int dim, int top_k,
   w.cand = a.take<uint2>((size_t)w.q_pad * w.SS * w.cap);
   w.cand_cnt = a.take<int>((size_t)w.q_pad * w.SS);
   w.fb_list = a.take<int>((size_t)n_query);
-  // seed pass: a strided sample of the bank tiles -- 1/24 of them, at most 128 (3.3 % of the main
-  // pass at 1M rows; a 125k-row shard of an 8-GPU run samples 20 tiles, 4 %, where a fixed 1/8 cost
-  // 12 %), at least 2k chunk maxima
+  // seed pass: a strided sample of the bank tiles -- 1/8 of them, at most 128 (3.3 % of the main
+  // pass at 1M rows, 6.5 % for a 500k-row shard).  A thinner sample was tried for shards (1/24):
+  // seed pass 1.41 -> 1.04 ms but main pass 13.5 -> 14.7 ms at 500k rows -- the looser start costs
+  // more than the sample saves.
   const int64_t tiles = w.n_pad / ST_BN;
   static const int seed_max = env_int("MCLST_SIM_SEED_TILES", 128);
-  int n_seed = (int)std::min<int64_t>(seed_max, std::max<int64_t>(tiles / 24, std::min<int64_t>(tiles / 8, (2 * top_k + 7) / 8)));
+  int n_seed = (int)std::min<int64_t>(seed_max, tiles / 8);
   static const int seed_env = env_int("MCLST_SIM_SEED", 1);
   if (!seed_env || n_seed * 8 < 2 * top_k) n_seed = 0;
   w.n_seed = n_seed;
