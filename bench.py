@@ -860,6 +860,7 @@ def main():
                          "N = pure bank sharding, 1 = pure query sharding")
     ap.add_argument("--full-loss-sweep", action="store_true", help="cfg5 sweep up to B=32768")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled-row parity check against the oracle")
+    ap.add_argument("--no-numa", action="store_true", help="N > 1: do not pin the rank to the CPUs next to its GPU")
     ap.add_argument("--loss-batch", type=int, default=32768, help="cfg5: batch the headline value is quoted on")
     ap.add_argument("--train-genes", type=int, default=1000, help="cfg2: spot_dim (1000 HVGs; 171 = real cSCC)")
     args = ap.parse_args()
@@ -904,6 +905,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         from mclstexp_b200 import distributed as mdist
+        # host buffers of this rank on its GPU's NUMA node (the end-to-end job is upload-bound)
+        config["numa_bound"] = bool(not args.no_numa and mdist.bind_to_gpu_cpus(local))
     peaks = load_peaks()
     N, Q, D, G, k = cfg["N"], cfg["Q"], cfg["D"], cfg["G"], cfg["k"]
 

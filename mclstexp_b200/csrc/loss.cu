@@ -465,7 +465,7 @@ struct LossPlan {
   // lean single-block path
   bool lean;
   PackedOperand G1, G2, Gs;        // [R, B64] each
-  float2 *part1, *part3, *partc;   // LSE partials: rows of P1 / P3 [2 * nt256][R], columns of P1 [chunks][B64]
+  float2 *part1, *part2, *part3, *partc;   // LSE partials: rows of P1 / P2 / P3 [2 * nt256][R], columns of P1 [chunks][B64]
   int nt256, cchunks;
 };
 
@@ -519,10 +519,11 @@ static LossPlan plan_loss(void* ws, size_t cap, int B, int D, int soft, int want
   L.P1 = a.take<float>((size_t)R * L.B64);
   L.P2 = L.lean ? nullptr : a.take<float>((size_t)R * L.B64);
   L.P3 = soft ? a.take<float>((size_t)R * L.B64) : nullptr;
-  if (L.lean) {
+  if (L.lean || L.nblocks == 1) {
     L.part1 = a.take<float2>((size_t)2 * L.nt256 * R);
     L.part3 = soft ? a.take<float2>((size_t)2 * L.nt256 * R) : nullptr;
-    L.partc = a.take<float2>((size_t)L.cchunks * L.B64);
+    if (L.lean) L.partc = a.take<float2>((size_t)L.cchunks * L.B64);
+    else L.part2 = a.take<float2>((size_t)2 * L.nt256 * R);
   }
   L.stats_ws = a.take<float>((size_t)MCLST_LOSS_STAT_ROWS * B);
   L.bytes = align_up(a.off, 256);
@@ -538,8 +539,10 @@ static size_t loss_budget() {
 }
 
 // rows [i0, i0+rows) of P1 = S I^T / T, P2 = I S^T / T, P3 = [I|S][I|S]^T * a
+// with_stats: the row log-sum-exp partials (and the diagonal of P1) come out of the product
+// epilogues (part1 / part2 / part3, rows indexed locally) instead of three sweeps over the products
 static int compute_blocks(const LossPlan& L, int64_t i0, int64_t rows, float inv_t, float a_scale,
-                          bool need_p2, cudaStream_t st) {
+                          bool need_p2, cudaStream_t st, bool with_stats = false) {
   const int nkbD = L.Sp.nkb;
   GemmParams g{};
   g.nseg = 3; g.batch = 1; g.M = rows; g.N = L.B; g.ldc = L.B64;
@@ -549,10 +552,13 @@ static int compute_blocks(const LossPlan& L, int64_t i0, int64_t rows, float inv
   g.nkb = nkbD;
   g.a_hi = L.Sp.hi + a_off; g.a_lo = L.Sp.lo + a_off; g.b_hi = L.Ip.hi; g.b_lo = L.Ip.lo;
   g.c = L.P1; g.alpha = inv_t;
+  if (with_stats) { g.lse_part = L.part1; g.lse_ld = L.R; g.diag = L.diag + i0; g.diag_offset = i0; }
   if ((rc = launch_gemm_tn(g, st))) return rc;
+  g.diag = nullptr;
   if (need_p2) {
     g.a_hi = L.Ip.hi + a_off; g.a_lo = L.Ip.lo + a_off; g.b_hi = L.Sp.hi; g.b_lo = L.Sp.lo;
     g.c = L.P2;
+    if (with_stats) g.lse_part = L.part2;
     if ((rc = launch_gemm_tn(g, st))) return rc;
   }
   if (L.soft) {
@@ -560,6 +566,7 @@ static int compute_blocks(const LossPlan& L, int64_t i0, int64_t rows, float inv
     g.nkb = L.ISp.nkb;
     g.a_hi = L.ISp.hi + a2; g.a_lo = L.ISp.lo + a2; g.b_hi = L.ISp.hi; g.b_lo = L.ISp.lo;
     g.c = L.P3; g.alpha = a_scale;
+    if (with_stats) g.lse_part = L.part3;
     if ((rc = launch_gemm_tn(g, st))) return rc;
   }
   return 0;
@@ -639,6 +646,17 @@ static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_em
       mj.j[1] = MergeJob{L.partc, L.cchunks, 1, L.cchunks, L.B64, L.cl, L.cl_lo, B};
       if (soft) mj.j[2] = MergeJob{L.part3, 2 * L.nt256, 128, B, L.R, L.za, L.za_lo, B};
       lse_merge_kernel<<<dim3((unsigned)ceil_div(B, 256), soft ? 3u : 2u), 256, 0, st>>>(mj);
+      MCLST_LAUNCH_CHECK();
+    } else if (L.nblocks == 1) {
+      // one block holds this call's rows (a rank's slice of a sharded batch): statistics out of the
+      // product epilogues, the transposed product P2 supplies the column statistics of the local rows
+      if ((rc = compute_blocks(L, row0, rows, inv_t, a_scale, true, st, true))) return rc;
+      prof_mark(st, "lse_merge");
+      MergeJobs mj{};
+      mj.j[0] = MergeJob{L.part1, 2 * L.nt256, 128, B, L.R, L.rl + row0, L.rl_lo + row0, (int)rows};
+      mj.j[1] = MergeJob{L.part2, 2 * L.nt256, 128, B, L.R, L.cl + row0, L.cl_lo + row0, (int)rows};
+      if (soft) mj.j[2] = MergeJob{L.part3, 2 * L.nt256, 128, B, L.R, L.za + row0, L.za_lo + row0, (int)rows};
+      lse_merge_kernel<<<dim3((unsigned)ceil_div(rows, 256), soft ? 3u : 2u), 256, 0, st>>>(mj);
       MCLST_LAUNCH_CHECK();
     } else
     for (int64_t b = 0; b < L.nblocks; ++b) {

@@ -31,8 +31,23 @@ import torch.distributed as dist
 from . import _lib
 from ._lib import WEIGHT_MODES, check, load, ptr, stream_ptr
 
-__all__ = ["shard_bounds", "BankShard", "CudaBackend", "retrieve_sharded", "contrastive_loss_sharded",
+__all__ = ["shard_bounds", "bind_to_gpu_cpus", "BankShard", "CudaBackend", "retrieve_sharded", "contrastive_loss_sharded",
            "RetrievalGrid", "make_retrieval_grid"]
+
+
+def bind_to_gpu_cpus(device_index: int) -> bool:
+    """Pin this process to the CPU cores next to its GPU (NVML's ideal affinity), so that the pinned
+    host buffers it allocates afterwards live on that GPU's NUMA node.  One process per GPU under
+    torchrun starts unbound; with all ranks' upload buffers on one socket the aggregate host-to-device
+    rate of an 8-GPU box stalled near 100-140 GB/s however many links were used.  Returns False when
+    NVML is not available (nothing changes)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(device_index))
+        return True
+    except Exception:
+        return False
 
 
 def shard_bounds(n: int, world: int) -> List[Tuple[int, int]]:
@@ -157,7 +172,7 @@ def _tc_eligible(shard: BankShard, k: int) -> bool:
 class _Block:
     """One query block of a sharded retrieval on its way through the pipeline."""
     __slots__ = ("q", "ws", "packed", "bounds", "w_bounds", "val", "idx", "dst", "g", "w_g", "expr", "emb",
-                 "w_out", "rows")
+                 "w_out", "rows", "a2a")
 
 
 def retrieve_sharded(shard: BankShard, query: torch.Tensor, top_k: int = 50, mode: str = "inv_sq_l2",
@@ -173,8 +188,9 @@ def retrieve_sharded(shard: BankShard, query: torch.Tensor, top_k: int = 50, mod
     Bank shards (CUDA backend): per query block  seed pass -> all-reduce of per-query bounds of the
     GLOBAL k-th best score (2 floats per query) -> candidate pass against that bound -> all-reduce
     (MAX) of the bounds the converged thresholds give -> exact re-rank of only the candidates that
-    can still win globally (short, padded lists) -> all-gather of the lists -> merge -> owner-only
-    partial sums -> reduce-scatter / all-reduce.  The queries
+    can still win globally (short, padded lists) -> all-to-all of the lists (every rank merges only
+    its own Q/R queries) -> all-gather of the merged lists -> owner-only partial sums ->
+    reduce-scatter / all-reduce.  The queries
     go in ``query_blocks`` blocks (default 2 when large) so that the collectives of one block run
     under the top-k kernels of the next."""
     backend = backend or CudaBackend()
@@ -194,9 +210,11 @@ def retrieve_sharded(shard: BankShard, query: torch.Tensor, top_k: int = 50, mod
         return idx, val, emb, expr
     rank = dist.get_rank(group)
     staged = isinstance(backend, CudaBackend) and _tc_eligible(shard, top_k) and Q > 0
-    nb = query_blocks if query_blocks else (2 if Q >= 8192 else 1)
+    nb = query_blocks if query_blocks else (2 if Q >= 32768 else 1)
     nb = max(1, min(nb, Q)) if Q else 1
-    scatter = scatter_output and dist.get_backend(group) == "nccl"
+    nccl = dist.get_backend(group) == "nccl"
+    scatter = scatter_output and nccl
+    a2a = nccl and isinstance(backend, CudaBackend)
     cuts = [Q * b // nb for b in range(nb + 1)]
     blocks: List[_Block] = []
     for b in range(nb):
@@ -241,23 +259,42 @@ def retrieve_sharded(shard: BankShard, query: torch.Tensor, top_k: int = 50, mod
         else:
             blk.val, blk.idx, blk.dst = backend.local_topk(shard, blk.q, top_k, p, need_dist)
         Qb = blk.q.shape[0]
-        # (similarity, distance, index) of every candidate in ONE collective: index as two float32 words
+        # (similarity, index, distance) of every candidate in ONE tensor: index as two float32 words
         parts = [blk.val.view(Qb, top_k, 1), blk.idx.view(torch.float32).view(Qb, top_k, 2)]
         if need_dist:
             parts.append(blk.dst.view(Qb, top_k, 1))
-        blk.g, blk.w_g = _all_gather_cat(torch.cat(parts, dim=2), group, async_op=True)
+        cand = torch.cat(parts, dim=2)
+        if a2a and Qb % world == 0:
+            # all-to-all: rank r receives every shard's candidates for ITS Qb/R queries only and merges
+            # those (1/R of the merge work, (R-1)/R x 1/R of the all-gather's bytes)
+            blk.g = torch.empty_like(cand)
+            blk.w_g = dist.all_to_all_single(blk.g, cand, group=group, async_op=True)
+            blk.a2a = True
+        else:
+            blk.g, blk.w_g = _all_gather_cat(cand, group, async_op=True)
+            blk.a2a = False
     # -- stage 4: merge, weights, owner-only partial sums (+ reduction in flight)
     if shard.expr_ready is not None:
         torch.cuda.current_stream(shard.expression_key.device).wait_event(shard.expr_ready)
     for blk in blocks:
         blk.w_g.wait()
         Qb = blk.q.shape[0]
-        g = blk.g.view(world, Qb, top_k, -1)
+        Qm = Qb // world if blk.a2a else Qb                       # queries this rank merges
+        g = blk.g.view(world, Qm, top_k, -1)
         vals = g[..., 0].contiguous()
-        idxs = g[..., 1:3].contiguous().view(torch.int64).view(world, Qb, top_k)
+        idxs = g[..., 1:3].contiguous().view(torch.int64).view(world, Qm, top_k)
         dsts = g[..., 3].contiguous() if need_dist else None
-        blk.val, blk.idx, blk.dst = backend.merge(vals, idxs, dsts, top_k)
-        w = backend.weights(blk.dst, blk.val, mode)
+        val, idx, dst = backend.merge(vals, idxs, dsts, top_k)
+        w = backend.weights(dst, val, mode)
+        if blk.a2a:
+            # the merged lists of every rank's slice, so that each owner can add up its winners
+            m = torch.cat([val.view(Qm, top_k, 1), idx.view(torch.float32).view(Qm, top_k, 2), w.view(Qm, top_k, 1)], 2)
+            mg, _ = _all_gather_cat(m, group)
+            mg = mg.view(Qb, top_k, 4)
+            val = mg[..., 0].contiguous()
+            idx = mg[..., 1:3].contiguous().view(torch.int64).view(Qb, top_k)
+            w = mg[..., 3].contiguous()
+        blk.val, blk.idx = val, idx
         part = backend.partial_average(shard.expression_key, shard.index_offset, blk.idx, w)
         if want_emb:
             part = torch.cat([part, backend.partial_average(shard.spot_key, shard.index_offset, blk.idx, w)], dim=1)

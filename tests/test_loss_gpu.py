@@ -58,11 +58,13 @@ def test_loss_shapes(B, D, T, scale_in, targets):
     _check(S, I, T, targets, "div")
 
 
-@pytest.mark.parametrize("B,mb", [(700, 3), (4096, 64)])
+@pytest.mark.parametrize("B,mb", [(700, 3), (4096, 64), (1300, 0)])
 @pytest.mark.parametrize("targets", ["eye", "soft"])
 def test_loss_row_blocked_equals_single_block(targets, B, mb):
-    """Force several row blocks (the streaming path a small scratch budget selects) and compare with
-    the float64 closed form: 3 MiB -> 128-row blocks at B=700; 64 MiB -> 512-row blocks at B=4096."""
+    """The general pipeline (what a rank of a row-sharded batch runs): several row blocks forced by a
+    small scratch budget (3 MiB -> 128-row blocks at B=700; 64 MiB -> 512-row blocks at B=4096), or
+    one block with the lean whole-batch path switched off (mb = 0: statistics from the product
+    epilogues + the transposed product), against the float64 closed form."""
     import subprocess, sys, os
     code = f"""
 import sys, torch
@@ -80,7 +82,7 @@ assert_grad_close(St.grad, dS64, 1e-3, name='dS')
 assert_grad_close(It.grad, dI64, 1e-3, name='dI')
 print('ok')
 """
-    env = dict(os.environ, MCLST_LOSS_SCRATCH_MB=str(mb))
+    env = dict(os.environ, MCLST_LOSS_SCRATCH_MB=str(mb)) if mb else dict(os.environ, MCLST_LOSS_LEAN="0")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
