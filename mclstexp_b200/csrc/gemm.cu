@@ -75,6 +75,44 @@ pack_plain_block(const float* __restrict__ x, int64_t rows, int64_t cols, int64_
   const int64_t r = (int64_t)bx * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows_pad) return;
   float inv = 1.f;
+  if (inv_scale && nkb_mine <= 16 && kb_offset == 0) {
+    // the whole row in registers (K <= 1024): ONE round trip to memory instead of eight dependent
+    // ones (max scan, then chunk by chunk) -- the pack of a training-step operand is pure latency
+    float v[4][8];
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = lane + 32 * j;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t k = (int64_t)c * 8 + i;
+        v[j][i] = (r < rows && k < cols) ? __ldg(x + r * ld + k) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[j][i]));
+    amax = warp_max(amax);
+    scale *= pow2_scale(amax, &inv);
+    if (lane == 0) inv_scale[(size_t)bz * rows_pad + r] = inv;
+    const int nchunks = nkb_mine * 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = lane + 32 * j;
+      if (c < nchunks) {
+        float w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = v[j][i] * scale;
+        uint4 h, l;
+        split8(w, &h, &l);
+        const size_t off = tilepack_chunk_offset(r, c, nkb_total);
+        *reinterpret_cast<uint4*>(hi + off) = h;
+        if (lo) *reinterpret_cast<uint4*>(lo + off) = l;
+      }
+    }
+    return;
+  }
   if (inv_scale) {
     float amax = 0.f;
     if (r < rows) {
@@ -141,6 +179,46 @@ pack_trans_block(const float* __restrict__ x, int64_t rows, int64_t cols, int64_
   const int cgroup = threadIdx.x >> 5;                                  // chunk lane
   const int ngroups = blockDim.x >> 5;                                  // 8 (y-split grid) or 32 (self-scaling)
   float inv = 1.f;
+  if (inv_scale && nkb_mine <= 16 && kb_offset == 0 && ngroups == 32 && ny == 1) {
+    // the thread's four chunks (32 input rows of its column) in registers: one round trip
+    float v[4][8];
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = cgroup + 32 * j;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t k = (int64_t)c * 8 + i;
+        v[j][i] = (r < cols && k < rows) ? __ldg(x + k * ld + r) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[j][i]));
+    s_amax[cgroup][lane] = amax;
+    __syncthreads();
+    for (int g = 0; g < 32; ++g) amax = fmaxf(amax, s_amax[g][lane]);
+    scale *= pow2_scale(amax, &inv);
+    if (cgroup == 0 && r < out_rows_pad) inv_scale[(size_t)bz * out_rows_pad + r] = inv;
+    if (r >= out_rows_pad) return;
+    const int nchunks = nkb_mine * 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = cgroup + 32 * j;
+      if (c < nchunks) {
+        float w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = v[j][i] * scale;
+        uint4 h, l;
+        split8(w, &h, &l);
+        const size_t off = tilepack_chunk_offset(r, c, nkb_total);
+        *reinterpret_cast<uint4*>(hi + off) = h;
+        if (lo) *reinterpret_cast<uint4*>(lo + off) = l;
+      }
+    }
+    return;
+  }
   if (inv_scale) {
     float amax = 0.f;
     if (r < cols) {
@@ -313,6 +391,15 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_tn_kernel(const GemmParams p) {
   static_assert(BN == 256 || (BN == 128 && CL == 1), "tile widths: 256, or 128 without B sharing");
   constexpr int STAGE_TX = (1 + BN / 128) * TP_SLICE_BYTES;
+  // The half-width kernel serves the small problems, and those are L2-bound, not tensor-bound: 96
+  // CTAs re-streaming 32 KiB per 256 MMA cycles ask L2 for > 20 TB/s (CUPTI timeline of the graphed
+  // training step: 26 us per product where the MMAs need 7).  It therefore loads the hi AND lo slice
+  // of both operands ONCE per K block (64 KiB stage, 3 stages) and issues all three split products
+  // from them, instead of streaming a 32 KiB stage per (segment, K block): a third less L2 traffic.
+  constexpr bool FUSE = BN == 128;
+  constexpr int NSTAGE = FUSE ? 3 : GM_STAGES;
+  constexpr int STAGE_BYTES = FUSE ? 4 * TP_SLICE_BYTES : GM_STAGE_BYTES;
+  static_assert(NSTAGE * STAGE_BYTES == GM_STAGES * GM_STAGE_BYTES, "same shared-memory footprint");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + GM_STAGES * GM_STAGE_BYTES);
@@ -353,6 +440,22 @@ gemm_tn_kernel(const GemmParams p) {
         const uint8_t* a_lo = p.a_lo ? p.a_lo + (size_t)z * p.a_batch_bytes : nullptr;
         const uint8_t* b_hi = p.b_hi + (size_t)z * p.b_batch_bytes;
         const uint8_t* b_lo = p.b_lo ? p.b_lo + (size_t)z * p.b_batch_bytes : nullptr;
+        if (FUSE) {
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&bar_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&bar_full[stage], (p.nseg == 3 ? 4 : 2) * TP_SLICE_BYTES);
+            uint8_t* dst = smem + stage * STAGE_BYTES;
+            const size_t ao = ((size_t)mb * nkb + kb) * TP_SLICE_BYTES, bo = ((size_t)nb * nkb + kb) * TP_SLICE_BYTES;
+            bulk_g2s(dst, a_hi + ao, TP_SLICE_BYTES, &bar_full[stage]);
+            bulk_g2s(dst + 2 * TP_SLICE_BYTES, b_hi + bo, TP_SLICE_BYTES, &bar_full[stage]);
+            if (p.nseg == 3) {
+              bulk_g2s(dst + TP_SLICE_BYTES, a_lo + ao, TP_SLICE_BYTES, &bar_full[stage]);
+              bulk_g2s(dst + 3 * TP_SLICE_BYTES, b_lo + bo, TP_SLICE_BYTES, &bar_full[stage]);
+            }
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int it = 0; it < iters; ++it) {
           const int seg = it / nkb, kb = it - seg * nkb;
           // segment 0: hi*hi, 1: lo*hi, 2: hi*lo
@@ -410,6 +513,25 @@ gemm_tn_kernel(const GemmParams p) {
         mbar_wait(&bar_tempty[buf], ((n >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
+        if (FUSE) {
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&bar_full[stage], phase);
+            tc_fence_after();
+            const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
+            for (int seg = 0; seg < p.nseg; ++seg) {          // hi*hi, lo*hi, hi*lo from the same slices
+              const uint32_t a_addr = base + (seg == 1 ? TP_SLICE_BYTES : 0);
+              const uint32_t b_addr = base + 2 * TP_SLICE_BYTES + (seg == 2 ? TP_SLICE_BYTES : 0);
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                mma_f16_ss(d_tmem, make_smem_desc_sw128(a_addr + k4 * 32), make_smem_desc_sw128(b_addr + k4 * 32),
+                           idesc, (kb | seg | k4) != 0 ? 1u : 0u);
+            }
+            mma_commit(&bar_empty[stage]);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          mma_commit(&bar_tfull[buf]);
+          continue;
+        }
         for (int it = 0; it < iters; ++it) {
           mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
@@ -621,7 +743,7 @@ int launch_gemm_tn(const GemmParams& p, cudaStream_t st) {
   const bool pair = force == 2 || (force == 0 && p.M > GM_BM && tiles >= 2 * (int64_t)sm_count());
   if (pair) return launch_gemm_cl<2, 256>(q, st);
   // under-filled grid: half-width tiles (the fused row statistics are laid out for 256-wide tiles)
-  const bool narrow = !p.lse_part && tiles < (int64_t)sm_count();
+  const bool narrow = !p.lse_part && p.a_nkb1 == 0 && tiles < (int64_t)sm_count();
   return narrow ? launch_gemm_cl<1, 128>(q, st) : launch_gemm_cl<1, 256>(q, st);
 }
 
