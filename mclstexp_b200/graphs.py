@@ -21,7 +21,9 @@ class GraphedTrainStep:
     loss tensor of an earlier eager step before constructing this (a live autograd graph
     created on the default stream invalidates the capture)."""
 
-    def __init__(self, model: torch.nn.Module, example_batch: Dict[str, torch.Tensor], warmup: int = 3):
+    def __init__(self, model: torch.nn.Module, example_batch: Dict[str, torch.Tensor], warmup: int = 3,
+                 defer_weight_grads: bool = True):
+        from .model import deferred_weight_grads
         # position tables owned by optim.LazyEmbeddingAdam (TrainOptimizer): the captured forward
         # contains their row catch-up (which follows the optimiser's device-side step counter) and the
         # captured backward leaves (position, d_out) in static buffers for ``optimizer.step()``
@@ -31,7 +33,9 @@ class GraphedTrainStep:
         self.table_rows = getattr(getattr(model, "x_embed", None), "num_embeddings", None)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):                      # warm-up off the default stream
+        # weight / bias gradients of the Linear layers leave the dX chain: a parallel branch of the
+        # graph that joins at the end of the backward pass (model.deferred_weight_grads)
+        with torch.cuda.stream(side), deferred_weight_grads(defer_weight_grads):   # warm-up off the default stream
             for _ in range(warmup):
                 for p in model.parameters():
                     p.grad = None
@@ -45,7 +49,7 @@ class GraphedTrainStep:
             p.grad = None                  # buffers from the graph's pool: every replay overwrites them
         if self.lazy is not None:
             self.lazy.zero_grad()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph), deferred_weight_grads(defer_weight_grads):
             self.loss = model(self.static)
             self.loss.backward()
         self._lazy_pending = self.lazy._pending if self.lazy is not None else None

@@ -34,12 +34,99 @@ from .loss import contrastive_loss
 __all__ = ["PreNorm", "FeedForward", "Attention", "attn_block", "ProjectionHead", "ImageEncoder",
            "ImageEncoder_Resnet", "ImageEncoder_VIT", "ImageEncdoer_res18", "ImageEncdoer_res101",
            "mclSTExp_MLP", "mclSTExp_Attention", "linear", "gelu", "layer_norm", "attention_core",
-           "embed_add"]
+           "embed_add", "deferred_weight_grads"]
+
+
+PARALLEL_BRANCHES = os.environ.get("MCLST_PARALLEL_BRANCHES", "1") != "0"
+_branch_streams: dict = {}
+
+
+_attn_streams: dict = {}
+
+
+def _attn_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """Side stream of the attention backward (distinct from the image-branch stream: that one may be
+    the CURRENT stream of a backward pass)."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    if key not in _attn_streams:
+        _attn_streams[key] = torch.cuda.Stream(device=dev)
+    return _attn_streams[key]
+
+
+def _branch_stream(dev: torch.device) -> "torch.cuda.Stream":
+    if dev.index not in _branch_streams:
+        _branch_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return _branch_streams[dev.index]
 
 
 # ----------------------------------------------------------------------------- primitives
 def _c2d(t: torch.Tensor) -> torch.Tensor:
     return t if (t.dim() == 2 and t.stride(1) == 1) else t.contiguous()
+
+
+# ---- weight gradients off the critical path -------------------------------------------------
+# dX is the only product of a Linear's backward that the rest of the backward pass waits for; dW
+# (and db) are leaves.  With ``deferred_weight_grads()`` active the backward launches them on a side
+# stream that forks from the current one, writes them straight into ``weight.grad`` / ``bias.grad``
+# (allocate-or-accumulate, what AccumulateGrad would do) and the two streams join once, when the
+# backward pass ends (autograd's end-of-pass callback).  A third of the step's products then run
+# next to the dX chain instead of in it -- at B = 1024 every product fills well under half of the
+# 148 SMs.  Inside a CUDA-graph capture the fork/join becomes two parallel branches of the graph
+# (``graphs.GraphedTrainStep`` turns this on).  Off by default: ``torch.autograd.grad`` on the
+# weights and gradient hooks on them need the ordinary route.
+class _WGrad:
+    on = False
+    state: dict = {}          # device index -> [side stream, tensors kept alive until the join, armed]
+
+
+class deferred_weight_grads:
+    """Context manager: Linear weight/bias gradients of every ``backward()`` inside it are computed
+    on a side stream and written directly into ``.grad``."""
+
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        self.prev, _WGrad.on = _WGrad.on, self.on
+        return self
+
+    def __exit__(self, *exc):
+        _WGrad.on = self.prev
+        return False
+
+
+def _wgrad_join(dev_index: int) -> None:
+    st = _WGrad.state[dev_index]
+    torch.cuda.current_stream(torch.device("cuda", dev_index)).wait_stream(st[0])
+    st[1].clear()
+    st[2] = False
+
+
+def _wgrad_submit(weight, bias, dy, x) -> None:
+    dev = dy.device
+    st = _WGrad.state.get(dev.index)
+    if st is None:
+        st = _WGrad.state[dev.index] = [torch.cuda.Stream(device=dev), [], False]
+    side = st[0]
+    if not st[2]:                                    # first product of this backward pass: fork
+        st[2] = True
+        side.wait_stream(torch.cuda.current_stream(dev))
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: _wgrad_join(dev.index))
+    else:
+        side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        if weight is not None:
+            if weight.grad is None:
+                weight.grad = ops.matmul(dy, x, a_trans=True, b_trans=True)
+            else:
+                ops.matmul(dy, x, a_trans=True, b_trans=True, out=weight.grad, residual=weight.grad)
+        if bias is not None:
+            g = col_sum(dy)
+            if bias.grad is None:
+                bias.grad = g
+            else:
+                bias.grad.add_(g)
+    st[1].append((dy, x))          # freed on the main stream only after the join
 
 
 class _Linear(torch.autograd.Function):
@@ -52,6 +139,8 @@ class _Linear(torch.autograd.Function):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
+        # the leaf objects themselves (``.grad`` is written directly when weight gradients are deferred)
+        ctx.leaves = (weight if weight.is_leaf else None, bias if (bias is not None and bias.is_leaf) else None)
         return y
 
     @staticmethod
@@ -61,6 +150,12 @@ class _Linear(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = ops.matmul(dy, weight, b_trans=True)               # [M,out] x [out,in]
+        wl, bl = ctx.leaves
+        want_w = ctx.needs_input_grad[1]
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if _WGrad.on and (not want_w or wl is not None) and (not want_b or bl is not None) and (want_w or want_b):
+            _wgrad_submit(wl if want_w else None, bl if want_b else None, dy, x)
+            return dx, None, None, (dy if ctx.has_res else None)
         if ctx.needs_input_grad[1]:
             dw = ops.matmul(dy, x, a_trans=True, b_trans=True)      # dY^T X -> [out,in]
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -209,6 +304,8 @@ class _AttentionCore(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         dq, dk, dv = (dqkv[:, i * inner:(i + 1) * inner].view(n, heads, dh).permute(1, 0, 2) for i in range(3))
         blocks = [(0, n)] if R == 0 else [(r0, min(n, r0 + R)) for r0 in range(0, n, R)]
+        cur = torch.cuda.current_stream(qkv.device)
+        side = _attn_stream(qkv.device)
         for b, (r0, r1) in enumerate(blocks):
             if R == 0:
                 probs = ctx.saved_tensors[1]
@@ -216,15 +313,22 @@ class _AttentionCore(torch.autograd.Function):
                 probs = ops.matmul(q[:, r0:r1], k, alpha=scale)
                 _softmax_rows_(probs)
             acc = None if b == 0 else True                           # dK / dV accumulate over the row blocks
-            ops.matmul(probs, do[:, r0:r1], a_trans=True, b_trans=True, out=dv,
-                       residual=dv if acc else None)                 # P^T dO
+            # dV and dK hang off the dP -> dS -> dQ chain: they go on the branch stream and join
+            # before dqkv is handed back (two of the four products leave the critical path)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                ops.matmul(probs, do[:, r0:r1], a_trans=True, b_trans=True, out=dv,
+                           residual=dv if acc else None)             # P^T dO
             ds = ops.matmul(do[:, r0:r1], v)                         # dP = dO V^T
             with torch.cuda.device(qkv.device):
                 check(load().mclst_softmax_backward(ptr(probs), ptr(ds), n, heads * (r1 - r0), n, stream_ptr()),
                       "softmax_backward")
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                ops.matmul(ds, q[:, r0:r1], a_trans=True, b_trans=True, alpha=scale, out=dk,
+                           residual=dk if acc else None)             # dS^T Q
             ops.matmul(ds, k, b_trans=True, alpha=scale, out=dq[:, r0:r1])       # dS K
-            ops.matmul(ds, q[:, r0:r1], a_trans=True, b_trans=True, alpha=scale, out=dk,
-                       residual=dk if acc else None)                 # dS^T Q
+            cur.wait_stream(side)                                    # (probs / ds die after the join)
             del probs, ds
         return dqkv, None, None
 
@@ -544,8 +648,23 @@ class mclSTExp_Attention(nn.Module):
         return h.squeeze(dim=0)
 
     def forward(self, batch):
-        image_features = self.image_encoder(batch["image"])
-        image_embeddings = self.image_projection(image_features)
-        spot_embeddings = self.embed_spots(batch["expression"], batch["position"])
+        image = batch["image"]
+        if PARALLEL_BRANCHES and image.is_cuda:
+            # the image branch (CNN + projection head) and the spot branch (position embeddings,
+            # attention blocks, projection head) share nothing before the loss: they run on two
+            # streams, forward AND backward (autograd replays each op on its forward stream)
+            dev = image.device
+            cur = torch.cuda.current_stream(dev)
+            side = _branch_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                image_embeddings = self.image_projection(self.image_encoder(image))
+            spot_embeddings = self.embed_spots(batch["expression"], batch["position"])
+            cur.wait_stream(side)
+            image_embeddings.record_stream(cur)
+        else:
+            image_features = self.image_encoder(image)
+            image_embeddings = self.image_projection(image_features)
+            spot_embeddings = self.embed_spots(batch["expression"], batch["position"])
         return contrastive_loss(spot_embeddings, image_embeddings, self.temperature, self.targets,
                                 self.soft_scale)

@@ -16,7 +16,7 @@ g = torch.Generator(device="cuda"); g.manual_seed(7)
 batch = {"image": torch.randn(1024, 1024, generator=g, device="cuda"),
          "expression": torch.rand(1024, G, generator=g, device="cuda"),
          "position": torch.randint(0, 64, (1024, 2), generator=g, device="cuda").float()}
-step = GraphedTrainStep(net, batch)
+step = GraphedTrainStep(net, batch, defer_weight_grads=os.environ.get("DEFER", "1") != "0")
 for _ in range(5):
     step(batch)
 torch.cuda.synchronize()
@@ -32,6 +32,11 @@ busy = sum(e.time_range.end - e.time_range.start for e in ev)
 gaps = [ev[i + 1].time_range.start - ev[i].time_range.end for i in range(len(ev) - 1)]
 print(f"kernels {len(ev)}  span {(t1 - t0):.1f} us  sum of kernel durations {busy:.1f} us  "
       f"sum of positive gaps {sum(x for x in gaps if x > 0):.1f} us  median gap {sorted(gaps)[len(gaps)//2]:.2f} us")
+if os.environ.get("DUMP"):
+    with open(os.environ["DUMP"], "w") as f:
+        for e in ev:
+            f.write(f"{e.time_range.start - t0:9.1f} {e.time_range.end - e.time_range.start:8.2f}  "
+                    f"{e.name.split('(')[0].replace('void ', '').replace('mclst::', '')[:70]}\n")
 agg = collections.OrderedDict()
 for e in ev:
     k = e.name.split("(")[0].replace("void ", "").replace("mclst::", "")[:60]
