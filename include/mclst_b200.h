@@ -292,6 +292,12 @@ int mclst_embed_add(const float* expression, int64_t ld_e, const float* position
 int mclst_embed_add_backward(const float* d_out, int64_t ld_d, const float* position, int64_t ld_p,
                              int table_rows, int batch, int genes, float* d_x_table,
                              float* d_y_table, mclst_stream_t stream);
+/* Same scatter-add WITHOUT the zero fill: the rows are added into whatever d_x_table / d_y_table
+ * hold (gradient accumulation; or buffers the caller zero-filled earlier, off the critical path --
+ * the fill of two [65536, genes] tables is 0.5 GB of writes that depend on nothing). */
+int mclst_embed_add_backward_accumulate(const float* d_out, int64_t ld_d, const float* position,
+                                        int64_t ld_p, int table_rows, int batch, int genes,
+                                        float* d_x_table, float* d_y_table, mclst_stream_t stream);
 
 /* nn.LayerNorm over the last dimension (model.py:13, :159): biased variance, eps inside the
  * square root; mean / rstd [rows] are kept for the backward. */

@@ -283,6 +283,22 @@ extern "C" int mclst_embed_add_backward(const float* d_out, int64_t ld_d, const 
   return 0;
 }
 
+extern "C" int mclst_embed_add_backward_accumulate(const float* d_out, int64_t ld_d, const float* position,
+                                                   int64_t ld_p, int table_rows, int batch, int genes,
+                                                   float* d_x_table, float* d_y_table,
+                                                   mclst_stream_t stream) {
+  MCLST_REQUIRE(d_out && position && d_x_table && d_y_table, MCLST_ERR_INVALID,
+                "embed_add_backward_accumulate: null pointer");
+  (void)table_rows;
+  if (batch == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_mark(st, "embed_scatter");
+  embed_scatter_kernel<<<batch, EN_THREADS, 0, st>>>(d_out, ld_d, position, ld_p, genes, d_x_table,
+                                                    d_y_table);
+  MCLST_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int mclst_layernorm_forward(const float* x, int64_t ld_x, const float* gamma,
                                        const float* beta, int64_t rows, int cols, float eps,
                                        float* y, int64_t ld_y, float* mean, float* rstd,

@@ -791,6 +791,23 @@ extern "C" int mclst_matmul(const float* A, int64_t lda, int a_trans, int64_t a_
   MCLST_REQUIRE(A && B && C && workspace, MCLST_ERR_INVALID, "matmul: null pointer");
   MCLST_REQUIRE(M > 0 && N > 0 && K > 0 && batch >= 1, MCLST_ERR_INVALID, "matmul: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
+  // Two fp32-accurate routes.  The packed fp16 hi/lo path below pays a pack launch that reads and
+  // writes both operands once before the product starts; the 3xTF32 kernel (gemm_tf32.cu) splits
+  // inside the K loop, straight from the row-major tensors, at a lower MMA rate.  Measured inside
+  // CUDA-graph replays on B200 (tools/gemm_bench.py, us: in-kernel split vs pack + product):
+  //   [1024,256] x [256,256]^T            12.7 vs 18.4   short K: the pack is pure overhead
+  //   [8,1024,1024] x [8,1024,64] (P V)   29.2 vs 45.7   a large batched operand used once
+  //   [1024,1000] x [1000,1000]^T         28.0 vs 28.5   tie -> packed (fewer resident CTAs)
+  //   [8,1024,64] x [8,1024,64]^T (Q K^T) 51.7 vs 36.9   output-bound: the packed path's epilogue
+  const bool short_k = K <= 256 && (int64_t)M * N * batch <= (1 << 20);
+  const bool batched_long = batch > 1 && K >= 512;
+  if (precise && (short_k || batched_long) &&
+      gemm_tf32x3_aligned(A, lda, a_trans, a_batch_stride, B, ldb, b_trans, b_batch_stride, K)) {
+    const int rc = launch_gemm_tf32x3(A, lda, a_trans, a_batch_stride, B, ldb, b_trans, b_batch_stride, C, ldc,
+                                      c_batch_stride, M, N, K, batch, alpha, bias, act, residual, st);
+    prof_mark(st, "end");
+    return rc;
+  }
   Arena a(workspace, workspace_bytes);
   PackedOperand pa = take_operand(a, M, K, false, true, batch, true);
   PackedOperand pb = take_operand(a, N, K, true, true, batch, true);

@@ -66,5 +66,13 @@ int launch_pack_split(const float* x, int64_t rows, int64_t cols, int64_t ld, bo
 // atomicMax of max|x| (as float bits) into *out (zeroed by the caller)
 int launch_amax_bits(const float* x, int64_t rows, int64_t cols, int64_t ld, uint32_t* out, cudaStream_t st);
 int launch_gemm_tn(const GemmParams& p, cudaStream_t st);
+// C_z = act(alpha * op(A_z) op(B_z)^T + bias) + residual straight from row-major fp32 tensors:
+// 3xTF32 split inside the kernel (gemm_tf32.cu); *_trans = 1: the operand is stored [K, rows].
+bool gemm_tf32x3_aligned(const float* A, int64_t lda, int a_trans, int64_t a_batch, const float* B, int64_t ldb,
+                         int b_trans, int64_t b_batch, int64_t K);
+int launch_gemm_tf32x3(const float* A, int64_t lda, int a_trans, int64_t a_batch, const float* B, int64_t ldb,
+                       int b_trans, int64_t b_batch, float* C, int64_t ldc, int64_t c_batch, int64_t M,
+                       int64_t N, int64_t K, int batch, float alpha, const float* bias, int act,
+                       const float* residual, cudaStream_t st);
 
 }  // namespace mclst

@@ -38,6 +38,7 @@ __all__ = ["PreNorm", "FeedForward", "Attention", "attn_block", "ProjectionHead"
 
 
 PARALLEL_BRANCHES = os.environ.get("MCLST_PARALLEL_BRANCHES", "1") != "0"
+EARLY_TABLE_GRAD_FILL = os.environ.get("MCLST_EARLY_TABLE_GRAD_FILL", "1") != "0"
 _branch_streams: dict = {}
 
 
@@ -341,7 +342,7 @@ class _EmbedAdd(torch.autograd.Function):
     """expression + x_embed[long(pos[:,0])] + y_embed[long(pos[:,1])]  (model.py:230-235)."""
 
     @staticmethod
-    def forward(ctx, expression, position, x_table, y_table):
+    def forward(ctx, expression, position, x_table, y_table, dense_grads=True):
         require_cuda(expression, position, x_table, y_table)
         expression = _c2d(expression.float())
         position = _c2d(position.float())
@@ -355,6 +356,19 @@ class _EmbedAdd(torch.autograd.Function):
         ctx.save_for_backward(position)
         ctx.table_rows = x_table.shape[0]
         ctx.err = err
+        ctx.zeroed = None
+        if EARLY_TABLE_GRAD_FILL and dense_grads and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]):
+            # the dense table gradients nn.Embedding + Adam(weight_decay) expect are 2 x [65536, G]
+            # of zeros plus B rows: the fill (0.5 GB of writes at G = 1000, ~90 us) depends on nothing,
+            # so it starts NOW on a side stream, under the whole forward and backward pass, instead of
+            # at the very end of the backward chain
+            dev = expression.device
+            side = _attn_stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                dwx = torch.zeros((ctx.table_rows, G), dtype=torch.float32, device=dev)
+                dwy = torch.zeros_like(dwx)
+                ctx.zeroed = (dwx, dwy, side.record_event())
         return out
 
     @staticmethod
@@ -368,13 +382,22 @@ class _EmbedAdd(torch.autograd.Function):
         B, G = d_out.shape
         dwx = dwy = None
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            dwx = torch.empty((ctx.table_rows, G), dtype=torch.float32, device=d_out.device)
-            dwy = torch.empty_like(dwx)
+            cur = torch.cuda.current_stream(d_out.device)
+            if ctx.zeroed is not None:
+                dwx, dwy, filled = ctx.zeroed
+                ctx.zeroed = None
+                cur.wait_event(filled)
+                dwx.record_stream(cur)
+                dwy.record_stream(cur)
+                fn, what = load().mclst_embed_add_backward_accumulate, "embed_add_backward_accumulate"
+            else:
+                dwx = torch.empty((ctx.table_rows, G), dtype=torch.float32, device=d_out.device)
+                dwy = torch.empty_like(dwx)
+                fn, what = load().mclst_embed_add_backward, "embed_add_backward"
             with torch.cuda.device(d_out.device):
-                check(load().mclst_embed_add_backward(ptr(d_out), d_out.stride(0), ptr(position),
-                                                      position.stride(0), ctx.table_rows, B, G, ptr(dwx),
-                                                      ptr(dwy), stream_ptr()), "embed_add_backward")
-        return (d_out if ctx.needs_input_grad[0] else None), None, dwx, dwy
+                check(fn(ptr(d_out), d_out.stride(0), ptr(position), position.stride(0), ctx.table_rows, B, G,
+                         ptr(dwx), ptr(dwy), stream_ptr()), what)
+        return (d_out if ctx.needs_input_grad[0] else None), None, dwx, dwy, None
 
 
 class _EmbedAddLazy(torch.autograd.Function):
@@ -383,7 +406,7 @@ class _EmbedAddLazy(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, expression, position, x_table, y_table, lazy):
-        out = _EmbedAdd.forward(ctx, expression, position, x_table, y_table)
+        out = _EmbedAdd.forward(ctx, expression, position, x_table, y_table, dense_grads=False)
         ctx.lazy = lazy
         return out
 
@@ -405,7 +428,7 @@ def embed_add(expression, position, x_table, y_table, check_range: bool = True):
         lazy.catch_up(_c2d(position.float()))
         if torch.is_grad_enabled() and (x_table.requires_grad or y_table.requires_grad):
             return _EmbedAddLazy.apply(expression, position, x_table, y_table, lazy)
-    out = _EmbedAdd.apply(expression, position, x_table, y_table)
+    out = _EmbedAdd.apply(expression, position, x_table, y_table, True)
     return out
 
 

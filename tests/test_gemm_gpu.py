@@ -122,3 +122,31 @@ def test_matmul_non_finite_inputs_propagate():
     assert not torch.isfinite(got[2]).any()          # inf * finite sums: inf or NaN, never a finite lie
     assert torch.isnan(got[:, 4]).all()
     assert torch.isfinite(got[[0, 1, 3]][:, [0, 1, 2, 3]]).all()
+
+
+@pytest.mark.parametrize("a_trans,b_trans", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K,nb", [(1024, 256, 256, 1), (130, 70, 36, 1), (3, 5, 4, 1), (257, 129, 200, 1),
+                                      (300, 64, 520, 8), (128, 40, 1024, 3)])
+def test_matmul_in_kernel_split_route(M, N, K, nb, a_trans, b_trans):
+    """Shapes mclst_matmul sends to the 3xTF32 kernel that splits inside the K loop (gemm_tf32.cu):
+    short contractions and large batched operands, every storage order, ragged tile edges, K not a
+    multiple of the 32-wide K block, with the full epilogue."""
+    g = torch.Generator().manual_seed(M + 3 * N + 5 * K + 7 * nb)
+    lead = (nb,) if nb > 1 else ()
+    a = torch.randn(lead + ((K, M) if a_trans else (M, K)), generator=g).cuda()
+    b = torch.randn(lead + ((K, N) if b_trans else (N, K)), generator=g).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    res = torch.randn(lead + (M, N), generator=g).cuda()
+    opa = a.transpose(-1, -2) if a_trans else a
+    opb = b.transpose(-1, -2) if b_trans else b
+    want = torch.nn.functional.gelu(0.25 * opa.double() @ opb.double().transpose(-1, -2) + bias.double()) + res.double()
+    got = ops.matmul(a, b, a_trans, b_trans, alpha=0.25, bias=bias, act="gelu", residual=res)
+    scale = (0.25 * opa.double() @ opb.double().transpose(-1, -2)).abs().max().item() + 1.0
+    # (K / 8 accumulating MMAs per pass, each rounding toward zero: 1.1e-3 absolute at K = 1024 on
+    # sums of magnitude 130 -- twice the packed fp16 route, whose MMAs take 16 K at a time)
+    assert (got.double() - want).abs().max().item() <= 6e-5 * scale
+    # in place: out aliases the residual (gradient accumulation into .grad)
+    acc = res.clone()
+    ops.matmul(a, b, a_trans, b_trans, out=acc, residual=acc)
+    want2 = opa.double() @ opb.double().transpose(-1, -2) + res.double()
+    assert (acc.double() - want2).abs().max().item() <= 6e-5 * 4 * scale

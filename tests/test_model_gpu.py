@@ -220,3 +220,56 @@ def test_attention_row_block_streaming_equals_dense(monkeypatch):
     (ref * w.double()).sum().backward()
     _close(out_s, ref.detach().cpu().numpy(), "streamed vs float64 output")
     _close(g_s, q64.grad.cpu().numpy(), "streamed vs float64 grad")
+
+
+def test_deferred_weight_grads_equal_autograd_route():
+    """model.deferred_weight_grads(): Linear weight / bias gradients computed on the side stream and
+    written straight into .grad (fresh and accumulating) equal the ordinary autograd route."""
+    import copy
+    from mclstexp_b200 import model as mm
+    torch.manual_seed(3)
+    net = mm.mclSTExp_Attention("none", 1.0, 96, 171, 64, 4, 16, 2, targets="soft")
+    net.image_encoder = torch.nn.Identity()
+    net = net.cuda()
+    ref = copy.deepcopy(net)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    batch = {"image": torch.randn(200, 96, generator=g, device="cuda"),
+             "expression": torch.rand(200, 171, generator=g, device="cuda"),
+             "position": torch.randint(0, 64, (200, 2), generator=g, device="cuda").float()}
+    for rounds in (1, 2):                       # second round accumulates into existing .grad
+        ref(batch).backward()
+        with mm.deferred_weight_grads():
+            net(batch).backward()
+        torch.cuda.synchronize()
+        for (n, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+            assert p.grad is not None, n
+            assert torch.allclose(p.grad, q.grad, rtol=2e-4, atol=2e-5 * float(q.grad.abs().max()) + 1e-12), n
+
+
+def test_graphed_step_with_deferred_weight_grads_trains():
+    from mclstexp_b200 import model as mm
+    from mclstexp_b200.graphs import GraphedTrainStep
+    torch.manual_seed(5)
+    net = mm.mclSTExp_Attention("none", 1.0, 96, 128, 64, 4, 16, 1, targets="eye")
+    net.image_encoder = torch.nn.Identity()
+    net = net.cuda()
+    g = torch.Generator(device="cuda").manual_seed(6)
+    batch = {"image": torch.randn(256, 96, generator=g, device="cuda"),
+             "expression": torch.rand(256, 128, generator=g, device="cuda"),
+             "position": torch.randint(0, 64, (256, 2), generator=g, device="cuda").float()}
+    eager = net(batch)
+    eager.backward()
+    want = {n: p.grad.clone() for n, p in net.named_parameters()}
+    del eager
+    step = GraphedTrainStep(net, batch)
+    loss = step(batch)
+    torch.cuda.synchronize()
+    for n, p in net.named_parameters():
+        assert torch.allclose(p.grad, want[n], rtol=2e-4, atol=2e-5 * float(want[n].abs().max()) + 1e-12), n
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    l0 = float(loss)
+    for _ in range(5):
+        opt.zero_grad()
+        loss = step(batch)
+        opt.step()
+    assert float(loss) < l0

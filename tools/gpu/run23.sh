@@ -1,0 +1,5 @@
+for B in 64 128; do echo "== BN $B"; MCLST_TF32_BN=$B timeout 300 python tools/gemm_bench.py 2>&1 | tail -9; done > gpurun_out/gemm_bench_bn.log 2>&1
+cat gpurun_out/gemm_bench_bn.log
+MCLST_TF32_BN=128 timeout 600 python -m pytest tests/test_gemm_gpu.py -m gpu -q --tb=short 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gemm_gpu.py tests/test_model_gpu.py -m gpu -q --tb=short 2>&1 | tail -3
+DUMP=gpurun_out/tl_tf32.txt timeout 300 python tools/cfg2_graph_timeline.py 2>&1 | tail -17 > gpurun_out/tl_tf32.log; head -8 gpurun_out/tl_tf32.log
