@@ -863,6 +863,8 @@ def main():
     ap.add_argument("--no-numa", action="store_true", help="N > 1: do not pin the rank to the CPUs next to its GPU")
     ap.add_argument("--loss-batch", type=int, default=32768, help="cfg5: batch the headline value is quoted on")
     ap.add_argument("--train-genes", type=int, default=1000, help="cfg2: spot_dim (1000 HVGs; 171 = real cSCC)")
+    ap.add_argument("--queries", type=int, default=0, help="tuning: override the query count of the workload")
+    ap.add_argument("--query-blocks", type=int, default=0, help="tuning: query blocks of the sharded pipeline")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == "reference", "timing rules: W >= 3"
     rank = int(os.environ.get("RANK", 0))
@@ -873,6 +875,8 @@ def main():
     if args.workload == "cfg2":
         return main_train(args, rank, world, local)
     cfg = dict(synth.CONFIGS[args.workload])
+    if args.queries:
+        cfg["Q"] = args.queries
     config = {"workload": f"{args.workload}: N={cfg['N']} bank spots x Q={cfg['Q']} queries, D={cfg['D']}, "
                           f"top_k={cfg['k']}, G={cfg['G']} genes, weights={args.mode}, {args.flavour} embeddings",
               "l2": "inputs larger than L2 (126 MB)",
@@ -935,7 +939,8 @@ def main():
 
         def step():
             # every rank ends with its share of the finished rows (reduce-scatter)
-            return mdist.retrieve_sharded(shard, qry, k, args.mode, group=grid.group, scatter_output=True)
+            return mdist.retrieve_sharded(shard, qry, k, args.mode, group=grid.group, scatter_output=True,
+                                          query_blocks=args.query_blocks or None)
     else:
         def step():
             return retrieval.retrieve_device(bank, expr, qry, k, args.mode, want_emb=False,

@@ -183,6 +183,24 @@ int mclst_debug_spec_rank(int top_k, double sampled_fraction);
 int mclst_debug_lane_plan(int64_t query_blocks, int64_t bank_tiles, int lanes, int max_slots,
                           int* units, int64_t max_units, int64_t* n_units, int* slots);
 
+/* The whole fold-loop body (evel_her2st.py:174-187: find_matches, then the per-query loop) in ONE
+ * call on device-resident arrays: out_indices [n_query, top_k] int64, out_values (nullable unless
+ * MCLST_W_SIMILARITY) [n_query, top_k] float32, out_emb (nullable) [n_query, dim], out_expr
+ * [n_query, genes] (float32, or float64 when out_is_f64).  Query sets beyond eight rounds of the
+ * persistent top-k kernel (8 x 128 x SM count rows) go through in blocks, which bounds the workspace;
+ * the expression average of a block then runs on an internal side stream next to the top-k pass of
+ * the following block and is joined back into `stream` before the call returns (stream-ordered
+ * like every other entry).  flags: MCLST_FM_*; with
+ * MCLST_FM_BANK_PACKED the workspace already holds this bank's packed image
+ * (mclst_find_matches_pack_bank on a workspace of mclst_retrieve_workspace_bytes). */
+int mclst_retrieve_workspace_bytes(int64_t n_bank, int64_t n_query, int dim, int top_k, int flags,
+                                   size_t* bytes);
+int mclst_retrieve(const float* bank, int64_t n_bank, int64_t ld_bank, const void* expression_key,
+                   int64_t ld_expr, int genes, int expr_is_f64, const float* query, int64_t n_query,
+                   int64_t ld_query, int dim, int top_k, int weight_mode, int64_t* out_indices,
+                   float* out_values, void* out_emb, void* out_expr, int out_is_f64, void* workspace,
+                   size_t workspace_bytes, int flags, mclst_stream_t stream);
+
 /* The per-query loop evel_her2st.py:175-187 / evel_visium.py:194-205 /
  * evel_cscc.py:198-215 / BLEEP_inference.ipynb cell 5: weights from the UN-normalised
  * spot_key rows selected by `indices` and the query, then the weighted average of those

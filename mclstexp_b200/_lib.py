@@ -90,6 +90,9 @@ def load() -> C.CDLL:
                                             i32, p]
     lib.mclst_weighted_average.argtypes = [p, i64, i64, p, i64, i32, i32, p, i64, i64, i32, p, p, p,
                                            i32, i64, i32, p, p, i32, p]
+    lib.mclst_retrieve_workspace_bytes.argtypes = [i64, i64, i32, i32, i32, C.POINTER(sz)]
+    lib.mclst_retrieve.argtypes = [p, i64, i64, p, i64, i32, i32, p, i64, i64, i32, i32, i32, p, p, p, p, i32,
+                                   p, sz, i32, p]
     lib.mclst_neighbor_distances.argtypes = [p, i64, i64, p, i64, i64, i32, p, i32, i64, i32, p, p]
     lib.mclst_weighted_gather.argtypes = [p, i64, i64, i32, i32, p, p, i64, i32, i64, p, p]
     f64 = C.c_double

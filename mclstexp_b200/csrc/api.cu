@@ -1,4 +1,5 @@
 // extern "C" surface of libmclst_b200.so: error plumbing + retrieval orchestration.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -22,7 +23,7 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---- per-kernel event trace ------------------------------------------------------------
-struct ProfMark { cudaEvent_t ev; const char* name; };
+struct ProfMark { cudaEvent_t ev; const char* name; cudaStream_t st; };
 static bool g_prof_on = false;
 static std::vector<ProfMark> g_marks;
 static std::vector<cudaEvent_t> g_pool;
@@ -35,7 +36,7 @@ void prof_mark(cudaStream_t st, const char* name) {
   if (!g_pool.empty()) { ev = g_pool.back(); g_pool.pop_back(); }
   else if (cudaEventCreate(&ev) != cudaSuccess) return;
   cudaEventRecord(ev, st);
-  g_marks.push_back({ev, name});
+  g_marks.push_back({ev, name, st});
 }
 
 int sm_count() {
@@ -129,8 +130,12 @@ extern "C" int mclst_profile_collect(char* names_out, float* ms_out, int cap, in
   int cnt = 0;
   for (size_t i = 0; i + 1 < g_marks.size() && cnt < cap; ++i) {
     if (!strcmp(g_marks[i].name, "end")) continue;
+    // the next mark on the SAME stream closes this one (calls may interleave two streams)
+    size_t j = i + 1;
+    while (j < g_marks.size() && g_marks[j].st != g_marks[i].st) ++j;
+    if (j == g_marks.size()) continue;
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, g_marks[i].ev, g_marks[i + 1].ev) != cudaSuccess) continue;
+    if (cudaEventElapsedTime(&ms, g_marks[i].ev, g_marks[j].ev) != cudaSuccess) continue;
     strncpy(names_out + 48 * cnt, g_marks[i].name, 47);
     names_out[48 * cnt + 47] = 0;
     ms_out[cnt++] = ms;
@@ -350,6 +355,160 @@ extern "C" int mclst_find_matches_finish(const float* bank, int64_t n_bank, int6
   return find_matches_stages(4, bank, n_bank, ld_bank, query, n_query, ld_query, dim, top_k, index_offset,
                              out_indices, out_values, out_distances, dist_p, &sb, workspace,
                              workspace_bytes, flags, (cudaStream_t)stream);
+}
+
+// ---- the whole fold-loop body in one call ------------------------------------------------------
+// find_matches (+ neighbour distances) and the weighted expression average.  Very large query
+// sets go through in blocks (bounded workspace): the candidate pass, re-rank and exact fallback of
+// block b run on `stream`, the HBM-bound average of block b on an internal side stream, so that it
+// fills whatever the candidate pass of block b + 1 leaves free, and is joined back at the end.
+namespace mclst {
+struct SideStream {
+  cudaStream_t st = nullptr;
+  std::vector<cudaEvent_t> ev;
+  size_t next = 0;
+  cudaEvent_t event() {                       // round-robin over a small pool (re-recording an event
+    if (ev.size() < 16) {                     // whose earlier waits are already enqueued is fine)
+      cudaEvent_t e;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      ev.push_back(e);
+      return e;
+    }
+    return ev[next++ % ev.size()];
+  }
+};
+static std::mutex g_side_mu;
+static SideStream g_side[64];
+
+int side_fork(cudaStream_t st, cudaStream_t* side_out) {
+  int dev = 0;
+  MCLST_CUDA(cudaGetDevice(&dev));
+  MCLST_REQUIRE(dev >= 0 && dev < 64, MCLST_ERR_DEVICE, "side stream: device ordinal %d", dev);
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  SideStream& s = g_side[dev];
+  if (!s.st) MCLST_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+  cudaEvent_t e = s.event();
+  MCLST_REQUIRE(e, MCLST_ERR_DEVICE, "side stream: event creation failed");
+  MCLST_CUDA(cudaEventRecord(e, st));
+  MCLST_CUDA(cudaStreamWaitEvent(s.st, e, 0));
+  *side_out = s.st;
+  return 0;
+}
+
+int side_join(cudaStream_t st) {
+  int dev = 0;
+  MCLST_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  SideStream& s = g_side[dev];
+  MCLST_REQUIRE(s.st, MCLST_ERR_INVALID, "side stream: join without fork");
+  cudaEvent_t e = s.event();
+  MCLST_REQUIRE(e, MCLST_ERR_DEVICE, "side stream: event creation failed");
+  MCLST_CUDA(cudaEventRecord(e, s.st));
+  MCLST_CUDA(cudaStreamWaitEvent(st, e, 0));
+  return 0;
+}
+
+// path counters of a blocked call: every block resets the four counters at the head of the
+// workspace (the exact-fallback list is indexed by one of them), so the totals are kept aside and
+// written back after the last block.  mode 0: clear totals, 1: totals += counters, 2: counters = totals
+__global__ void counters_fold_kernel(int* counters, int* totals, int mode) {
+  const int i = threadIdx.x;
+  if (i >= 4) return;
+  if (mode == 0) totals[i] = 0;
+  else if (mode == 1) totals[i] += counters[i];
+  else counters[i] = totals[i];
+}
+
+// Measured at cfg4 (65 536 queries): blocks of one lane round gain nothing -- the persistent
+// candidate kernel owns the whole register file of every SM (10 warps are allocated as 12 x 168
+// registers), so the average of a block cannot run beside it and only moves to the gaps, while four
+// seed passes instead of one cost 0.4 ms (33.5 vs 33.1 ms per step).  Blocking therefore only bounds
+// the workspace of very large query sets (candidate buffers: 8 KiB per query).
+static int64_t retrieve_block_rows(int64_t n_query) {
+  const int64_t round = 128ll * sm_count();
+  return n_query > 8 * round ? 4 * round : n_query;
+}
+}  // namespace mclst
+
+extern "C" int mclst_retrieve_workspace_bytes(int64_t n_bank, int64_t n_query, int dim, int top_k, int flags,
+                                              size_t* bytes) {
+  MCLST_REQUIRE(bytes, MCLST_ERR_INVALID, "retrieve_workspace_bytes: null pointer");
+  MCLST_REQUIRE(n_bank >= 0 && n_query >= 0 && dim >= 1 && top_k >= 1, MCLST_ERR_INVALID,
+                "retrieve_workspace_bytes: bad shape");
+  const size_t fm = carve_fm(nullptr, 0, n_bank, retrieve_block_rows(n_query), dim, top_k, flags).bytes;
+  *bytes = align_up(fm, 256) + align_up((size_t)n_query * top_k * sizeof(float), 256) + 256 /*counter totals*/;
+  return 0;
+}
+
+extern "C" int mclst_weighted_average(const float* spot_key, int64_t n_bank, int64_t ld_key,
+                                      const void* expression_key, int64_t ld_expr, int genes,
+                                      int expr_is_f64, const float* image_query, int64_t n_query,
+                                      int64_t ld_query, int dim, const int64_t* indices,
+                                      const float* values, const float* distances, int top_k,
+                                      int64_t index_offset, int weight_mode, void* out_emb,
+                                      void* out_expr, int out_is_f64, mclst_stream_t stream);
+
+extern "C" int mclst_retrieve(const float* bank, int64_t n_bank, int64_t ld_bank, const void* expression_key,
+                              int64_t ld_expr, int genes, int expr_is_f64, const float* query,
+                              int64_t n_query, int64_t ld_query, int dim, int top_k, int weight_mode,
+                              int64_t* out_indices, float* out_values, void* out_emb, void* out_expr,
+                              int out_is_f64, void* workspace, size_t workspace_bytes, int flags,
+                              mclst_stream_t stream) {
+  MCLST_REQUIRE(bank && expression_key && workspace && out_indices && out_expr && (query || n_query == 0),
+                MCLST_ERR_INVALID, "retrieve: null pointer");
+  MCLST_REQUIRE(weight_mode >= 0 && weight_mode <= MCLST_W_BLEEP_EXP, MCLST_ERR_INVALID,
+                "retrieve: bad weight mode %d", weight_mode);
+  MCLST_REQUIRE(weight_mode != MCLST_W_SIMILARITY || out_values, MCLST_ERR_INVALID,
+                "retrieve: similarity weights need out_values");
+  if (n_query == 0) return 0;
+  size_t need = 0;
+  int rc = mclst_retrieve_workspace_bytes(n_bank, n_query, dim, top_k, flags, &need);
+  if (rc) return rc;
+  MCLST_REQUIRE(need <= workspace_bytes, MCLST_ERR_WORKSPACE, "retrieve: workspace %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t QB = retrieve_block_rows(n_query);
+  const size_t fm_bytes = align_up(carve_fm(nullptr, 0, n_bank, QB, dim, top_k, flags).bytes, 256);
+  const bool need_dist = weight_mode == MCLST_W_INV_SQ_L1 || weight_mode == MCLST_W_INV_SQ_L2 ||
+                         weight_mode == MCLST_W_BLEEP_EXP;
+  float* dist = need_dist ? reinterpret_cast<float*>(static_cast<char*>(workspace) + fm_bytes) : nullptr;
+  const int dist_p = weight_mode == MCLST_W_INV_SQ_L1 ? 1 : 2;
+  int* counters = static_cast<int*>(workspace);
+  int* totals = reinterpret_cast<int*>(static_cast<char*>(workspace) + fm_bytes +
+                                       align_up((size_t)n_query * top_k * sizeof(float), 256));
+  const size_t esz = expr_is_f64 ? 8 : 4, osz = out_is_f64 ? 8 : 4;
+  (void)esz;
+  const bool overlap = QB < n_query;
+  if (overlap) counters_fold_kernel<<<1, 32, 0, st>>>(counters, totals, 0);
+  for (int64_t q0 = 0, b = 0; q0 < n_query; q0 += QB, ++b) {
+    const int64_t nq = std::min(QB, n_query - q0);
+    // the bank is packed by the first block; later blocks find its image at the head of the workspace
+    const int f = flags | (b > 0 ? MCLST_FM_BANK_PACKED : 0);
+    const bool tc = tc_eligible(n_bank, nq, dim, top_k, f);
+    rc = find_matches_stages(7, bank, n_bank, ld_bank, query + q0 * ld_query, nq, ld_query, dim, top_k, 0,
+                             out_indices + q0 * top_k, out_values ? out_values + q0 * top_k : nullptr,
+                             dist ? dist + q0 * top_k : nullptr, dist_p, nullptr, workspace, fm_bytes,
+                             tc ? f : (f & ~MCLST_FM_BANK_PACKED), st);
+    if (rc) return rc;
+    cudaStream_t as = st;
+    if (overlap) {
+      counters_fold_kernel<<<1, 32, 0, st>>>(counters, totals, 1);
+      if ((rc = side_fork(st, &as))) return rc;
+    }
+    rc = mclst_weighted_average(bank, n_bank, ld_bank, expression_key, ld_expr, genes, expr_is_f64,
+                                query + q0 * ld_query, nq, ld_query, dim, out_indices + q0 * top_k,
+                                out_values ? out_values + q0 * top_k : nullptr, dist ? dist + q0 * top_k : nullptr,
+                                top_k, 0, weight_mode,
+                                out_emb ? static_cast<char*>(out_emb) + (size_t)q0 * dim * osz : nullptr,
+                                static_cast<char*>(out_expr) + (size_t)q0 * genes * osz, out_is_f64,
+                                (mclst_stream_t)as);
+    if (rc) return rc;
+  }
+  if (overlap) {                                         // join: `stream` continues after the last average
+    counters_fold_kernel<<<1, 32, 0, st>>>(counters, totals, 2);
+    MCLST_LAUNCH_CHECK();
+    if ((rc = side_join(st))) return rc;
+  }
+  return 0;
 }
 
 // Testing aid: the raw tensor-core similarities the candidate pass sees (fp16-rounded

@@ -43,6 +43,12 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();
+// One internal side stream per device for independent work inside a call: side_fork makes it wait
+// for everything enqueued on `st` so far and hands it out, side_join makes `st` wait for it.  Both
+// are plain event dependencies, so they also work inside a CUDA-graph capture of `st` (the side
+// work becomes a parallel branch of the graph).  Every fork must be joined before the call returns.
+int side_fork(cudaStream_t st, cudaStream_t* side);
+int side_join(cudaStream_t st);
 
 // Bump allocator over a caller-provided workspace.
 struct Arena {

@@ -555,6 +555,11 @@ static int compute_blocks(const LossPlan& L, int64_t i0, int64_t rows, float inv
   if (with_stats) { g.lse_part = L.part1; g.lse_ld = L.R; g.diag = L.diag + i0; g.diag_offset = i0; }
   if ((rc = launch_gemm_tn(g, st))) return rc;
   g.diag = nullptr;
+  // small batches: one product is a handful of tiles (B = 1024: 32 of 148 SMs), and the products are
+  // independent -- the last one goes on the side stream, next to the first
+  const bool side_ok = L.soft && !need_p2 && ceil_div(rows, 128) * ceil_div(L.B, 256) * 2 <= sm_count();
+  cudaStream_t s3 = st;
+  if (side_ok && (rc = side_fork(st, &s3))) return rc;
   if (need_p2) {
     g.a_hi = L.Ip.hi + a_off; g.a_lo = L.Ip.lo + a_off; g.b_hi = L.Sp.hi; g.b_lo = L.Sp.lo;
     g.c = L.P2;
@@ -567,8 +572,10 @@ static int compute_blocks(const LossPlan& L, int64_t i0, int64_t rows, float inv
     g.a_hi = L.ISp.hi + a2; g.a_lo = L.ISp.lo + a2; g.b_hi = L.ISp.hi; g.b_lo = L.ISp.lo;
     g.c = L.P3; g.alpha = a_scale;
     if (with_stats) g.lse_part = L.part3;
-    if ((rc = launch_gemm_tn(g, st))) return rc;
+    if ((rc = launch_gemm_tn(g, s3))) return rc;
+    if (side_ok) prof_mark(s3, "end");
   }
+  if (side_ok && (rc = side_join(st))) return rc;
   return 0;
 }
 
@@ -713,6 +720,11 @@ static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_em
       if (soft) { g.a_nkb1 = L.G1.nkb; g.a2_hi = L.Gs.hi; g.a2_lo = L.Gs.lo; }
       g.a_hi = L.G1.hi; g.a_lo = L.G1.lo; g.b_hi = L.XT_IS.hi; g.b_lo = L.XT_IS.lo;
       g.c = d_spot; g.ldc = ld_ds;
+      // dS and dI are independent and, for small batches, a few tiles each (B = 1024: 8 CTAs walking
+      // K = 2048 for 47 us): side by side on two streams
+      const bool pair = ceil_div(B, 128) * ceil_div(D, 256) * 2 <= sm_count();
+      cudaStream_t s2 = st;
+      if (pair && (rc = side_fork(st, &s2))) return rc;
       if ((rc = launch_gemm_tn(g, st))) return rc;
       if (L.G2.hi) {
         g.a_hi = L.G2.hi; g.a_lo = L.G2.lo;
@@ -722,7 +734,9 @@ static int loss_phase(const float* spot_emb, int64_t ld_s, const float* image_em
       }
       g.b_hi = L.XT_SI.hi; g.b_lo = L.XT_SI.lo;
       g.c = d_image; g.ldc = ld_di;
-      if ((rc = launch_gemm_tn(g, st))) return rc;
+      if ((rc = launch_gemm_tn(g, s2))) return rc;
+      if (pair) prof_mark(s2, "end");
+      if (pair && (rc = side_join(st))) return rc;
     } else if (d_spot) {
       for (int64_t b = 0; b < L.nblocks; ++b) {
         const int64_t i0 = row0 + b * L.R, nr = std::min<int64_t>(L.R, row0 + rows - i0);

@@ -25,7 +25,8 @@ ArrayLike = Union[np.ndarray, torch.Tensor]
 
 __all__ = ["find_matches", "find_matches_cscc", "find_matches_device", "fm_workspace", "fm_pack_bank", "fm_seed",
            "fm_candidates", "fm_main", "weighted_topk_average",
-           "weighted_topk_average_device", "retrieve", "retrieve_device", "last_counters", "to_host", "Bank"]
+           "weighted_topk_average_device", "retrieve", "retrieve_device", "retrieve_workspace", "last_counters",
+           "to_host", "Bank"]
 
 _last_ws: Optional[torch.Tensor] = None
 _side_streams: dict = {}
@@ -290,22 +291,54 @@ def weighted_topk_average(spot_key: ArrayLike, expression_key: ArrayLike, image_
     return emb_np, expr_np
 
 
+def _retrieve_call(spot_key, expression_key, image_query, top_k, mode, want_emb, out_dtype, flags, ws=None):
+    """mclst_retrieve: find_matches + neighbour distances + weighted average in one C call (query
+    blocks pipelined inside: the average of one block runs under the top-k pass of the next)."""
+    global _last_ws
+    require_cuda(spot_key, expression_key, image_query)
+    lib = load()
+    assert spot_key.dtype == torch.float32 and image_query.dtype == torch.float32
+    assert expression_key.dtype in (torch.float32, torch.float64)
+    assert out_dtype in (torch.float32, torch.float64)
+    assert spot_key.dim() == 2 and image_query.dim() == 2 and spot_key.shape[1] == image_query.shape[1]
+    assert spot_key.stride(1) == 1 and expression_key.stride(1) == 1 and image_query.stride(1) == 1
+    N, D = spot_key.shape
+    Q = image_query.shape[0]
+    G = expression_key.shape[1]
+    assert expression_key.shape[0] == N
+    dev = spot_key.device
+    idx = torch.empty((Q, top_k), dtype=torch.int64, device=dev)
+    val = torch.empty((Q, top_k), dtype=torch.float32, device=dev)
+    emb = torch.empty((Q, D), dtype=out_dtype, device=dev) if want_emb else None
+    expr = torch.empty((Q, G), dtype=out_dtype, device=dev)
+    if Q == 0:
+        return idx, val, emb, expr
+    if ws is None:
+        ws = retrieve_workspace(N, Q, D, top_k, dev, flags)
+    with torch.cuda.device(dev):
+        check(lib.mclst_retrieve(ptr(spot_key), N, spot_key.stride(0), ptr(expression_key),
+                                 expression_key.stride(0), G, int(expression_key.dtype == torch.float64),
+                                 ptr(image_query), Q, image_query.stride(0), D, top_k, WEIGHT_MODES[mode],
+                                 ptr(idx), ptr(val), ptr(emb), ptr(expr), int(out_dtype == torch.float64),
+                                 ptr(ws), ws.numel(), flags, stream_ptr()), "retrieve")
+    _last_ws = ws
+    return idx, val, emb, expr
+
+
+def retrieve_workspace(n_bank: int, n_query: int, dim: int, top_k: int, device, flags: int = 0) -> torch.Tensor:
+    nbytes = C.c_size_t()
+    check(load().mclst_retrieve_workspace_bytes(n_bank, n_query, dim, top_k, flags, C.byref(nbytes)),
+          "retrieve_workspace_bytes")
+    return torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=device)
+
+
 def retrieve_device(spot_key: torch.Tensor, expression_key: torch.Tensor, image_query: torch.Tensor,
                     top_k: int = 50, mode: str = "inv_sq_l2", want_emb: bool = False,
                     out_dtype=torch.float32, exact_only: bool = False):
     """find_matches + weighted average with everything resident on the device.
     Returns (indices int64 [Q,k], values f32 [Q,k], emb_pred | None, expr_pred [Q,G])."""
-    need_dist = mode in ("inv_sq_l1", "inv_sq_l2", "bleep_exp")
-    dst = None
-    if need_dist:
-        val, idx, dst = find_matches_device(spot_key, image_query, top_k, exact_only=exact_only,
-                                            dist_p=1 if mode == "inv_sq_l1" else 2)
-    else:
-        val, idx = find_matches_device(spot_key, image_query, top_k, exact_only=exact_only)
-    emb, expr = weighted_topk_average_device(spot_key, expression_key, image_query, idx, mode,
-                                             val if mode == "similarity" else None, want_emb,
-                                             out_dtype, distances=dst)
-    return idx, val, emb, expr
+    flags = _lib.FM_EXACT_ONLY if exact_only else _lib.FM_DEFAULT
+    return _retrieve_call(spot_key, expression_key, image_query, top_k, mode, want_emb, out_dtype, flags)
 
 
 def _to_dev(x: ArrayLike, device, dtypes=(torch.float32,)) -> torch.Tensor:
@@ -375,7 +408,10 @@ class Bank:
         ent = self._packed.get(top_k)
         if ent is None or ent[1] < n_query:
             cap = max(n_query, 1024)
-            ws = fm_workspace(len(self), cap, self.spot_key.shape[1], top_k, self.spot_key.device)
+            # (laid out for mclst_retrieve: the find_matches workspace first, so the staged entry
+            # points can use it as well)
+            ws = retrieve_workspace(len(self), cap, self.spot_key.shape[1], top_k, self.spot_key.device,
+                                    _lib.FM_BANK_PACKED)
             fm_pack_bank(self.spot_key, top_k, ws)
             ent = self._packed[top_k] = (ws, cap)
         return ent[0]
@@ -393,13 +429,13 @@ class Bank:
 
     def retrieve_device(self, image_query: torch.Tensor, top_k: int = 50, mode: str = "inv_sq_l2",
                         want_emb: bool = False, out_dtype=torch.float32):
-        need_dist = mode in ("inv_sq_l1", "inv_sq_l2", "bleep_exp")
-        r = self.find_matches(image_query, top_k, dist_p=(1 if mode == "inv_sq_l1" else 2) if need_dist else None)
-        val, idx, dst = (r[0], r[1], r[2]) if need_dist else (r[0], r[1], None)
-        emb, expr = weighted_topk_average_device(self.spot_key, self.expression_key, image_query, idx, mode,
-                                                 val if mode == "similarity" else None, want_emb, out_dtype,
-                                                 distances=dst)
-        return idx, val, emb, expr
+        N, D = self.spot_key.shape
+        if D <= 256 and top_k <= 896 and N >= top_k and image_query.shape[0] > 0:
+            ws = self._workspace(image_query.shape[0], top_k)
+            return _retrieve_call(self.spot_key, self.expression_key, image_query, top_k, mode, want_emb,
+                                  out_dtype, _lib.FM_BANK_PACKED, ws)
+        return _retrieve_call(self.spot_key, self.expression_key, image_query, top_k, mode, want_emb, out_dtype,
+                              _lib.FM_DEFAULT)
 
     def retrieve(self, image_query: ArrayLike, top_k: int = 50, p: int = 2, mode: Optional[str] = None,
                  want_emb: bool = True, out_dtype=torch.float64):

@@ -335,3 +335,38 @@ def test_resident_bank_equals_one_shot_retrieve():
         np.testing.assert_array_equal(ex, ex1)
         np.testing.assert_array_equal(emb, emb1)
     assert set(b._packed) == {50, 200}
+
+
+@pytest.mark.parametrize("mode,want_emb", [("inv_sq_l2", True), ("inv_sq_l1", False), ("similarity", False)])
+def test_blocked_retrieve_equals_unblocked(mode, want_emb):
+    """mclst_retrieve sends query sets beyond eight lane rounds (> 8 x 128 x SMs rows) through in
+    blocks of four, the average of one block on a side stream next to the top-k pass of the next: results must
+    be byte-identical to the same queries retrieved in unblocked pieces, the path counters must add
+    up over the blocks, and a second call on the same stream must not disturb the first."""
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    N, D, G, k = 2000, 256, 24, 50
+    Q = 8 * 128 * sms + 777                                      # blocks: four rounds, four rounds, 777 rows
+    bank = torch.tensor(synth.embeddings(N, D, 5101, "clustered")).cuda()
+    expr = torch.tensor(synth.expression(N, G, 5102)).cuda()
+    qry = torch.tensor(synth.embeddings(Q, D, 5103, "clustered")).cuda()
+    idx, val, emb, ex = retrieval.retrieve_device(bank, expr, qry, k, mode, want_emb=want_emb)
+    counters = retrieval.last_counters()
+    assert counters["tensor_core"] + counters["exact_fallback"] == Q, counters
+    again = retrieval.retrieve_device(bank, expr, qry, k, mode, want_emb=want_emb)   # right behind it
+    torch.cuda.synchronize()
+    cut = Q // 2 + 5                                             # both pieces below the blocking threshold
+    parts = [retrieval.retrieve_device(bank, expr, qry[a:b], k, mode, want_emb=want_emb)
+             for a, b in ((0, cut), (cut, Q))]
+    for i, got in enumerate((idx, val, emb, ex)):
+        if got is None:
+            continue
+        want = torch.cat([p[i] for p in parts])
+        assert torch.equal(got, want), i
+        assert torch.equal(again[i], want), i
+    rows = np.arange(0, Q, 997)
+    sval, sidx = oracle.find_matches_spec(bank.cpu().numpy(), qry.cpu().numpy()[rows], k)
+    np.testing.assert_array_equal(idx.cpu().numpy()[rows], sidx)
+    # resident bank: same blocks against the packed image kept in the workspace
+    res = retrieval.Bank(bank, expr)
+    r_idx, r_val, _, r_ex = res.retrieve_device(qry, k, mode)
+    assert torch.equal(r_idx, idx) and torch.equal(r_val, val) and torch.equal(r_ex, ex)
