@@ -80,13 +80,24 @@ pack_plain_block(const float* __restrict__ x, int64_t rows, int64_t cols, int64_
     // ones (max scan, then chunk by chunk) -- the pack of a training-step operand is pure latency
     float v[4][8];
     float amax = 0.f;
+    // 16-byte loads when the rows allow it: a lane's chunk is 32 contiguous bytes, and eight scalar
+    // loads per chunk made the pack (pure latency at these sizes) issue four times the instructions
+    const bool vec = (ld % 4 == 0) && (((uintptr_t)x & 15) == 0) && (x_batch % 4 == 0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = lane + 32 * j;
+      const int64_t k0 = (int64_t)c * 8;
+      if (vec && r < rows && k0 + 8 <= cols) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ld + k0));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(x + r * ld + k0) + 1);
+        v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w;
+        v[j][4] = b.x; v[j][5] = b.y; v[j][6] = b.z; v[j][7] = b.w;
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t k = (int64_t)c * 8 + i;
-        v[j][i] = (r < rows && k < cols) ? __ldg(x + r * ld + k) : 0.f;
+        for (int i = 0; i < 8; ++i) {
+          const int64_t k = k0 + i;
+          v[j][i] = (r < rows && k < cols) ? __ldg(x + r * ld + k) : 0.f;
+        }
       }
     }
 #pragma unroll

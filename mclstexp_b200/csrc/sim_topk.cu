@@ -1323,7 +1323,7 @@ struct RerankParams {
 
 // exact cosine of one bank row against the query held in qh[] (raw values as doubles):
 // fp64 dot of the raw fp32 rows / (fp64 norm product), rounded once to fp32.
-template <bool VEC>
+template <bool VEC, bool L1>
 __device__ __forceinline__ double row_dot(const float* __restrict__ sp, const double (&qh)[8],
                                           int dim, int lane, float* l1) {
   double acc = 0.0;
@@ -1341,7 +1341,7 @@ __device__ __forceinline__ double row_dot(const float* __restrict__ sp, const do
   }
 #pragma unroll
   for (int t = 0; t < 8; ++t) acc = fma((double)v[t], qh[t], acc);
-  if (l1) {
+  if (L1) {                        // (compile-time: predicated off it still cost 10 % of the kernel's issue slots)
     float s = 0.f;
 #pragma unroll
     for (int t = 0; t < 8; ++t) s += fabsf(v[t] - (float)qh[t]);
@@ -1353,7 +1353,7 @@ __device__ __forceinline__ double row_dot(const float* __restrict__ sp, const do
 #ifndef RR_MIN_BLOCKS
 #define RR_MIN_BLOCKS 4      // 5 (96 registers, 140 B of spills) measured equal: latency is hidden by the 4x unrolled loads
 #endif
-template <bool VEC>
+template <bool VEC, bool WANT_L1>
 __global__ void __launch_bounds__(128, RR_MIN_BLOCKS)
 rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
   extern __shared__ __align__(16) unsigned char rr_smem[];
@@ -1370,7 +1370,7 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
                                (size_t)warps_per_block * per_warp_entries) + (size_t)warps_per_block * RR_MAX) +
       (size_t)warp * RR_MAX;
   const bool want_dist = p.out_dist != nullptr;
-  const bool want_l1 = want_dist && p.dist_p == 1;
+  constexpr bool want_l1 = WANT_L1;          // (host: out_dist != nullptr && dist_p == 1)
   // ---- gather the streams' candidates
   bool bad = (p.bank_stats[1] | p.q_stats[1]) != 0;    // non-finite input: exact path decides
   int M = 0;
@@ -1382,8 +1382,16 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
   const float rs_max = __uint_as_float(p.bank_stats[0]);
   const float e2 = 2.02f * pair_eps(p.q_resid[q], rs_max);
   auto tighten = [&](int count) -> int {      // radix descent (24 bits) + in-place band compaction
-    uint32_t T = 0;
-    for (int bit = 31; bit >= 8; --bit) {
+    // the keys are cosines of one narrow range: their leading bits agree (typically 9-10 of them),
+    // and the descent starts below that common prefix instead of confirming it bit by bit
+    uint32_t k_and = 0xffffffffu, k_or = 0u;
+    for (int i = lane; i < count; i += 32) { const uint32_t kk = (uint32_t)(ent[i] >> 32); k_and &= kk; k_or |= kk; }
+    k_and = __reduce_and_sync(0xffffffffu, k_and);
+    k_or = __reduce_or_sync(0xffffffffu, k_or);
+    const uint32_t diff = (k_and ^ k_or) & 0xffffff00u;
+    const int top = diff ? 31 - __clz(diff) : 7;          // highest bit (>= 8) on which two keys differ
+    uint32_t T = (top < 31) ? (k_and & ~((2u << top) - 1u)) : 0u;
+    for (int bit = top; bit >= 8; --bit) {
       const uint32_t candT = T | (1u << bit);
       int c = 0;
       for (int i = lane; i < count; i += 32) c += ((uint32_t)(ent[i] >> 32) >= candT) ? 1 : 0;
@@ -1486,7 +1494,7 @@ rerank_kernel(const RerankParams p, int warps_per_block, int per_warp_entries) {
     for (int u = 0; u < 8; ++u) r[u] = (uint32_t)ent[min(i + u, n_s - 1)];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
-      acc[u] = row_dot<VEC>(p.bank + (int64_t)r[u] * p.ldb, qh, p.dim, lane, want_l1 ? &l1[u] : nullptr);
+      acc[u] = row_dot<VEC, WANT_L1>(p.bank + (int64_t)r[u] * p.ldb, qh, p.dim, lane, &l1[u]);
 #pragma unroll
     for (int u = 0; u < 8; ++u) acc[u] = warp_sum(acc[u]);
     if (want_l1) {
@@ -1888,15 +1896,22 @@ int launch_rerank(const TcWorkspace& w, const float* bank, int64_t n_bank, int64
   const size_t smem = (size_t)wpb * per_warp * 8 + (size_t)wpb * RR_MAX * 6;
   const bool vec = (dim == 256) && (ldb % 4 == 0) && (ldq % 4 == 0) && ((uintptr_t)bank % 16 == 0) &&
                    ((uintptr_t)query % 16 == 0);
-  static size_t attr[2] = {0, 0};
-  if (smem > attr[vec]) {
-    if (vec) MCLST_CUDA(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-    else MCLST_CUDA(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-    attr[vec] = smem;
-  }
+  const bool l1 = out_dist != nullptr && dist_p == 1;
   const unsigned grid = (unsigned)ceil_div(n_query, wpb);
-  if (vec) rerank_kernel<true><<<grid, 128, smem, st>>>(p, wpb, per_warp);
-  else rerank_kernel<false><<<grid, 128, smem, st>>>(p, wpb, per_warp);
+  auto launch = [&](auto kern, size_t& attr) -> int {
+    if (smem > attr) {
+      MCLST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)std::max<size_t>(smem, 48 * 1024)));
+      attr = smem;
+    }
+    kern<<<grid, 128, smem, st>>>(p, wpb, per_warp);
+    return 0;
+  };
+  static size_t attr[4] = {0, 0, 0, 0};
+  int rc;
+  if (vec) rc = l1 ? launch(rerank_kernel<true, true>, attr[3]) : launch(rerank_kernel<true, false>, attr[2]);
+  else rc = l1 ? launch(rerank_kernel<false, true>, attr[1]) : launch(rerank_kernel<false, false>, attr[0]);
+  if (rc) return rc;
   MCLST_LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,8 @@
+timeout 1200 python -m pytest tests/test_retrieval_gpu.py tests/test_simtopk_gpu.py tests/test_gemm_gpu.py tests/test_model_gpu.py -m gpu -q --tb=short -x 2>&1 | tail -4
+timeout 900 python bench.py --steps 5 --warmup 3 --no-extra --no-cpu-baseline --no-e2e > gpurun_out/r2_bench28_cfg4.json 2> gpurun_out/r2_bench28_cfg4.err; echo "cfg4 rc=$?"; tail -n 3 gpurun_out/r2_bench28_cfg4.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_bench28_cfg4.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['gpu_launches'], d['roofline']['kernels_ms_per_step'], d['roofline']['frac'], d['parity_check']['ok'], d['clocks'])
+PY
+DUMP=gpurun_out/tl_v6.txt timeout 300 python tools/cfg2_graph_timeline.py 2>&1 | tail -17 > gpurun_out/tl_v6.log; head -6 gpurun_out/tl_v6.log
