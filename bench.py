@@ -863,6 +863,7 @@ def main():
     ap.add_argument("--no-numa", action="store_true", help="N > 1: do not pin the rank to the CPUs next to its GPU")
     ap.add_argument("--loss-batch", type=int, default=32768, help="cfg5: batch the headline value is quoted on")
     ap.add_argument("--train-genes", type=int, default=1000, help="cfg2: spot_dim (1000 HVGs; 171 = real cSCC)")
+    ap.add_argument("--no-alt-grids", action="store_true", help="N > 1: skip timing the other decompositions")
     ap.add_argument("--queries", type=int, default=0, help="tuning: override the query count of the workload")
     ap.add_argument("--query-blocks", type=int, default=0, help="tuning: query blocks of the sharded pipeline")
     args = ap.parse_args()
@@ -1041,6 +1042,36 @@ def main():
                              "sampled from each rank's own query slice, against the full bank")
         torch.cuda.empty_cache()
 
+    # ---- the other decompositions of the same job (N > 1), on record next to the default one:
+    # pure bank sharding (1 x N: the north star's literal topology, every collective on the critical
+    # path) and pure query sharding (N x 1: bank replicated, no exchange at all)
+    other_grids = None
+    if world > 1 and not args.no_alt_grids:
+        other_grids = {}
+        for bs in sorted({1, world} - {grid.bank_shards}):
+            g2 = mdist.make_retrieval_grid(bs, world, rank)
+            b2, q2, e2 = make_inputs_device(cfg, 1234 + 4, dev, args.flavour)
+            sh2 = mdist.BankShard.from_full(b2, e2, g2.b_index, g2.bank_shards)
+            qa, qb = g2.query_slice(cfg["Q"])
+            qq = q2[qa:qb].contiguous()
+            del b2, e2, q2
+            torch.cuda.empty_cache()
+            for _ in range(3):
+                mdist.retrieve_sharded(sh2, qq, k, args.mode, group=g2.group, scatter_output=True)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(3):
+                mdist.retrieve_sharded(sh2, qq, k, args.mode, group=g2.group, scatter_output=True)
+            a1.record()
+            barrier()
+            t2 = torch.tensor([a0.elapsed_time(a1) / 3], device=dev)
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            other_grids[f"{g2.query_groups} query groups x {g2.bank_shards} bank shards"] = {
+                "ms_per_step": float(t2.item()), "value": cfg["Q"] / (float(t2.item()) * 1e-3), "unit": UNIT}
+            del sh2, qq
+            torch.cuda.empty_cache()
+
     # ---- end to end through the public host-array API: host (pinned) buffers in, host arrays
     # out, every H2D / D2H copy inside the timed region
     e2e = None
@@ -1128,7 +1159,7 @@ def main():
                 "data": "synthetic", "config": config,
                 "clocks": clk.summary(), "gpu_launches": int(launches), "e2e": e2e,
                 "roofline": roofline, "step_roofline": step_roof, "cpu_baseline": cpu_baseline,
-                "parity_check": parity, "path_counters": counters, "extra": extra}
+                "parity_check": parity, "path_counters": counters, "other_grids": other_grids, "extra": extra}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
