@@ -24,13 +24,17 @@
 // both operands are always K-major for the tensor core and one shared-memory descriptor type
 // serves all four storage combinations.
 //
-// What bounds it (tools/gemm_bench.py, ncu): ~0.6 us per K block = the latency of the one K block
-// of register loads each thread keeps in flight (24 KiB per SM); neither the stores, nor the proxy
-// fence, nor the MMA issue (ablated one by one) move it, a deeper register ring spills (168
-// registers per thread at 9 warps) and an inlined epilogue per ring slot overflowed the
-// instruction cache.  mclst_matmul therefore routes here only the shapes where the pack launch
-// costs more than that (gemm.cu: mclst_matmul); the next step is TMA tensor-map loads of the raw
-// tiles (no registers held across the latency) with the same in-place split.
+// What bounds it (clock64 stamps per K block from a -DTF_TIMING build, tools/tf32_timing.py,
+// profiles/r2_tf32_kblock_timing.log): ~1200 cycles per K block on the worker side, of which
+// 650-950 are the twelve 16-byte shared-memory stores per thread (48 KiB of hi / lo tiles per
+// K block at ~64 B/clk: every STS.128 of a warp is four wavefronts), 200 the load issue, 100 fence +
+// arrival; the MMA side needs 560 (issue) and waits for the workers.  Ablations agree: without the
+// fence, with a deeper register ring, with the issue moved to an elected lane of a uniform warp
+// (each worth 1-2 us of 30), nothing changes the slope, and 128 x 128 tiles are slower per CTA.
+// Converting inside the kernel costs 0.18 B of shared-memory stores per MAC because every CTA
+// re-converts its A block for its own 64 columns; the packed route converts every element once.
+// mclst_matmul therefore routes here only the shapes where the pack launch costs more than that
+// (gemm.cu: mclst_matmul).
 #include <algorithm>
 #include "common.cuh"
 #include "gemm.cuh"
@@ -38,6 +42,13 @@
 
 namespace mclst {
 using namespace ptx;
+
+#ifdef TF_TIMING
+__device__ long long g_tf_dbg[64 * 16];
+#define TF_STAMP(kb, slot) do { if (blockIdx.x == 0 && (kb) < 64) g_tf_dbg[(kb) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TF_STAMP(kb, slot) do {} while (0)
+#endif
 
 constexpr int TF_BM = 128, TF_BK = 32;              // tile width BN = 64 or 128: template parameter
 constexpr int TF_WORKERS = 256;                       // 8 warps: loaders/splitters, then the epilogue
@@ -253,7 +264,9 @@ gemm_tf32x3_kernel(const __grid_constant__ Tf32Params p) {
       // (the accumulator is free: the workers publish the first K block of a tile only after
       // they have drained the previous tile)
       for (int kb = 0; kb < nkb; ++kb) {
+        if (lane == 0) TF_STAMP(kb, 8);
         mbar_wait_fast(&bar_full[stage], phase);
+        if (lane == 0) TF_STAMP(kb, 9);
         tc_fence_after();
         const uint64_t sd = desc0 + (uint64_t)((stage * TF_STAGE_BYTES) >> 4);
         if (leader) {
@@ -269,6 +282,7 @@ gemm_tf32x3_kernel(const __grid_constant__ Tf32Params p) {
           mma_commit(&bar_empty[stage]);
         }
         __syncwarp();
+        if (lane == 0) TF_STAMP(kb, 10);
         if (++stage == TF_STAGES) { stage = 0; phase ^= 1; }
       }
       if (leader) mma_commit(bar_tfull);
@@ -291,14 +305,19 @@ gemm_tf32x3_kernel(const __grid_constant__ Tf32Params p) {
       if (kb < nkb_full) { la.template load<false>(kb, a); lb.template load<false>(kb, b); }
       else { la.template load<true>(kb, a); lb.template load<true>(kb, b); }
     };
-    auto publish = [&](const float (&a)[TF_A_CHUNKS][4], const float (&b)[TF_B_CHUNKS][4]) {
+    auto publish = [&](const float (&a)[TF_A_CHUNKS][4], const float (&b)[TF_B_CHUNKS][4], int kbs) {
+      if (threadIdx.x == 32) TF_STAMP(kbs, 1);
       mbar_wait_fast(&bar_empty[stage], phase ^ 1);
+      if (threadIdx.x == 32) TF_STAMP(kbs, 2);
       const uint32_t st = smem_base + stage * TF_STAGE_BYTES;
       la.store(st, st + TF_A_BYTES, a);
       lb.store(st + 2 * TF_A_BYTES, st + 2 * TF_A_BYTES + TF_B_BYTES, b);
+      if (threadIdx.x == 32) TF_STAMP(kbs, 3);
       fence_proxy_async_smem();                           // generic-proxy writes -> visible to the MMA
+      if (threadIdx.x == 32) TF_STAMP(kbs, 4);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[stage]);       // one arrival per warp
+      if (threadIdx.x == 32) TF_STAMP(kbs, 5);
       if (++stage == TF_STAGES) { stage = 0; phase ^= 1; }
     };
 #pragma unroll 1
@@ -310,11 +329,13 @@ gemm_tf32x3_kernel(const __grid_constant__ Tf32Params p) {
       load(0, va[0], vb[0]);
 #pragma unroll 1
       for (int kb = 0; kb < nkb; kb += 2) {
+        if (threadIdx.x == 32) TF_STAMP(kb, 0);
         if (kb + 1 < nkb) load(kb + 1, va[1], vb[1]);
-        publish(va[0], vb[0]);
+        publish(va[0], vb[0], kb);
         if (kb + 1 < nkb) {
+          if (threadIdx.x == 32) TF_STAMP(kb + 1, 0);
           if (kb + 2 < nkb) load(kb + 2, va[0], vb[0]);
-          publish(va[1], vb[1]);
+          publish(va[1], vb[1], kb + 1);
         }
       }
       mbar_wait_fast(bar_tfull, n_done & 1);
@@ -370,3 +391,9 @@ int launch_gemm_tf32x3(const float* A, int64_t lda, int a_trans, int64_t a_batch
 }
 
 }  // namespace mclst
+
+#ifdef TF_TIMING
+extern "C" int mclst_debug_tf32_timing(long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, mclst::g_tf_dbg, sizeof(long long) * (size_t)n);
+}
+#endif
