@@ -515,20 +515,22 @@ gemm_tn_kernel(const GemmParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(GM_BM, BN, false);
-      uint32_t stage = 0, phase = 0;
-      int n = 0;
-      for (int64_t g = g0; g < groups; g += gstep, ++n) {
-        const int buf = n & 1;
-        mbar_wait(&bar_tempty[buf], ((n >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
-        if (FUSE) {
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&bar_full[stage], phase);
-            tc_fence_after();
-            const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
+    // uniform control flow for the whole warp, one elected lane issues (umma.cuh: elect_one)
+    constexpr uint32_t idesc = make_idesc_f16(GM_BM, BN, false);
+    const uint32_t leader = elect_one();
+    uint32_t stage = 0, phase = 0;
+    int n = 0;
+    for (int64_t g = g0; g < groups; g += gstep, ++n) {
+      const int buf = n & 1;
+      mbar_wait(&bar_tempty[buf], ((n >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      if (FUSE) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bar_full[stage], phase);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
+          if (leader) {
             for (int seg = 0; seg < p.nseg; ++seg) {          // hi*hi, lo*hi, hi*lo from the same slices
               const uint32_t a_addr = base + (seg == 1 ? TP_SLICE_BYTES : 0);
               const uint32_t b_addr = base + 2 * TP_SLICE_BYTES + (seg == 2 ? TP_SLICE_BYTES : 0);
@@ -538,17 +540,21 @@ gemm_tn_kernel(const GemmParams p) {
                            idesc, (kb | seg | k4) != 0 ? 1u : 0u);
             }
             mma_commit(&bar_empty[stage]);
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
-          mma_commit(&bar_tfull[buf]);
-          continue;
+          __syncwarp();
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
-        for (int it = 0; it < iters; ++it) {
-          mbar_wait(&bar_full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * GM_STAGE_BYTES);
-          const uint32_t b_addr = a_addr + TP_SLICE_BYTES;
-          const int kb_it = it % nkb;
+        if (leader) mma_commit(&bar_tfull[buf]);
+        __syncwarp();
+        continue;
+      }
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&bar_full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * GM_STAGE_BYTES);
+        const uint32_t b_addr = a_addr + TP_SLICE_BYTES;
+        const int kb_it = it % nkb;
+        if (leader) {
           if (p.a1_mn > 0 && kb_it < p.a_nkb1) {
             // A read MN-major: 16 K' = two 8-row atoms (2 KiB) per instruction; the two 64-column
             // halves of the tile lie 8 KiB apart
@@ -558,16 +564,18 @@ gemm_tn_kernel(const GemmParams p) {
                          make_smem_desc_sw128(b_addr + k4 * 32), idesc_a_mn_major(idesc), (it | k4) != 0 ? 1u : 0u);
           } else {
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            mma_f16_ss(d_tmem, make_smem_desc_sw128(a_addr + k4 * 32),
-                       make_smem_desc_sw128(b_addr + k4 * 32), idesc, (it | k4) != 0 ? 1u : 0u);
+            for (int k4 = 0; k4 < 4; ++k4)
+              mma_f16_ss(d_tmem, make_smem_desc_sw128(a_addr + k4 * 32),
+                         make_smem_desc_sw128(b_addr + k4 * 32), idesc, (it | k4) != 0 ? 1u : 0u);
           }
           if (CL == 1) mma_commit(&bar_empty[stage]);
           else mma_commit_mcast(&bar_empty[stage], kMask);
-          if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
         }
-        mma_commit(&bar_tfull[buf]);
+        __syncwarp();
+        if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
       }
+      if (leader) mma_commit(&bar_tfull[buf]);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue

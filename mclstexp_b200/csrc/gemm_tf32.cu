@@ -88,12 +88,6 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
-__device__ __forceinline__ uint32_t elect_one() {     // 1 in exactly one lane of a converged warp
-  uint32_t r;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(r));
-  return r;
-}
-
 __device__ __noinline__ float gelu_erf_tf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }

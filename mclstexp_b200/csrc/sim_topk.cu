@@ -708,24 +708,27 @@ sim_topk_lanes_kernel(const SimParams p, const LanePlan L) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, ST_BN, false);
-      const uint32_t a_base = smem_u32(sA);
-      const uint32_t b_base = smem_u32(sB);
-      uint32_t stage = 0, phase = 0;
-      int it = 0;
-      LaneUnit u;
-      for (int j = 0; lane_unit(L, T, c, j, u); ++j) {
-        mbar_wait(bar_a, (uint32_t)j & 1u);
+    // the whole warp walks the loop (uniform control flow: descriptors in uniform registers), one
+    // elected lane issues -- umma.cuh: elect_one
+    constexpr uint32_t idesc = make_idesc_f16(128, ST_BN, false);
+    const uint32_t leader = elect_one();
+    const uint32_t a_base = smem_u32(sA);
+    const uint32_t b_base = smem_u32(sB);
+    uint32_t stage = 0, phase = 0;
+    int it = 0;
+    LaneUnit u;
+    for (int j = 0; lane_unit(L, T, c, j, u); ++j) {
+      mbar_wait(bar_a, (uint32_t)j & 1u);
+      tc_fence_after();
+      for (int t = u.t0; t < u.t1; ++t, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&bar_tempty[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        for (int t = u.t0; t < u.t1; ++t, ++it) {
-          const int buf = it & 1;
-          mbar_wait(&bar_tempty[buf], ((it >> 1) & 1) ^ 1);
+        const uint32_t d_tmem = tmem_base + buf * ST_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * ST_BN;
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&bar_full[stage], phase);
-            tc_fence_after();
+          if (leader) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               const uint64_t ad = make_smem_desc_sw128(a_base + kb * TP_SLICE_BYTES + k4 * 32);
@@ -733,12 +736,15 @@ sim_topk_lanes_kernel(const SimParams p, const LanePlan L) {
               mma_f16_ss(d_tmem, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
             }
             mma_commit(&bar_empty[stage]);
-            if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
           }
-          mma_commit(&bar_tfull[buf]);
+          __syncwarp();
+          if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
         }
-        mma_commit(bar_afree);
+        if (leader) mma_commit(&bar_tfull[buf]);
+        __syncwarp();
       }
+      if (leader) mma_commit(bar_afree);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue: threshold filter

@@ -109,6 +109,17 @@ __device__ __forceinline__ void cluster_sync_all() {     // every thread of ever
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// 1 in exactly one lane of a converged warp.  The MMA-issuing warps run their loops in uniform
+// control flow (all 32 lanes) and only issue under this predicate: with `if (lane == 0)` around the
+// whole loop the descriptor arithmetic is per-thread code with R2UR moves in front of every
+// tcgen05.mma (~100 cycles per instruction, measured), which outruns the tensor pipe for tiles of
+// 128 columns or fewer.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t r;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(r));
+  return r;
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
