@@ -1012,6 +1012,10 @@ def main():
                 traffic = tj["bytes_per_launch"].get(top)
         roofline = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
                     "frac": ach / peak, "traffic": traffic, "peak_source": peaks["source"],
+                    # the sustained figure is cuBLAS bf16 8192^3 back to back for 4 s; a kernel timed
+                    # inside a step may exceed it, so the burst figure is given as well
+                    **({"peak_kind": "bf16 sustained", "frac_of_burst_peak": ach / peaks["tf_burst"],
+                        "burst_peak": peaks["tf_burst"]} if bound == "tensor" else {}),
                     "kernel_ms": t_ms, "launches_per_step": len(per[top]) // args.steps,
                     "share_of_step": t_ms / ms,
                     "kernels_ms_per_step": share}
