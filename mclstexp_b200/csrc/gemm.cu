@@ -307,12 +307,12 @@ pack_pair_kernel(const PackJob a, const PackJob b) {
 }
 
 static PackJob make_pack_job(const float* x, int64_t rows, int64_t cols, int64_t ld, bool transpose,
-                             const PackedOperand& dst, int batch, int64_t x_batch_elems) {
+                             const PackedOperand& dst, int batch, int64_t x_batch_elems, int rows_per_block = 32) {
   PackJob j{};
   j.x = x; j.rows = rows; j.cols = cols; j.ld = ld; j.rows_pad = dst.rows_pad; j.x_batch = x_batch_elems;
   j.hi = dst.hi; j.lo = dst.lo; j.inv_scale = dst.inv_scale; j.out_batch = dst.bytes; j.nkb = dst.nkb;
   j.transpose = transpose ? 1 : 0;
-  j.blocks_x = (int)ceil_div(dst.rows_pad, 32);      // 32 rows (plain: one per warp) or 32 columns per block
+  j.blocks_x = (int)ceil_div(dst.rows_pad, rows_per_block);   // plain: one row per warp; transposed: 32 columns per block
   j.blocks = j.blocks_x * batch;
   return j;
 }
@@ -321,9 +321,13 @@ int launch_pack_pair(const float* A, int64_t a_rows, int64_t a_cols, int64_t lda
                      const PackedOperand& pa, int64_t a_batch_elems, const float* B, int64_t b_rows,
                      int64_t b_cols, int64_t ldb, bool b_trans, const PackedOperand& pb,
                      int64_t b_batch_elems, int batch, cudaStream_t st) {
-  const PackJob ja = make_pack_job(A, a_rows, a_cols, lda, a_trans, pa, batch, a_batch_elems);
-  const PackJob jb = make_pack_job(B, b_rows, b_cols, ldb, b_trans, pb, batch, b_batch_elems);
-  pack_pair_kernel<<<(unsigned)(ja.blocks + jb.blocks), 1024, 0, st>>>(ja, jb);
+  // two plain operands (every forward Linear): 8 rows per block instead of 32 -- 64 blocks of 1024
+  // threads left more than half of the SMs idle in a kernel that is one load-compute-store latency
+  // chain; the transposed pack needs its 32 warps (column maxima across 32 K groups)
+  const int threads = (!a_trans && !b_trans) ? 256 : 1024;
+  const PackJob ja = make_pack_job(A, a_rows, a_cols, lda, a_trans, pa, batch, a_batch_elems, threads / 32);
+  const PackJob jb = make_pack_job(B, b_rows, b_cols, ldb, b_trans, pb, batch, b_batch_elems, threads / 32);
+  pack_pair_kernel<<<(unsigned)(ja.blocks + jb.blocks), threads, 0, st>>>(ja, jb);
   MCLST_LAUNCH_CHECK();
   return 0;
 }
