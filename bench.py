@@ -1005,7 +1005,9 @@ def main():
         else:
             ach, peak, unit = work / t / 1e9, peaks["hbm"], "GB/s"
         traffic = None          # DRAM bytes per launch from the committed ncu capture of this workload
-        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        if not os.path.exists(tp):
+            tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
             if tj.get("workload") == args.workload and tj.get("n_gpus") == world:
