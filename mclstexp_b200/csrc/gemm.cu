@@ -377,6 +377,12 @@ int launch_pack_split(const float* x, int64_t rows, int64_t cols, int64_t ld, bo
 }
 
 // ============================================================================ gemm_tn
+#ifdef GM_TIMING
+__device__ unsigned long long g_gm_dbg[16];
+#define GM_STAMP(slot) do { if (blockIdx.x == 0) g_gm_dbg[slot] = ptx::globaltimer(); } while (0)
+#else
+#define GM_STAMP(slot) do {} while (0)
+#endif
 constexpr int GM_EPI_WARPS = 8;                              // two per TMEM lane quadrant, 4 column chunks each
 constexpr int GM_THREADS = 64 + 32 * GM_EPI_WARPS;
 constexpr int GM_BM = 128, GM_BN = 256;
@@ -432,6 +438,7 @@ gemm_tn_kernel(const GemmParams p) {
   const int64_t g0 = blockIdx.x / CL, gstep = gridDim.x / CL;
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
+  if (threadIdx.x == 0) GM_STAMP(0);
   if (threadIdx.x == 0) {
     for (int i = 0; i < GM_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], GM_EPI_WARPS); }
@@ -443,6 +450,7 @@ gemm_tn_kernel(const GemmParams p) {
   if (CL > 1) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) GM_STAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -532,6 +540,7 @@ gemm_tn_kernel(const GemmParams p) {
       if (FUSE) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bar_full[stage], phase);
+          if (lane == 0 && kb == 0) GM_STAMP(2);
           tc_fence_after();
           const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
           if (leader) {
@@ -550,6 +559,7 @@ gemm_tn_kernel(const GemmParams p) {
         }
         if (leader) mma_commit(&bar_tfull[buf]);
         __syncwarp();
+        if (lane == 0) GM_STAMP(3);
         continue;
       }
       for (int it = 0; it < iters; ++it) {
@@ -611,10 +621,26 @@ gemm_tn_kernel(const GemmParams p) {
 #pragma unroll
       for (int it = 0; it < 8; ++it)
         rs[it] = alpha * ((p.a_scale && mb < mt) ? __ldg(p.a_scale + (size_t)z * p.a_scale_batch + m0 + it * 4 + sub) : 1.f);
+      // bias and per-column operand factors of this warp's chunks: fetched BEFORE the accumulator
+      // is waited for (inside the chunk loop each of them was an exposed L2 round trip: the epilogue
+      // of a 128 x 128 tile took 3.0 us of a 13.8 us kernel -- globaltimer stamps, tools/gemm_timing.py)
+      constexpr int NC = BN / 64;
+      const int64_t n0 = (int64_t)nb * BN;
+      float pbias[NC][4], pcs[NC][4];
+#pragma unroll
+      for (int u = 0; u < NC; ++u) {
+        const int64_t col = n0 + (chalf * NC + u) * 32 + c4 * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          pbias[u][i] = (p.bias && col + i < p.N) ? __ldg(p.bias + col + i) : 0.f;
+          // (b_scale is padded to the tile width: always in bounds)
+          pcs[u][i] = p.b_scale ? __ldg(p.b_scale + (size_t)z * p.b_scale_batch + col + i) : 1.f;
+        }
+      }
       mbar_wait(&bar_tfull[buf], (n >> 1) & 1);
+      if (threadIdx.x == 64) GM_STAMP(4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
-      const int64_t n0 = (int64_t)nb * BN;
       // fused row log-sum-exp (loss products): running (max, sum exp) of MY row (TMEM lane) over
       // the 128 columns this warp drains, written as one partial per (row, tile column, half)
       float lm = -INFINITY, ls = 0.f;
@@ -625,6 +651,7 @@ gemm_tn_kernel(const GemmParams p) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
+        if (threadIdx.x == 64 && c == chalf * (BN / 64)) GM_STAMP(8);
         if (p.lse_part) {
           // 6 instructions per element: scale + max, then subtract + scale + ex2 + add.  The running
           // maximum is taken on the scaled values themselves (exact), so the exponent arguments are
@@ -665,16 +692,19 @@ gemm_tn_kernel(const GemmParams p) {
               make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         __syncwarp();
+        if (threadIdx.x == 64 && c == chalf * (BN / 64)) GM_STAMP(9);
         const int64_t col = n0 + c * 32 + c4 * 4;
         const bool full4 = vec_ok && col + 4 <= p.N;
-        float bias[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {1.f, 1.f, 1.f, 1.f};
-        if (p.bias) {
+        float bias[4], cs[4];
+        const int cc = c - chalf * NC;                     // (selects with compile-time indices: registers)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) if (col + i < p.N) bias[i] = __ldg(p.bias + col + i);
-        }
-        if (p.b_scale) {                                   // (padded to 256 rows: always in bounds)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) cs[i] = __ldg(p.b_scale + (size_t)z * p.b_scale_batch + col + i);
+        for (int i = 0; i < 4; ++i) {
+          float bv = pbias[0][i], cv = pcs[0][i];
+          if (NC > 1 && cc == 1) { bv = pbias[1 % NC][i]; cv = pcs[1 % NC][i]; }
+          if (NC > 2 && cc == 2) { bv = pbias[2 % NC][i]; cv = pcs[2 % NC][i]; }
+          if (NC > 3 && cc == 3) { bv = pbias[3 % NC][i]; cv = pcs[3 % NC][i]; }
+          bias[i] = bv;
+          cs[i] = cv;
         }
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
@@ -703,6 +733,7 @@ gemm_tn_kernel(const GemmParams p) {
               if (col + i < p.N) crow[i] = o[i] + (rbase ? rbase[m * p.ldc + col + i] : 0.f);
           }
         }
+        if (threadIdx.x == 64 && c == chalf * (BN / 64)) GM_STAMP(10);
         __syncwarp();
       }
       if (p.lse_part && mb < mt && my_row < p.M && n0 + chalf * 128 < p.N)
@@ -710,13 +741,16 @@ gemm_tn_kernel(const GemmParams p) {
       // accumulator drained: hand the buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
+      if (threadIdx.x == 64) GM_STAMP(5);
       if (lane == 0) mbar_arrive(&bar_tempty[buf]);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) GM_STAMP(6);
   if (CL > 1) cluster_sync_all();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (threadIdx.x == 32) GM_STAMP(7);
 }
 
 template <int CL, int BN>
@@ -792,6 +826,12 @@ PackedOperand take_operand(Arena& a, int64_t rows, int64_t k, bool is_b, bool sp
 }  // namespace mclst
 
 using namespace mclst;
+
+#ifdef GM_TIMING
+extern "C" int mclst_debug_gemm_timing(unsigned long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, mclst::g_gm_dbg, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
 
 // C-ABI: generic (batched) fp32 matmul through the split-precision tensor-core path -- the
 // building block behind every nn.Linear / einsum on the path and their backward passes.
