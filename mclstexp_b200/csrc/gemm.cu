@@ -410,14 +410,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
 template <int CL, int BN>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_tn_kernel(const GemmParams p) {
-  static_assert(BN == 256 || (BN == 128 && CL == 1), "tile widths: 256, or 128 without B sharing");
+  static_assert(BN == 256 || ((BN == 128 || BN == 64) && CL == 1), "tile widths: 256, or 128 / 64 without B sharing");
   constexpr int STAGE_TX = (1 + BN / 128) * TP_SLICE_BYTES;
   // The half-width kernel serves the small problems, and those are L2-bound, not tensor-bound: 96
   // CTAs re-streaming 32 KiB per 256 MMA cycles ask L2 for > 20 TB/s (CUPTI timeline of the graphed
   // training step: 26 us per product where the MMAs need 7).  It therefore loads the hi AND lo slice
   // of both operands ONCE per K block (64 KiB stage, 3 stages) and issues all three split products
   // from them, instead of streaming a 32 KiB stage per (segment, K block): a third less L2 traffic.
-  constexpr bool FUSE = BN == 128;
+  // BN = 64 (quarter width) once even 128-wide tiles leave half of the SMs idle: per tile the K loop
+  // is bound by the per-SM L2 -> shared-memory rate (116 GB/s: 8.9 us for 16 K blocks of 64 KiB) and
+  // the drain by the per-SM store rate (3.0 us for 64 KiB), so twice as many SMs with 48 / 32 KiB
+  // each finish sooner (globaltimer stamps, tools/gemm_timing.py).  The B half tile is the first or
+  // second 8 KiB of a TilePack slice (8 of its 16 swizzle atoms).
+  constexpr bool FUSE = BN <= 128;
+  constexpr int B_BYTES = (BN == 64) ? TP_SLICE_BYTES / 2 : TP_SLICE_BYTES;
   constexpr int NSTAGE = FUSE ? 3 : GM_STAGES;
   constexpr int STAGE_BYTES = FUSE ? 4 * TP_SLICE_BYTES : GM_STAGE_BYTES;
   static_assert(NSTAGE * STAGE_BYTES == GM_STAGES * GM_STAGE_BYTES, "same shared-memory footprint");
@@ -466,14 +472,16 @@ gemm_tn_kernel(const GemmParams p) {
         if (FUSE) {
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&bar_empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&bar_full[stage], (p.nseg == 3 ? 4 : 2) * TP_SLICE_BYTES);
+            mbar_arrive_expect_tx(&bar_full[stage], (p.nseg == 3 ? 2 : 1) * (TP_SLICE_BYTES + B_BYTES));
             uint8_t* dst = smem + stage * STAGE_BYTES;
-            const size_t ao = ((size_t)mb * nkb + kb) * TP_SLICE_BYTES, bo = ((size_t)nb * nkb + kb) * TP_SLICE_BYTES;
+            const size_t ao = ((size_t)mb * nkb + kb) * TP_SLICE_BYTES;
+            const size_t bo = (BN == 64) ? ((size_t)(nb >> 1) * nkb + kb) * TP_SLICE_BYTES + (size_t)(nb & 1) * B_BYTES
+                                         : ((size_t)nb * nkb + kb) * TP_SLICE_BYTES;
             bulk_g2s(dst, a_hi + ao, TP_SLICE_BYTES, &bar_full[stage]);
-            bulk_g2s(dst + 2 * TP_SLICE_BYTES, b_hi + bo, TP_SLICE_BYTES, &bar_full[stage]);
+            bulk_g2s(dst + 2 * TP_SLICE_BYTES, b_hi + bo, B_BYTES, &bar_full[stage]);
             if (p.nseg == 3) {
               bulk_g2s(dst + TP_SLICE_BYTES, a_lo + ao, TP_SLICE_BYTES, &bar_full[stage]);
-              bulk_g2s(dst + 3 * TP_SLICE_BYTES, b_lo + bo, TP_SLICE_BYTES, &bar_full[stage]);
+              bulk_g2s(dst + 3 * TP_SLICE_BYTES, b_lo + bo, B_BYTES, &bar_full[stage]);
             }
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
@@ -801,7 +809,9 @@ int launch_gemm_tn(const GemmParams& p, cudaStream_t st) {
   if (pair) return launch_gemm_cl<2, 256>(q, st);
   // under-filled grid: half-width tiles (the fused row statistics are laid out for 256-wide tiles)
   const bool narrow = !p.lse_part && p.a_nkb1 == 0 && tiles < (int64_t)sm_count();
-  return narrow ? launch_gemm_cl<1, 128>(q, st) : launch_gemm_cl<1, 256>(q, st);
+  if (!narrow) return launch_gemm_cl<1, 256>(q, st);
+  const int64_t tiles128 = ceil_div(p.M, GM_BM) * ceil_div(p.N, 128) * q.batch;
+  return 2 * tiles128 <= (int64_t)sm_count() ? launch_gemm_cl<1, 64>(q, st) : launch_gemm_cl<1, 128>(q, st);
 }
 
 // ---- operand bookkeeping --------------------------------------------------------------
