@@ -422,8 +422,11 @@ __global__ void counters_fold_kernel(int* counters, int* totals, int mode) {
 // Measured at cfg4 (65 536 queries): blocks of one lane round gain nothing -- the persistent
 // candidate kernel owns the whole register file of every SM (10 warps are allocated as 12 x 168
 // registers), so the average of a block cannot run beside it and only moves to the gaps, while four
-// seed passes instead of one cost 0.4 ms (33.5 vs 33.1 ms per step).  Blocking therefore only bounds
-// the workspace of very large query sets (candidate buffers: 8 KiB per query).
+// seed passes instead of one cost 0.4 ms (33.5 vs 33.1 ms per step).  With the candidate kernel capped
+// at 144 / 128 registers (__maxnreg__) the average does run underneath (1.8 ms of overlap measured),
+// but the cap costs the candidate pass 1.1 / 3.0 ms: 29.7 / 31.5 ms against 29.5 ms unblocked.
+// Blocking therefore only bounds the workspace of very large query sets (candidate buffers: 8 KiB
+// per query).
 static int64_t retrieve_block_rows(int64_t n_query) {
   const int64_t round = 128ll * sm_count();
   return n_query > 8 * round ? 4 * round : n_query;
