@@ -313,6 +313,9 @@ int mclst_embed_add_backward(const float* d_out, int64_t ld_d, const float* posi
 /* Same scatter-add WITHOUT the zero fill: the rows are added into whatever d_x_table / d_y_table
  * hold (gradient accumulation; or buffers the caller zero-filled earlier, off the critical path --
  * the fill of two [65536, genes] tables is 0.5 GB of writes that depend on nothing). */
+/* x[0..n) = 0 by a grid of only `ctas` blocks: a fill that runs in the background of other work on
+ * another stream instead of occupying every SM (x 16-byte aligned). */
+int mclst_zero_fill_background(float* x, int64_t n, int ctas, mclst_stream_t stream);
 int mclst_embed_add_backward_accumulate(const float* d_out, int64_t ld_d, const float* position,
                                         int64_t ld_p, int table_rows, int batch, int genes,
                                         float* d_x_table, float* d_y_table, mclst_stream_t stream);

@@ -75,6 +75,7 @@ def load() -> C.CDLL:
     lib.mclst_embed_add.argtypes = [p, i64, p, i64, p, p, i32, i32, i32, p, i64, p, p]
     lib.mclst_embed_add_backward.argtypes = [p, i64, p, i64, i32, i32, i32, p, p, p]
     lib.mclst_embed_add_backward_accumulate.argtypes = lib.mclst_embed_add_backward.argtypes
+    lib.mclst_zero_fill_background.argtypes = [p, i64, i32, p]
     lib.mclst_layernorm_forward.argtypes = [p, i64, p, p, i64, i32, f32, p, i64, p, p, p]
     lib.mclst_layernorm_backward.argtypes = [p, i64, p, i64, p, p, p, i64, i32, p, i64, p, p, p, sz, p]
     lib.mclst_gelu_forward.argtypes = [p, p, i64, p]

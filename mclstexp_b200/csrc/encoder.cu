@@ -283,6 +283,30 @@ extern "C" int mclst_embed_add_backward(const float* d_out, int64_t ld_d, const 
   return 0;
 }
 
+// Background zero fill with a BOUNDED grid.  The dense table gradients are 0.5 GB of zeros that
+// nothing waits for until the very end of the backward pass; a full-size fill kernel (torch.zeros)
+// launched early on a side stream took every CTA slot of the GPU for 2 x 37 us and the forward
+// chain queued behind it (CUPTI timeline: the first LayerNorm started 33 us late).  `ctas` blocks
+// trickle the stores out at ~30 GB/s each and leave the other SMs -- and the rest of their own --
+// to the step.
+__global__ void __launch_bounds__(256)
+zero_fill_kernel(float4* __restrict__ p, size_t n16, float* __restrict__ tail, int n_tail) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = z;
+  if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) tail[threadIdx.x] = 0.f;
+}
+
+extern "C" int mclst_zero_fill_background(float* x, int64_t n, int ctas, mclst_stream_t stream) {
+  MCLST_REQUIRE(x && n >= 0 && ctas >= 1, MCLST_ERR_INVALID, "zero_fill_background: bad args");
+  MCLST_REQUIRE(((uintptr_t)x & 15) == 0, MCLST_ERR_INVALID, "zero_fill_background: pointer not 16-byte aligned");
+  if (n == 0) return 0;
+  const size_t n16 = (size_t)n / 4;
+  zero_fill_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(x), n16,
+                                                                     x + n16 * 4, (int)((size_t)n - n16 * 4));
+  MCLST_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int mclst_embed_add_backward_accumulate(const float* d_out, int64_t ld_d, const float* position,
                                                    int64_t ld_p, int table_rows, int batch, int genes,
                                                    float* d_x_table, float* d_y_table,
